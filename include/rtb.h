@@ -1,0 +1,194 @@
+/* rtb.h — C ABI of librtb200.so, the B200-native replacement for the per-pixel render path of
+ * mpoboas/cosig-raytracing.
+ *
+ * The reference has no FFI: its render path is the C# class `RayTracer` (Assets/Services/RayTracer.cs:17) which drives a
+ * Unity compute shader (Assets/Shaders/BVHRayTracing.compute).  This header is the plugin interface a maintainer binds with
+ * P/Invoke ([DllImport("rtb200")]) in place of ComputeShader.Set / Dispatch / ReadPixels.  Each entry
+ * point cites the reference member it replaces.  Plain pointers and sizes only; no exceptions cross the boundary; every
+ * function returns an rtb_status (0 = OK).  A context is thread-compatible (one caller at a time, like the reference's
+ * main-thread-only RayTracer); calls are blocking unless stated otherwise.
+ *
+ * All paths in comments are relative to the reference repository root.
+ */
+#ifndef RTB_H
+#define RTB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_API_VERSION 1
+
+typedef struct rtb_context rtb_context; /* opaque: owns streams, device memory, peer mappings */
+
+typedef enum rtb_status {
+  RTB_OK = 0,
+  RTB_E_ARG = -1,       /* null / out-of-range argument */
+  RTB_E_CUDA = -2,      /* CUDA runtime failure (no device, OOM, launch error): rtb_last_error has the text */
+  RTB_E_NOSCENE = -3,   /* render before upload (reference: null shader -> null, RayTracer.cs:84-88) */
+  RTB_E_SIZE = -4,      /* output buffer too small */
+  RTB_E_CANCELLED = -5, /* cancel flag observed (reference: token.IsCancellationRequested, RayTracer.cs:283) */
+  RTB_E_IO = -6,        /* scene file missing/unreadable */
+  RTB_E_PARSE = -7      /* scene file malformed (reference would throw FormatException) */
+} rtb_status;
+
+/* TransformType, Assets/Models/ObjectData.cs:66-73 — same enumerator order. */
+typedef enum rtb_xform_type { RTB_XF_T = 0, RTB_XF_RX = 1, RTB_XF_RY = 2, RTB_XF_RZ = 3, RTB_XF_S = 4 } rtb_xform_type;
+
+/* TransformElement, ObjectData.cs:80-90.  x,y,z used by T and S; angle_deg by Rx/Ry/Rz. */
+typedef struct rtb_xform_elem { int32_t type; float x, y, z; float angle_deg; } rtb_xform_elem;
+
+/* MaterialDescription, ObjectData.cs:157-176 == GPUMaterial (32 B), RayTracer.cs:442-450. */
+typedef struct rtb_material { float r, g, b; float ka, kd, ks, kr, ior; } rtb_material;
+
+/* Triangle, ObjectData.cs:196-215. */
+typedef struct rtb_triangle { int32_t material; float v0[3], v1[3], v2[3]; } rtb_triangle;
+
+/* TrianglesMesh, ObjectData.cs:183-190: a range of `triangles` sharing one transformation. */
+typedef struct rtb_mesh { int32_t xform; int32_t reserved; int64_t first_tri; int64_t n_tris; } rtb_mesh;
+
+/* SphereDescription / BoxDescription, ObjectData.cs:221-241. */
+typedef struct rtb_prim { int32_t xform; int32_t material; } rtb_prim;
+
+/* ObjectData, ObjectData.cs:9-34.  The library copies everything it needs during rtb_upload_scene; the caller keeps
+ * ownership of all pointed-to memory. */
+typedef struct rtb_scene_desc {
+  int32_t has_image; int32_t image_w, image_h; float bg[3];                /* ImageSettings  :40-50  */
+  int32_t has_camera; int32_t cam_xform; float cam_distance, cam_vfov_deg; /* CameraSettings :128-138 */
+  int32_t n_xforms;                    /* CompositeTransformation list as CSR: elements of transform i are   */
+  const int32_t* xform_offsets;        /*   xform_elems[xform_offsets[i] .. xform_offsets[i+1])  (n_xforms+1) */
+  const rtb_xform_elem* xform_elems;
+  int32_t n_lights; const int32_t* light_xforms; const float* light_rgb;   /* LightSource :144-151 (rgb: 3 per light) */
+  int32_t n_materials; const rtb_material* materials;
+  int32_t n_meshes; const rtb_mesh* meshes;
+  int64_t n_triangles; const rtb_triangle* triangles;
+  int32_t n_spheres; const rtb_prim* spheres;
+  int32_t n_boxes; const rtb_prim* boxes;
+} rtb_scene_desc;
+
+/* How geometry is intersected. */
+enum { RTB_PRIM_TESSELLATED = 0, /* reference behaviour: spheres -> 768 tris, boxes -> 12 tris (SceneGeometryConverter.cs) */
+       RTB_PRIM_ANALYTIC = 1 };  /* unit-sphere quadratic / unit-box slabs (semantics of Services/BVH/HittableObjects.cs)   */
+/* Which acceleration structure is traversed. */
+enum { RTB_BVH_REFERENCE = 0,    /* host median-split build identical to BVHBuilder.cs, reference traversal order: ids bit-exact */
+       RTB_BVH_LBVH = 1 };       /* Morton-code LBVH built on the GPU, ordered traversal (tie winners may differ)               */
+/* Output addressing for the device-pointer entry point. */
+enum { RTB_OUT_FRAME = 0,        /* dst is a full W*H frame; only this rank's rows are written (peer-store gather)    */
+       RTB_OUT_COMPACT = 1 };    /* dst holds this rank's bands packed in local row order (NCCL gather staging)       */
+
+/* RenderSettings, Assets/Models/RenderSettings.cs:7-70 (nullable -> has_*), plus the knobs this library adds. */
+typedef struct rtb_render_params {
+  int32_t has_resolution, width, height;          /* ResolutionOverride       */
+  int32_t has_bg; float bg[3];                    /* BackgroundColorOverride  */
+  float light_intensity;                          /* LightIntensityScale      */
+  int32_t has_cam_pos; float cam_pos[3];          /* CameraPositionOverride   */
+  int32_t has_cam_rot; float cam_rot_euler_deg[3];/* CameraRotationOverride   */
+  int32_t has_fov; float fov_deg;                 /* CameraFovOverride        */
+  int32_t max_depth;                              /* MaxDepth                 */
+  int32_t enable_ambient, enable_diffuse, enable_specular, enable_refraction;
+  int32_t is_orthographic;
+  int32_t aa_samples;
+  int32_t soft_shadows; float light_size;
+  int32_t glossy; float roughness;
+  int32_t motion_blur; float shutter_speed;
+  /* --- additions (all zero = reference behaviour) --- */
+  int32_t debug_mode;        /* _DebugMode 0..3, BVHRayTracing.compute:484-508; the reference host always passes 0 */
+  int32_t srgb_encode;       /* 0: byte = floor(saturate(c)*255+0.5) */
+  int32_t band_rank, band_world, band_rows; /* process-per-GPU tile sharding: bands of band_rows rows, band b -> rank b % world.
+                                               band_world <= 1 means the whole frame.  band_rows 0 -> 32.               */
+  int32_t out_layout;        /* RTB_OUT_*; only used by rtb_render_device */
+  int32_t reserved[6];
+} rtb_render_params;
+
+/* Counters of the last render call on this context (rays are TraverseBVH-equivalent queries). */
+typedef struct rtb_stats {
+  int64_t rays_primary, rays_continuation, rays_shadow;
+  int64_t paths_hit_primary;
+  int64_t n_triangles, n_nodes;
+  int32_t width, height, spp, chunks;
+  int32_t kernel_launches;        /* launches of this library's kernels in the last render */
+  int32_t n_devices;
+  float ms_upload, ms_build;      /* last rtb_upload_scene: host prep + H2D, device build (flatten + BVH) */
+  float ms_render_device;         /* last render: first launch -> last kernel, CUDA events, max over devices */
+  float ms_trace, ms_shadow, ms_resolve; /* per kernel family, summed over depths/chunks on device 0 (only when profiling enabled) */
+  int64_t h2d_bytes, d2h_bytes;   /* bytes copied across PCIe by the last render call */
+  int64_t reserved[4];
+} rtb_stats;
+
+/* new RayTracer() + SetComputeShader, RayTracer.cs:17-32.  device_ids == NULL -> {0}.  With n_devices > 1 the frame is
+ * sharded by row bands over the devices of this process and gathered on device_ids[0] by peer stores over NVLink. */
+int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices);
+
+/* ReleaseBuffers + destruction, RayTracer.cs:47-59. */
+void rtb_destroy(rtb_context* ctx);
+
+/* Fills `p` with the reference UI defaults (SceneBuilder.cs:335-343,401,439-445): depth 2, all lighting toggles on,
+ * intensity 1, AA 1, no overrides, tessellated primitives, reference BVH. */
+void rtb_params_default(rtb_render_params* p);
+
+/* RebuildBVH, RayTracer.cs:386-404 (ExtractTriangles + BVHBuilder.Build + SetData) and SetupMaterialBuffer :455-499.
+ * primitive_mode / bvh_mode are RTB_PRIM_* / RTB_BVH_*.  Geometry is flattened and (for LBVH) the hierarchy built on
+ * the device(s).  An empty scene is legal and renders the background. */
+int rtb_upload_scene(rtb_context* ctx, const rtb_scene_desc* scene, int32_t primitive_mode, int32_t bvh_mode);
+
+/* InvalidateBVHCache, RayTracer.cs:38-42: drops device geometry; the next render returns RTB_E_NOSCENE until re-upload. */
+int rtb_invalidate(rtb_context* ctx);
+
+/* ClearRenderTarget, RayTracer.cs:65-72: frees the cached frame/queue buffers (they are re-created on demand). */
+int rtb_clear_target(rtb_context* ctx);
+
+/* RenderAsync, RayTracer.cs:212-380 (blocking).  Writes width*height RGBA8 pixels, row 0 = bottom of the picture
+ * (Unity Texture2D convention), into caller memory (host; pinned memory from rtb_alloc_pinned avoids
+ * a staging copy).  `bytes` is the capacity of rgba8.  out_w/out_h (optional) receive the resolved resolution. */
+int rtb_render(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* out_w, int32_t* out_h);
+
+/* RenderToTexture, RayTracer.cs:82-202 (no readback): renders into device memory `dst_device` (on device_ids[0], or a
+ * peer-mapped pointer into another GPU's frame for the fused NVLink gather).  Asynchronous on the context's stream unless
+ * `sync` != 0.  Honors band_rank/band_world/out_layout. */
+int rtb_render_device(rtb_context* ctx, const rtb_render_params* p, void* dst_device, size_t bytes, int32_t sync);
+
+/* Primary-hit maps for parity checks (the reference exposes them only as debug views, BVHRayTracing.compute:484-508):
+ * per pixel (row 0 = bottom) the closest hit of the pixel-centre ray: prim_id = triangle index in ExtractTriangles
+ * emission order (-1 = miss), t, material index.  Any pointer may be NULL.  Host pointers. */
+int rtb_render_aux(rtb_context* ctx, const rtb_render_params* p, int32_t* prim_id, float* t, int32_t* material);
+
+/* Copies the flattened object-space triangle arrays back to the host for parity checks against the oracle:
+ * for triangle i in emission order: v0,v1,v2,n0,n1,n2 (18 floats) and material.  Either pointer may be NULL;
+ * n_out receives the triangle count. */
+int rtb_get_triangles(rtb_context* ctx, float* v_n_18, int32_t* material, int64_t capacity, int64_t* n_out);
+
+int rtb_get_stats(rtb_context* ctx, rtb_stats* out);
+int rtb_set_profiling(rtb_context* ctx, int32_t enable); /* per-kernel-family CUDA-event timing in rtb_stats */
+int rtb_set_cancel_flag(rtb_context* ctx, const volatile int32_t* flag); /* polled between wavefront depths */
+int rtb_synchronize(rtb_context* ctx);
+
+/* Context-owned UTF-8 text for the last failing call on this context (ctx may be NULL for rtb_create failures). */
+const char* rtb_last_error(rtb_context* ctx);
+
+/* Page-locked host memory for rgba8 outputs (C# side: wrap with NativeArray / LoadRawTextureData). */
+void* rtb_alloc_pinned(size_t bytes);
+void rtb_free_pinned(void* p);
+
+/* CUDA IPC plumbing for process-per-GPU hosts (bench.py under torchrun): export the context's device-0 frame buffer of
+ * `bytes` bytes (allocated on demand) as a 64-byte handle; open a peer's handle and get a device pointer usable as
+ * `dst_device`.  Opened pointers are closed by rtb_destroy. */
+int rtb_frame_export(rtb_context* ctx, size_t bytes, void** dev_ptr, uint8_t handle64[64]);
+int rtb_frame_import(rtb_context* ctx, const uint8_t handle64[64], void** dev_ptr);
+
+/* SceneService.LoadScene, Assets/Services/SceneService.cs:26-242: parses the COSIG scene text format.  The returned
+ * object owns its arrays; rtb_scene_get gives a desc view valid until rtb_scene_free. */
+typedef struct rtb_scene rtb_scene;
+int rtb_scene_load(const char* path, rtb_scene** out, char* err, size_t err_cap);
+int rtb_scene_parse(const char* text, size_t len, rtb_scene** out, char* err, size_t err_cap);
+const rtb_scene_desc* rtb_scene_get(const rtb_scene* s);
+void rtb_scene_free(rtb_scene* s);
+
+int rtb_api_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB_H */
