@@ -1,0 +1,791 @@
+// api.cu — the C ABI of librtb200.so (include/rtb.h): context, scene upload, the per-frame wavefront schedule, readback.
+//
+// This file is the B200-native counterpart of Assets/Services/RayTracer.cs: rtb_upload_scene = RebuildBVH (:386-404) +
+// SetupMaterialBuffer (:455-499); rtb_render = RenderAsync (:212-380); rtb_render_device = RenderToTexture (:82-202).
+// There is no CPU fallback: every entry point that computes needs a CUDA device and fails with RTB_E_CUDA otherwise.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "kernels.hpp"
+
+using namespace rtb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceScene {
+  float4 *raw = nullptr, *nrm = nullptr, *isect = nullptr, *shade = nullptr, *nodes = nullptr, *materials = nullptr;
+  int32_t* perm = nullptr;
+  int32_t n_tris = 0, n_nodes = 0, n_mats = 0, root = 0;
+  int bvh_mode = RTB_BVH_REFERENCE;
+  int node_floats = 8;
+};
+
+struct Queues {
+  float4* base = nullptr;      // one allocation: 11 arrays of capacity slots
+  int32_t* counters = nullptr;
+  unsigned long long* totals = nullptr;
+  int32_t capacity = 0, depth_cap = 0;
+};
+
+struct DeviceState {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_done = nullptr;
+  float* sphere_table = nullptr;
+  DeviceScene scene;
+  Queues q;
+  void* frame = nullptr;  // RGBA8 frame (device 0) — also the IPC-exported buffer
+  size_t frame_bytes = 0;
+  int32_t *aux_prim = nullptr, *aux_mat = nullptr;
+  float* aux_t = nullptr;
+  size_t aux_px = 0;
+  int grid_trace[2][2] = {{0, 0}, {0, 0}}, grid_shadow[2] = {0, 0};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_trace, prof_shadow, prof_resolve;
+  size_t prof_used[3] = {0, 0, 0};
+};
+
+}  // namespace
+
+struct rtb_context {
+  std::vector<DeviceState> devs;
+  HostScene host;       // description without the triangle array
+  bool has_scene = false;
+  int primitive_mode = 0, bvh_mode = 0;
+  std::string err;
+  rtb_stats stats{};
+  const volatile int32_t* cancel = nullptr;
+  bool profiling = false;
+  int64_t chunk_slots = 1 << 23;
+  std::vector<void*> ipc_opened;
+};
+
+struct rtb_scene {
+  HostScene h;
+};
+
+namespace {
+
+int fail(rtb_context* ctx, int code, const std::string& what) {
+  if (ctx) ctx->err = what; else g_create_error = what;
+  return code;
+}
+#define CK(ctx, call)                                                                                                  \
+  do {                                                                                                                 \
+    cudaError_t e__ = (call);                                                                                          \
+    if (e__ != cudaSuccess) {                                                                                          \
+      std::ostringstream os__;                                                                                         \
+      os__ << #call << " failed at " << __FILE__ << ":" << __LINE__ << ": " << cudaGetErrorString(e__);                \
+      return fail(ctx, RTB_E_CUDA, os__.str());                                                                        \
+    }                                                                                                                  \
+  } while (0)
+
+template <typename T>
+void dfree(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void free_scene(DeviceState& d) {
+  cudaSetDevice(d.device);
+  DeviceScene& s = d.scene;
+  dfree(s.raw); dfree(s.nrm); dfree(s.isect); dfree(s.shade); dfree(s.nodes); dfree(s.materials); dfree(s.perm);
+  s = DeviceScene();
+}
+
+void free_targets(DeviceState& d) {
+  cudaSetDevice(d.device);
+  dfree(d.q.base); dfree(d.q.counters); dfree(d.q.totals);
+  d.q = Queues();
+  dfree(d.frame); d.frame_bytes = 0;
+  dfree(d.aux_prim); dfree(d.aux_mat); dfree(d.aux_t); d.aux_px = 0;
+}
+
+int ensure_queues(rtb_context* ctx, DeviceState& d, int32_t capacity, int32_t depth_cap) {
+  if (d.q.capacity >= capacity && d.q.depth_cap >= depth_cap) return RTB_OK;
+  dfree(d.q.base); dfree(d.q.counters); dfree(d.q.totals);
+  d.q = Queues();
+  CK(ctx, cudaMalloc(&d.q.base, (size_t)capacity * 11 * sizeof(float4)));
+  CK(ctx, cudaMalloc(&d.q.counters, (size_t)depth_cap * 4 * sizeof(int32_t)));
+  CK(ctx, cudaMalloc(&d.q.totals, 8 * sizeof(unsigned long long)));
+  d.q.capacity = capacity;
+  d.q.depth_cap = depth_cap;
+  return RTB_OK;
+}
+
+QueueView queue_view(const Queues& q) {
+  QueueView v;
+  float4* p = q.base;
+  const size_t c = (size_t)q.capacity;
+  v.ray_o[0] = p; v.ray_o[1] = p + c; v.ray_d[0] = p + 2 * c; v.ray_d[1] = p + 3 * c; v.ray_att[0] = p + 4 * c; v.ray_att[1] = p + 5 * c;
+  v.sh_o = p + 6 * c; v.sh_d = p + 7 * c; v.sh_lit = p + 8 * c; v.sh_unlit = p + 9 * c;
+  v.accum = p + 10 * c;
+  v.counters = q.counters;
+  v.totals = q.totals;
+  v.depth_cap = q.depth_cap;
+  return v;
+}
+
+SceneView scene_view(const DeviceScene& s) {
+  SceneView v;
+  v.tri_isect = s.isect; v.tri_shade = s.shade; v.nodes = s.nodes; v.materials = s.materials;
+  v.n_tris = s.n_tris; v.n_nodes = s.n_nodes; v.n_mats = s.n_mats; v.root = s.root;
+  return v;
+}
+
+int ensure_frame(rtb_context* ctx, DeviceState& d, size_t bytes) {
+  if (d.frame_bytes >= bytes) return RTB_OK;
+  dfree(d.frame);
+  d.frame_bytes = 0;
+  CK(ctx, cudaMalloc(&d.frame, bytes));
+  d.frame_bytes = bytes;
+  return RTB_OK;
+}
+
+void prof_pair(DeviceState& d, int family, cudaEvent_t& a, cudaEvent_t& b) {
+  auto& pool = family == 0 ? d.prof_trace : (family == 1 ? d.prof_shadow : d.prof_resolve);
+  size_t& used = d.prof_used[family];
+  if (used == pool.size()) {
+    cudaEvent_t x, y;
+    cudaEventCreate(&x);
+    cudaEventCreate(&y);
+    pool.emplace_back(x, y);
+  }
+  a = pool[used].first;
+  b = pool[used].second;
+  used++;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Scene upload on one device
+// ---------------------------------------------------------------------------------------------------------------------
+int upload_on_device(rtb_context* ctx, DeviceState& d, const rtb_scene_desc& desc, const std::vector<FlattenObject>& objs, int32_t n_out,
+                     const std::vector<float>& mats, int bvh_mode, float& ms_build) {
+  CK(ctx, cudaSetDevice(d.device));
+  free_scene(d);
+  DeviceScene& s = d.scene;
+  s.bvh_mode = bvh_mode;
+  s.n_tris = n_out;
+  s.n_mats = (int32_t)(mats.size() / 8);
+  CK(ctx, cudaMalloc(&s.materials, mats.size() * sizeof(float)));
+  CK(ctx, cudaMemcpyAsync(s.materials, mats.data(), mats.size() * sizeof(float), cudaMemcpyHostToDevice, d.stream));
+  if (n_out == 0) { CK(ctx, cudaStreamSynchronize(d.stream)); return RTB_OK; }
+
+  float* tri_in = nullptr;
+  FlattenObject* dobjs = nullptr;
+  struct Guard { float*& a; FlattenObject*& b; ~Guard() { if (a) cudaFree(a); if (b) cudaFree(b); } } guard{tri_in, dobjs};
+  if (desc.n_triangles > 0) {
+    CK(ctx, cudaMalloc(&tri_in, (size_t)desc.n_triangles * sizeof(rtb_triangle)));
+    CK(ctx, cudaMemcpyAsync(tri_in, desc.triangles, (size_t)desc.n_triangles * sizeof(rtb_triangle), cudaMemcpyHostToDevice, d.stream));
+  }
+  CK(ctx, cudaMalloc(&dobjs, objs.size() * sizeof(FlattenObject)));
+  CK(ctx, cudaMemcpyAsync(dobjs, objs.data(), objs.size() * sizeof(FlattenObject), cudaMemcpyHostToDevice, d.stream));
+  const size_t tri_bytes = (size_t)n_out * 3 * sizeof(float4);
+  CK(ctx, cudaMalloc(&s.raw, tri_bytes));
+  CK(ctx, cudaMalloc(&s.nrm, tri_bytes));
+  CK(ctx, cudaMalloc(&s.isect, tri_bytes));
+  CK(ctx, cudaMalloc(&s.shade, tri_bytes));
+  CK(ctx, cudaMalloc(&s.perm, (size_t)n_out * sizeof(int32_t)));
+
+  CK(ctx, cudaEventRecord(d.ev_begin, d.stream));
+  launch_flatten(tri_in, dobjs, (int)objs.size(), d.sphere_table, n_out, s.raw, s.nrm, d.stream);
+  CK(ctx, cudaGetLastError());
+
+  if (bvh_mode == RTB_BVH_REFERENCE) {
+    // Parity mode: the reference's own tree shape (BVHBuilder.cs) decides tie winners, so it is rebuilt on the host from
+    // the device-flattened triangles and uploaded.
+    std::vector<float> raw_host((size_t)n_out * 12);
+    CK(ctx, cudaMemcpyAsync(raw_host.data(), s.raw, tri_bytes, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaStreamSynchronize(d.stream));
+    RefBvh bvh;
+    build_reference_bvh(raw_host.data(), n_out, bvh);
+    s.n_nodes = (int32_t)(bvh.nodes.size() / 8);
+    s.node_floats = 8;
+    CK(ctx, cudaMalloc(&s.nodes, bvh.nodes.size() * sizeof(float)));
+    CK(ctx, cudaMemcpyAsync(s.nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(float), cudaMemcpyHostToDevice, d.stream));
+    CK(ctx, cudaMemcpyAsync(s.perm, bvh.perm.data(), (size_t)n_out * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
+    launch_pack(s.raw, s.nrm, s.perm, n_out, s.isect, s.shade, d.stream);
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaEventRecord(d.ev_end, d.stream));
+    CK(ctx, cudaStreamSynchronize(d.stream));  // bvh vectors go out of scope
+  } else {
+    s.n_nodes = n_out > 1 ? n_out - 1 : 1;
+    s.node_floats = 16;
+    CK(ctx, cudaMalloc(&s.nodes, (size_t)s.n_nodes * 4 * sizeof(float4)));
+    CK(ctx, cudaMemsetAsync(s.nodes, 0, (size_t)s.n_nodes * 4 * sizeof(float4), d.stream));
+    LbvhBuffers b;
+    b.nodes = s.nodes;
+    b.perm = s.perm;
+    b.workspace_bytes = lbvh_workspace_bytes(n_out);
+    void* ws = nullptr;
+    int32_t* root_dev = nullptr;
+    CK(ctx, cudaMalloc(&ws, b.workspace_bytes));
+    if (cudaMalloc(&root_dev, sizeof(int32_t)) != cudaSuccess) { cudaFree(ws); return fail(ctx, RTB_E_CUDA, "cudaMalloc(root) failed"); }
+    b.workspace = ws;
+    b.root_out = root_dev;
+    cudaError_t e = lbvh_build(s.raw, n_out, b, d.stream);
+    if (e == cudaSuccess) { launch_pack(s.raw, s.nrm, s.perm, n_out, s.isect, s.shade, d.stream); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaEventRecord(d.ev_end, d.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&s.root, root_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    cudaFree(ws);
+    cudaFree(root_dev);
+    if (e != cudaSuccess) return fail(ctx, RTB_E_CUDA, std::string("LBVH build failed: ") + cudaGetErrorString(e));
+  }
+  CK(ctx, cudaEventElapsedTime(&ms_build, d.ev_begin, d.ev_end));
+  return RTB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One frame on one device: chunks of <= chunk_slots pixel-samples, each a fixed sequence of persistent kernels.
+// `dst` is a device pointer valid on d.device (local memory or a peer/IPC mapping).
+// ---------------------------------------------------------------------------------------------------------------------
+int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, void* dst, int& launches, int& chunks) {
+  CK(ctx, cudaSetDevice(d.device));
+  const int bvh = d.scene.bvh_mode;
+  const SceneView sv = scene_view(d.scene);
+  const int32_t local_rows = band_local_rows(f.height, f.band_rank, f.band_world, f.band_rows);
+  const int32_t tiles_x = (f.width + 7) / 8;
+  const int64_t slots_per_tile_row = (int64_t)tiles_x * 32 * f.spp;  // 4 pixel rows
+  int64_t tile_rows_per_chunk = ctx->chunk_slots / slots_per_tile_row;
+  if (tile_rows_per_chunk < 1) tile_rows_per_chunk = 1;
+  if (tile_rows_per_chunk * slots_per_tile_row > (int64_t)INT32_MAX - 64) return fail(ctx, RTB_E_ARG, "a 4-row strip of this frame exceeds 2^31 samples");
+  const int32_t rows_per_chunk = (int32_t)std::min<int64_t>(tile_rows_per_chunk * 4, ((int64_t)local_rows + 3) / 4 * 4);
+  const int32_t capacity = (int32_t)(((int64_t)rows_per_chunk / 4) * slots_per_tile_row);
+  const int32_t depth_cap = f.max_depth + 2;
+  if (local_rows > 0) {
+    const int rc = ensure_queues(ctx, d, capacity, depth_cap);
+    if (rc != RTB_OK) return rc;
+  }
+  if (!d.grid_trace[bvh][0]) {
+    d.grid_trace[bvh][0] = d.sm_count * trace_blocks_per_sm(bvh, false);
+    d.grid_trace[bvh][1] = d.sm_count * trace_blocks_per_sm(bvh, true);
+    d.grid_shadow[bvh] = d.sm_count * shadow_blocks_per_sm(bvh);
+  }
+  const QueueView qv = queue_view(d.q);
+  CK(ctx, cudaEventRecord(d.ev_begin, d.stream));
+  if (local_rows > 0) CK(ctx, cudaMemsetAsync(d.q.totals, 0, 8 * sizeof(unsigned long long), d.stream));
+  d.prof_used[0] = d.prof_used[1] = d.prof_used[2] = 0;
+  auto timed = [&](int family, auto&& launch) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (ctx->profiling) { prof_pair(d, family, a, b); cudaEventRecord(a, d.stream); }
+    launch();
+    if (ctx->profiling) cudaEventRecord(b, d.stream);
+    launches++;
+  };
+  for (int32_t row0 = 0; row0 < local_rows; row0 += rows_per_chunk) {
+    if (ctx->cancel && *ctx->cancel) { cudaStreamSynchronize(d.stream); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
+    ChunkView c;
+    c.row0 = row0;
+    c.rows = std::min(rows_per_chunk, local_rows - row0);
+    c.tiles_x = tiles_x;
+    c.n_slots = (int32_t)((int64_t)((c.rows + 3) / 4) * slots_per_tile_row);
+    chunks++;
+    const int resolve_grid = std::min(d.sm_count * 8, (c.rows * f.width + 255) / 256);
+    if (f.debug != 0) {
+      timed(2, [&] { launch_debug(bvh, f, sv, c, dst, resolve_grid, d.stream); });
+      continue;
+    }
+    if (f.max_depth <= 0) {  // the depth loop never runs: sampleColor stays 0
+      CK(ctx, cudaMemsetAsync(qv.accum, 0, (size_t)c.n_slots * sizeof(float4), d.stream));
+    } else {
+      CK(ctx, cudaMemsetAsync(d.q.counters, 0, (size_t)depth_cap * 4 * sizeof(int32_t), d.stream));
+      for (int depth = 0; depth < f.max_depth; depth++) {
+        if (depth > 0 && ctx->cancel && *ctx->cancel) { cudaStreamSynchronize(d.stream); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
+        timed(0, [&] { launch_trace_shade(bvh, depth == 0, f, sv, qv, c, depth, d.grid_trace[bvh][depth == 0], d.stream); });
+        if (f.en_diffuse == 1) timed(1, [&] { launch_shadow(bvh, f, sv, qv, depth, d.grid_shadow[bvh], d.stream); });
+      }
+    }
+    timed(2, [&] { launch_resolve(f, qv, c, dst, resolve_grid, d.stream); });
+  }
+  CK(ctx, cudaGetLastError());
+  CK(ctx, cudaEventRecord(d.ev_end, d.stream));
+  return RTB_OK;
+}
+
+float sum_pairs(std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& pool, size_t used) {
+  float total = 0.0f;
+  for (size_t i = 0; i < used; i++) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, pool[i].first, pool[i].second) == cudaSuccess) total += ms;
+  }
+  return total;
+}
+
+// Renders the frame over the context's devices into `dst` (memory of device 0, or a peer mapping) and waits.
+int render_frame(rtb_context* ctx, const rtb_render_params* p, void* dst, size_t dst_bytes, bool to_internal_frame, bool sync, FrameParams& f_out) {
+  if (!ctx || !p) return fail(ctx, RTB_E_ARG, "null argument");
+  if (!ctx->has_scene) return fail(ctx, RTB_E_NOSCENE, "no scene uploaded (rtb_upload_scene)");
+  FrameParams f;
+  std::string why;
+  if (!resolve_frame(ctx->host.d, *p, f, why)) return fail(ctx, RTB_E_ARG, why);
+  const int n_dev = (int)ctx->devs.size();
+  if (n_dev > 1 && f.band_world > 1) return fail(ctx, RTB_E_ARG, "band sharding across processes needs a single-device context");
+  f_out = f;
+  if (to_internal_frame) {
+    const size_t need = (size_t)f.width * f.height * 4;
+    const int rc = ensure_frame(ctx, ctx->devs[0], need);
+    if (rc != RTB_OK) return rc;
+    dst = ctx->devs[0].frame;
+    dst_bytes = ctx->devs[0].frame_bytes;
+    f.out_compact = 0;
+  }
+  const size_t rows_out = f.out_compact ? (size_t)band_local_rows(f.height, f.band_rank, f.band_world, f.band_rows) : (size_t)f.height;
+  if (!dst || dst_bytes < rows_out * (size_t)f.width * 4) return fail(ctx, RTB_E_SIZE, "output buffer too small for the resolved resolution");
+
+  int launches = 0, chunks = 0;
+  for (int k = 0; k < n_dev; k++) {
+    FrameParams fk = f;
+    if (n_dev > 1) { fk.band_world = n_dev; fk.band_rank = k; fk.out_compact = 0; }
+    const int rc = render_on_device(ctx, ctx->devs[(size_t)k], fk, dst, launches, chunks);
+    if (rc != RTB_OK) return rc;
+  }
+  // device 0 waits for the peers' stores (the NVLink gather is complete when their resolve kernels have finished)
+  for (int k = 1; k < n_dev; k++) {
+    CK(ctx, cudaSetDevice(ctx->devs[(size_t)k].device));
+    CK(ctx, cudaEventRecord(ctx->devs[(size_t)k].ev_done, ctx->devs[(size_t)k].stream));
+    CK(ctx, cudaSetDevice(ctx->devs[0].device));
+    CK(ctx, cudaStreamWaitEvent(ctx->devs[0].stream, ctx->devs[(size_t)k].ev_done, 0));
+  }
+  CK(ctx, cudaSetDevice(ctx->devs[0].device));
+  rtb_stats& st = ctx->stats;
+  st.width = f.width; st.height = f.height; st.spp = f.spp; st.chunks = chunks; st.kernel_launches = launches; st.n_devices = n_dev;
+  st.h2d_bytes = (int64_t)sizeof(FrameParams) * launches;  // uniforms travel as kernel parameters
+  st.d2h_bytes = 0;
+  if (sync) {
+    for (int k = 0; k < n_dev; k++) {
+      CK(ctx, cudaSetDevice(ctx->devs[(size_t)k].device));
+      CK(ctx, cudaStreamSynchronize(ctx->devs[(size_t)k].stream));
+    }
+    CK(ctx, cudaSetDevice(ctx->devs[0].device));
+  }
+  return RTB_OK;
+}
+
+int collect_stats(rtb_context* ctx) {
+  rtb_stats& st = ctx->stats;
+  st.rays_primary = st.rays_continuation = st.rays_shadow = st.paths_hit_primary = 0;
+  st.ms_render_device = 0.0f;
+  st.ms_trace = st.ms_shadow = st.ms_resolve = 0.0f;
+  int64_t overflow = 0;
+  for (auto& d : ctx->devs) {
+    CK(ctx, cudaSetDevice(d.device));
+    CK(ctx, cudaStreamSynchronize(d.stream));
+    if (d.q.totals) {
+      unsigned long long t[8];
+      CK(ctx, cudaMemcpy(t, d.q.totals, sizeof t, cudaMemcpyDeviceToHost));
+      st.rays_primary += (int64_t)t[0]; st.rays_continuation += (int64_t)t[1]; st.rays_shadow += (int64_t)t[2];
+      st.paths_hit_primary += (int64_t)t[3]; overflow += (int64_t)t[4];
+    }
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end) == cudaSuccess) st.ms_render_device = std::max(st.ms_render_device, ms);
+    else cudaGetLastError();
+    if (ctx->profiling && &d == &ctx->devs[0]) {
+      st.ms_trace = sum_pairs(d.prof_trace, d.prof_used[0]);
+      st.ms_shadow = sum_pairs(d.prof_shadow, d.prof_used[1]);
+      st.ms_resolve = sum_pairs(d.prof_resolve, d.prof_used[2]);
+    }
+  }
+  st.reserved[0] = overflow;
+  cudaSetDevice(ctx->devs[0].device);
+  return RTB_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+extern "C" {
+
+int rtb_api_version(void) { return RTB_API_VERSION; }
+
+void rtb_abi_sizes(int32_t* out, int32_t n) {
+  const int32_t v[] = {(int32_t)sizeof(rtb_xform_elem), (int32_t)sizeof(rtb_material), (int32_t)sizeof(rtb_triangle), (int32_t)sizeof(rtb_mesh),
+                       (int32_t)sizeof(rtb_prim), (int32_t)sizeof(rtb_scene_desc), (int32_t)sizeof(rtb_render_params), (int32_t)sizeof(rtb_stats)};
+  for (int32_t i = 0; i < n && i < (int32_t)(sizeof v / sizeof v[0]); i++) out[i] = v[i];
+}
+
+void rtb_params_default(rtb_render_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof *p);
+  p->light_intensity = 1.0f;
+  p->max_depth = 2;
+  p->enable_ambient = p->enable_diffuse = p->enable_specular = p->enable_refraction = 1;
+  p->aa_samples = 1;
+}
+
+int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) {
+  if (!out) return fail(nullptr, RTB_E_ARG, "out is null");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    return fail(nullptr, RTB_E_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                         " (librtb200 has no CPU fallback)");
+  }
+  std::vector<int32_t> ids;
+  if (!device_ids || n_devices <= 0) ids.push_back(0);
+  else ids.assign(device_ids, device_ids + n_devices);
+  for (int32_t id : ids)
+    if (id < 0 || id >= count) return fail(nullptr, RTB_E_ARG, "device id out of range");
+  std::unique_ptr<rtb_context> ctx(new rtb_context());
+  if (const char* env = std::getenv("RTB_CHUNK_SLOTS")) {
+    const long long v = std::atoll(env);
+    if (v >= 1024) ctx->chunk_slots = v;
+  }
+  ctx->devs.resize(ids.size());
+  for (size_t k = 0; k < ids.size(); k++) {
+    DeviceState& d = ctx->devs[k];
+    d.device = ids[k];
+    CK(nullptr, cudaSetDevice(d.device));
+    cudaDeviceProp prop;
+    CK(nullptr, cudaGetDeviceProperties(&prop, d.device));
+    if (prop.major < 10) return fail(nullptr, RTB_E_CUDA, "librtb200 is built for sm_100a (B200) only");
+    d.sm_count = prop.multiProcessorCount;
+    CK(nullptr, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    CK(nullptr, cudaEventCreate(&d.ev_begin));
+    CK(nullptr, cudaEventCreate(&d.ev_end));
+    CK(nullptr, cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming));
+    CK(nullptr, cudaMalloc(&d.sphere_table, kSphereVerts * 3 * sizeof(float)));
+    CK(nullptr, cudaMemcpy(d.sphere_table, unit_sphere_table(), kSphereVerts * 3 * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  // peers store their bands straight into device 0's frame
+  for (size_t k = 1; k < ids.size(); k++) {
+    int can = 0;
+    CK(nullptr, cudaDeviceCanAccessPeer(&can, ids[k], ids[0]));
+    if (!can) return fail(nullptr, RTB_E_CUDA, "peer access to device 0 is not available");
+    CK(nullptr, cudaSetDevice(ids[k]));
+    e = cudaDeviceEnablePeerAccess(ids[0], 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(nullptr, RTB_E_CUDA, cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+  cudaSetDevice(ids[0]);
+  *out = ctx.release();
+  return RTB_OK;
+}
+
+void rtb_destroy(rtb_context* ctx) {
+  if (!ctx) return;
+  for (void* p : ctx->ipc_opened) {
+    cudaSetDevice(ctx->devs[0].device);
+    cudaIpcCloseMemHandle(p);
+  }
+  for (auto& d : ctx->devs) {
+    cudaSetDevice(d.device);
+    if (d.stream) cudaStreamSynchronize(d.stream);
+    free_scene(d);
+    free_targets(d);
+    dfree(d.sphere_table);
+    for (auto* pool : {&d.prof_trace, &d.prof_shadow, &d.prof_resolve})
+      for (auto& pr : *pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    if (d.ev_begin) cudaEventDestroy(d.ev_begin);
+    if (d.ev_end) cudaEventDestroy(d.ev_end);
+    if (d.ev_done) cudaEventDestroy(d.ev_done);
+    if (d.stream) cudaStreamDestroy(d.stream);
+  }
+  delete ctx;
+}
+
+const char* rtb_last_error(rtb_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rtb_upload_scene(rtb_context* ctx, const rtb_scene_desc* scene, int32_t primitive_mode, int32_t bvh_mode) {
+  if (!ctx || !scene) return fail(ctx, RTB_E_ARG, "null argument");
+  if (primitive_mode != RTB_PRIM_TESSELLATED)
+    return fail(ctx, RTB_E_ARG, "primitive_mode: only RTB_PRIM_TESSELLATED (the reference's behaviour) is implemented");
+  if (bvh_mode != RTB_BVH_REFERENCE && bvh_mode != RTB_BVH_LBVH) return fail(ctx, RTB_E_ARG, "unknown bvh_mode");
+  const std::string why = ctx->host.assign(*scene, /*copy_triangles=*/false);
+  if (!why.empty()) return fail(ctx, RTB_E_ARG, why);
+  ctx->has_scene = false;
+  std::vector<FlattenObject> objs;
+  const int64_t n_out = build_object_table(*scene, objs);
+  if (n_out < 0) return fail(ctx, RTB_E_ARG, "scene has more than 2^31 triangles");
+  if (bvh_mode == RTB_BVH_LBVH && n_out >= (1 << 28)) return fail(ctx, RTB_E_ARG, "LBVH mode supports fewer than 2^28 triangles");
+  std::vector<float> mats;
+  pack_materials(*scene, mats);
+  float ms_build = 0.0f;
+  struct timespec a, b;
+  clock_gettime(CLOCK_MONOTONIC, &a);
+  for (auto& d : ctx->devs) {
+    float ms = 0.0f;
+    const int rc = upload_on_device(ctx, d, *scene, objs, (int32_t)n_out, mats, bvh_mode, ms);
+    if (rc != RTB_OK) return rc;
+    ms_build = std::max(ms_build, ms);
+  }
+  clock_gettime(CLOCK_MONOTONIC, &b);
+  cudaSetDevice(ctx->devs[0].device);
+  ctx->primitive_mode = primitive_mode;
+  ctx->bvh_mode = bvh_mode;
+  ctx->has_scene = true;
+  ctx->stats.n_triangles = n_out;
+  ctx->stats.n_nodes = ctx->devs[0].scene.n_nodes;
+  ctx->stats.ms_build = ms_build;
+  ctx->stats.ms_upload = (float)((b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) * 1e-6);
+  return RTB_OK;
+}
+
+int rtb_invalidate(rtb_context* ctx) {
+  if (!ctx) return RTB_E_ARG;
+  for (auto& d : ctx->devs) { cudaSetDevice(d.device); cudaStreamSynchronize(d.stream); free_scene(d); }
+  cudaSetDevice(ctx->devs[0].device);
+  ctx->has_scene = false;
+  return RTB_OK;
+}
+
+int rtb_clear_target(rtb_context* ctx) {
+  if (!ctx) return RTB_E_ARG;
+  if (!ctx->ipc_opened.empty()) return fail(ctx, RTB_E_ARG, "frame buffers are shared over IPC; destroy the context instead");
+  for (auto& d : ctx->devs) { cudaSetDevice(d.device); cudaStreamSynchronize(d.stream); free_targets(d); }
+  cudaSetDevice(ctx->devs[0].device);
+  return RTB_OK;
+}
+
+int rtb_render(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* out_w, int32_t* out_h) {
+  if (!ctx || !p || !rgba8) return fail(ctx, RTB_E_ARG, "null argument");
+  if (p->band_world > 1) return fail(ctx, RTB_E_ARG, "rtb_render renders whole frames; use rtb_render_device for band sharding");
+  if (ctx->has_scene) {  // check the caller's capacity before any work
+    FrameParams f;
+    std::string why;
+    if (!resolve_frame(ctx->host.d, *p, f, why)) return fail(ctx, RTB_E_ARG, why);
+    if (out_w) *out_w = f.width;
+    if (out_h) *out_h = f.height;
+    if (bytes < (size_t)f.width * f.height * 4) return fail(ctx, RTB_E_SIZE, "rgba8 buffer too small for the resolved resolution");
+  }
+  FrameParams f;
+  const int rc = render_frame(ctx, p, nullptr, 0, /*to_internal_frame=*/true, /*sync=*/false, f);
+  if (rc != RTB_OK) return rc;
+  DeviceState& d0 = ctx->devs[0];
+  const size_t need = (size_t)f.width * f.height * 4;
+  CK(ctx, cudaMemcpyAsync(rgba8, d0.frame, need, cudaMemcpyDeviceToHost, d0.stream));  // ReadPixels, RayTracer.cs:371-375
+  CK(ctx, cudaStreamSynchronize(d0.stream));
+  for (size_t k = 1; k < ctx->devs.size(); k++) { cudaSetDevice(ctx->devs[k].device); CK(ctx, cudaStreamSynchronize(ctx->devs[k].stream)); }
+  cudaSetDevice(d0.device);
+  ctx->stats.d2h_bytes = (int64_t)need;
+  return RTB_OK;
+}
+
+int rtb_render_device(rtb_context* ctx, const rtb_render_params* p, void* dst_device, size_t bytes, int32_t sync) {
+  if (!ctx || !p || !dst_device) return fail(ctx, RTB_E_ARG, "null argument");
+  FrameParams f;
+  return render_frame(ctx, p, dst_device, bytes, /*to_internal_frame=*/false, sync != 0, f);
+}
+
+int rtb_render_aux(rtb_context* ctx, const rtb_render_params* p, int32_t* prim_id, float* t, int32_t* material) {
+  if (!ctx || !p) return fail(ctx, RTB_E_ARG, "null argument");
+  if (!ctx->has_scene) return fail(ctx, RTB_E_NOSCENE, "no scene uploaded (rtb_upload_scene)");
+  FrameParams f;
+  std::string why;
+  if (!resolve_frame(ctx->host.d, *p, f, why)) return fail(ctx, RTB_E_ARG, why);
+  DeviceState& d = ctx->devs[0];
+  CK(ctx, cudaSetDevice(d.device));
+  const size_t n_px = (size_t)f.width * f.height;
+  if (d.aux_px < n_px) {
+    dfree(d.aux_prim); dfree(d.aux_mat); dfree(d.aux_t);
+    d.aux_px = 0;
+    CK(ctx, cudaMalloc(&d.aux_prim, n_px * 4));
+    CK(ctx, cudaMalloc(&d.aux_mat, n_px * 4));
+    CK(ctx, cudaMalloc(&d.aux_t, n_px * 4));
+    d.aux_px = n_px;
+  }
+  launch_aux(d.scene.bvh_mode, f, scene_view(d.scene), d.aux_prim, d.aux_t, d.aux_mat, d.sm_count * 8, d.stream);
+  CK(ctx, cudaGetLastError());
+  if (prim_id) CK(ctx, cudaMemcpyAsync(prim_id, d.aux_prim, n_px * 4, cudaMemcpyDeviceToHost, d.stream));
+  if (t) CK(ctx, cudaMemcpyAsync(t, d.aux_t, n_px * 4, cudaMemcpyDeviceToHost, d.stream));
+  if (material) CK(ctx, cudaMemcpyAsync(material, d.aux_mat, n_px * 4, cudaMemcpyDeviceToHost, d.stream));
+  CK(ctx, cudaStreamSynchronize(d.stream));
+  return RTB_OK;
+}
+
+int rtb_get_triangles(rtb_context* ctx, float* v_n_18, int32_t* material, int64_t capacity, int64_t* n_out) {
+  if (!ctx) return RTB_E_ARG;
+  if (!ctx->has_scene) return fail(ctx, RTB_E_NOSCENE, "no scene uploaded (rtb_upload_scene)");
+  DeviceState& d = ctx->devs[0];
+  const int64_t n = d.scene.n_tris;
+  if (n_out) *n_out = n;
+  if (!v_n_18 && !material) return RTB_OK;
+  if (capacity < n) return fail(ctx, RTB_E_SIZE, "triangle capacity too small");
+  if (n == 0) return RTB_OK;
+  CK(ctx, cudaSetDevice(d.device));
+  std::vector<float> raw((size_t)n * 12), nrm((size_t)n * 12);
+  CK(ctx, cudaMemcpy(raw.data(), d.scene.raw, raw.size() * 4, cudaMemcpyDeviceToHost));
+  CK(ctx, cudaMemcpy(nrm.data(), d.scene.nrm, nrm.size() * 4, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; i++) {
+    if (v_n_18)
+      for (int k = 0; k < 3; k++)
+        for (int c = 0; c < 3; c++) {
+          v_n_18[i * 18 + k * 3 + c] = raw[(size_t)i * 12 + (size_t)k * 4 + (size_t)c];
+          v_n_18[i * 18 + 9 + k * 3 + c] = nrm[(size_t)i * 12 + (size_t)k * 4 + (size_t)c];
+        }
+    if (material) std::memcpy(&material[i], &nrm[(size_t)i * 12 + 3], 4);
+  }
+  return RTB_OK;
+}
+
+// Parity/debug access to the acceleration structure: nodes as stored on the device (reference mode: 8 floats per node =
+// GPUBVHNode; LBVH: 16 floats per node) and the leaf-order -> emission-order permutation.
+int rtb_get_bvh(rtb_context* ctx, void* nodes, int64_t nodes_capacity_bytes, int64_t* n_nodes, int32_t* perm, int64_t perm_capacity) {
+  if (!ctx) return RTB_E_ARG;
+  if (!ctx->has_scene) return fail(ctx, RTB_E_NOSCENE, "no scene uploaded (rtb_upload_scene)");
+  DeviceState& d = ctx->devs[0];
+  CK(ctx, cudaSetDevice(d.device));
+  if (n_nodes) *n_nodes = d.scene.n_tris > 0 ? d.scene.n_nodes : 0;
+  const size_t node_bytes = d.scene.n_tris > 0 ? (size_t)d.scene.n_nodes * (size_t)d.scene.node_floats * 4 : 0;
+  if (nodes && node_bytes) {
+    if ((size_t)nodes_capacity_bytes < node_bytes) return fail(ctx, RTB_E_SIZE, "node capacity too small");
+    CK(ctx, cudaMemcpy(nodes, d.scene.nodes, node_bytes, cudaMemcpyDeviceToHost));
+  }
+  if (perm && d.scene.n_tris) {
+    if (perm_capacity < d.scene.n_tris) return fail(ctx, RTB_E_SIZE, "perm capacity too small");
+    CK(ctx, cudaMemcpy(perm, d.scene.perm, (size_t)d.scene.n_tris * 4, cudaMemcpyDeviceToHost));
+  }
+  return RTB_OK;
+}
+
+int rtb_get_stats(rtb_context* ctx, rtb_stats* out) {
+  if (!ctx || !out) return RTB_E_ARG;
+  const int rc = collect_stats(ctx);
+  if (rc != RTB_OK) return rc;
+  *out = ctx->stats;
+  return RTB_OK;
+}
+
+int rtb_set_profiling(rtb_context* ctx, int32_t enable) {
+  if (!ctx) return RTB_E_ARG;
+  ctx->profiling = enable != 0;
+  return RTB_OK;
+}
+
+int rtb_set_cancel_flag(rtb_context* ctx, const volatile int32_t* flag) {
+  if (!ctx) return RTB_E_ARG;
+  ctx->cancel = flag;
+  return RTB_OK;
+}
+
+int rtb_synchronize(rtb_context* ctx) {
+  if (!ctx) return RTB_E_ARG;
+  for (auto& d : ctx->devs) { CK(ctx, cudaSetDevice(d.device)); CK(ctx, cudaStreamSynchronize(d.stream)); }
+  cudaSetDevice(ctx->devs[0].device);
+  return RTB_OK;
+}
+
+void* rtb_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void rtb_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+int rtb_frame_export(rtb_context* ctx, size_t bytes, void** dev_ptr, uint8_t handle64[64]) {
+  if (!ctx || !handle64) return fail(ctx, RTB_E_ARG, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DeviceState& d = ctx->devs[0];
+  CK(ctx, cudaSetDevice(d.device));
+  const int rc = ensure_frame(ctx, d, bytes);
+  if (rc != RTB_OK) return rc;
+  cudaIpcMemHandle_t h;
+  CK(ctx, cudaIpcGetMemHandle(&h, d.frame));
+  std::memcpy(handle64, &h, 64);
+  if (dev_ptr) *dev_ptr = d.frame;
+  return RTB_OK;
+}
+
+int rtb_frame_import(rtb_context* ctx, const uint8_t handle64[64], void** dev_ptr) {
+  if (!ctx || !handle64 || !dev_ptr) return fail(ctx, RTB_E_ARG, "null argument");
+  CK(ctx, cudaSetDevice(ctx->devs[0].device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  CK(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  ctx->ipc_opened.push_back(p);
+  *dev_ptr = p;
+  return RTB_OK;
+}
+
+// Copies device 0's internal frame (the buffer rtb_frame_export shares) to the host: the readback step after a
+// multi-process peer-store gather.
+int rtb_frame_read(rtb_context* ctx, uint8_t* rgba8, size_t bytes) {
+  if (!ctx || !rgba8) return fail(ctx, RTB_E_ARG, "null argument");
+  DeviceState& d = ctx->devs[0];
+  if (!d.frame || d.frame_bytes < bytes) return fail(ctx, RTB_E_SIZE, "internal frame smaller than requested");
+  CK(ctx, cudaSetDevice(d.device));
+  CK(ctx, cudaMemcpyAsync(rgba8, d.frame, bytes, cudaMemcpyDeviceToHost, d.stream));
+  CK(ctx, cudaStreamSynchronize(d.stream));
+  ctx->stats.d2h_bytes = (int64_t)bytes;
+  return RTB_OK;
+}
+
+// ---- host-only helpers (no device needed) -----------------------------------------------------------------------------
+
+// The uniform block RayTracer.cs:221-355 would upload for (scene, settings): out25 = cameraToObject row-major 4x4,
+// camDist, tanHalf, orthoSize, light xyz, bg xyz; wh = resolved width, height.
+int rtb_resolve_frame(const rtb_scene_desc* scene, const rtb_render_params* p, float* out25, int32_t* wh) {
+  if (!scene || !p) return RTB_E_ARG;
+  FrameParams f;
+  std::string why;
+  if (!resolve_frame(*scene, *p, f, why)) { g_create_error = why; return RTB_E_ARG; }
+  if (out25) {
+    std::memcpy(out25, f.cam, 48);
+    out25[12] = 0.0f; out25[13] = 0.0f; out25[14] = 0.0f; out25[15] = 1.0f;
+    out25[16] = f.cam_dist; out25[17] = f.tan_half; out25[18] = f.ortho_size;
+    std::memcpy(out25 + 19, f.light, 12);
+    std::memcpy(out25 + 22, f.bg, 12);
+  }
+  if (wh) { wh[0] = f.width; wh[1] = f.height; }
+  return RTB_OK;
+}
+
+// Host restatement of the reference BVH build on caller-provided triangles (12 floats each: v0,cx,v1,cy,v2,cz): lets
+// the CPU test-suite compare the product's builder with the checker's without a GPU.
+int rtb_build_reference_bvh(const float* raw12, int32_t n, float* nodes8, int64_t nodes_capacity, int64_t* n_nodes, int32_t* perm) {
+  if (!raw12 && n > 0) return RTB_E_ARG;
+  RefBvh b;
+  build_reference_bvh(raw12, n, b);
+  const int64_t nn = (int64_t)(b.nodes.size() / 8);
+  if (n_nodes) *n_nodes = n > 0 ? nn : 0;
+  if (n <= 0) return RTB_OK;
+  if (nodes8) {
+    if (nodes_capacity < nn) return RTB_E_SIZE;
+    std::memcpy(nodes8, b.nodes.data(), b.nodes.size() * 4);
+  }
+  if (perm) std::memcpy(perm, b.perm.data(), (size_t)n * 4);
+  return RTB_OK;
+}
+
+int rtb_scene_parse(const char* text, size_t len, rtb_scene** out, char* err, size_t err_cap) {
+  if (!text || !out) return RTB_E_ARG;
+  std::unique_ptr<rtb_scene> s(new rtb_scene());
+  try {
+    parse_scene_text(text, len, s->h);
+  } catch (const std::exception& e) {
+    if (err && err_cap) std::snprintf(err, err_cap, "%s", e.what());
+    return RTB_E_PARSE;
+  }
+  *out = s.release();
+  return RTB_OK;
+}
+
+int rtb_scene_load(const char* path, rtb_scene** out, char* err, size_t err_cap) {
+  if (!path || !out) return RTB_E_ARG;
+  std::ifstream in(path, std::ios::binary);
+  if (!in) {  // the reference logs and returns an empty ObjectData (SceneService.cs:28-33); here it is an error code
+    if (err && err_cap) std::snprintf(err, err_cap, "cannot open %s", path);
+    return RTB_E_IO;
+  }
+  std::stringstream buf;
+  buf << in.rdbuf();
+  const std::string text = buf.str();
+  return rtb_scene_parse(text.data(), text.size(), out, err, err_cap);
+}
+
+const rtb_scene_desc* rtb_scene_get(const rtb_scene* s) { return s ? &s->h.d : nullptr; }
+void rtb_scene_free(rtb_scene* s) { delete s; }
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+// kernels.hpp — host-callable launchers of the library's CUDA kernels (flatten.cu, lbvh.cu, trace.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/rtb.h"
+#include "rtb_device.cuh"
+#include "scene_host.hpp"
+
+namespace rtb {
+
+// ---- flatten.cu (K1: scene upload) ------------------------------------------------------------------------------------
+// tri_in: device copy of the caller's rtb_triangle array (10 words each); objs: device FlattenObject table;
+// sphere_table: 410 float3 on the device.  Writes, in emission order, raw[3i..] = (v0,c.x)(v1,c.y)(v2,c.z) and
+// nrm[3i..] = (n0,material)(n1,0)(n2,0).
+void launch_flatten(const float* tri_in, const FlattenObject* objs, int n_objs, const float* sphere_table, int32_t n_out, float4* raw,
+                    float4* nrm, cudaStream_t st);
+// Gathers into leaf order: isect[3j..] = (v0,prim_id)(v1-v0,material)(v2-v0,0), shade[3j..] = n0 n1 n2, prim_id = perm[j].
+void launch_pack(const float4* raw, const float4* nrm, const int32_t* perm, int32_t n, float4* isect, float4* shade, cudaStream_t st);
+
+// ---- lbvh.cu (K2: Morton-code LBVH built on the GPU) -------------------------------------------------------------------
+struct LbvhBuffers {            // all device memory, sized by lbvh_workspace_bytes / allocated by the caller
+  float4* nodes;                // 4 * max(1, n-1)
+  int32_t* perm;                // n
+  void* workspace;              // lbvh_workspace_bytes(n)
+  size_t workspace_bytes;
+  int32_t* root_out;            // 1 int on the device: root reference
+};
+size_t lbvh_workspace_bytes(int32_t n);
+// Returns cudaSuccess or the failing call's error.  Asynchronous on `st`.
+cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaStream_t st);
+
+// ---- trace.cu (K3-K8: the per-pixel wavefront) --------------------------------------------------------------------------
+// `grid` = number of persistent blocks (sm_count * *_blocks_per_sm for the wavefront kernels).
+void launch_trace_shade(int bvh, bool primary, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth,
+                        int grid, cudaStream_t st);
+void launch_shadow(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, int depth, int grid, cudaStream_t st);
+void launch_resolve(const FrameParams& f, const QueueView& q, const ChunkView& c, void* dst, int grid, cudaStream_t st);
+void launch_debug(int bvh, const FrameParams& f, const SceneView& s, const ChunkView& c, void* dst, int grid, cudaStream_t st);
+void launch_aux(int bvh, const FrameParams& f, const SceneView& s, int32_t* prim, float* t, int32_t* mat, int grid, cudaStream_t st);
+// Resident blocks per SM of the persistent kernels (occupancy query), by variant.
+int trace_blocks_per_sm(int bvh, bool primary);
+int shadow_blocks_per_sm(int bvh);
+
+}  // namespace rtb

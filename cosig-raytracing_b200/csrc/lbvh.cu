@@ -1,0 +1,259 @@
+// lbvh.cu — K2: Morton-code LBVH built on the GPU (replaces the recursive CPU median-split build of
+// Assets/Services/BVH/BVHBuilder.cs:76-238 for triangle-heavy scenes; the exact reference-shape build stays available
+// on the host for parity mode, scene_host.cpp).
+//
+// Pipeline (all on one stream, no host round trip):
+//   k_centroid_bounds   min/max of the triangle centroids (warp shuffles + one atomic per block and component)
+//   k_morton            63-bit Morton key (21 bits per axis) of each centroid, value = emission index
+//   cub radix sort      keys + values
+//   k_hierarchy         Karras 2012 binary radix tree over the sorted keys (ties broken by index), parent links, ranges
+//   k_refit             bottom-up AABBs: each leaf thread climbs, the second arrival at a node merges its children
+//   k_emit              traversal nodes: every tree node whose range holds <= RTB_LEAF_MAX triangles collapses into a
+//                       leaf (its triangles are contiguous in sorted order), every larger node becomes a 64-byte record
+//                       carrying BOTH children's boxes, so one fetch decides both descents
+// The sorted value array is the leaf order (perm) used by launch_pack.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels.hpp"
+
+namespace rtb {
+namespace {
+
+constexpr int kBlock = 256;
+
+// Order-preserving float <-> uint map for atomicMin/Max.
+__device__ __forceinline__ unsigned f2o(float f) { const unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float o2f(unsigned o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
+
+struct Workspace {
+  unsigned* bounds;          // 6: min xyz, max xyz (ordered-uint encoded)
+  unsigned long long* keys;  // n
+  unsigned long long* keys_sorted;
+  int32_t* vals;             // n
+  int2* child;               // n-1: Karras children (>= 0 internal, < 0: ~leaf index)
+  int2* range;               // n-1: [first, last] in sorted order
+  int32_t* parent;           // 2n-1: parents of internal nodes [0,n-1) then of leaves [n-1, 2n-1)
+  int32_t* flag;             // n-1
+  float4* box;               // 2*(2n-1): min,max of internal nodes then leaves
+  void* cub_temp;
+  size_t cub_bytes;
+};
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t cub_temp_bytes(int32_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, n, 0, 63);
+  return bytes;
+}
+
+Workspace carve(void* base, int32_t n) {
+  char* p = (char*)base;
+  Workspace w;
+  auto take = [&](size_t bytes) { void* r = p; p += align_up(bytes); return r; };
+  const size_t ni = (size_t)(n > 1 ? n - 1 : 1), nt = (size_t)n, na = 2 * nt;
+  w.bounds = (unsigned*)take(6 * sizeof(unsigned));
+  w.keys = (unsigned long long*)take(nt * 8);
+  w.keys_sorted = (unsigned long long*)take(nt * 8);
+  w.vals = (int32_t*)take(nt * 4);
+  w.child = (int2*)take(ni * 8);
+  w.range = (int2*)take(ni * 8);
+  w.parent = (int32_t*)take(na * 4);
+  w.flag = (int32_t*)take(ni * 4);
+  w.box = (float4*)take(na * 2 * sizeof(float4));
+  w.cub_bytes = cub_temp_bytes(n);
+  w.cub_temp = take(w.cub_bytes);
+  return w;
+}
+
+__global__ void k_init_bounds(unsigned* bounds) {
+  if (threadIdx.x < 3) bounds[threadIdx.x] = 0xffffffffu;
+  else if (threadIdx.x < 6) bounds[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(kBlock) k_centroid_bounds(const float4* __restrict__ raw, int32_t n, unsigned* bounds) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    for (int a = 0; a < 3; a++) {
+      const float c = raw[3 * (size_t)i + a].w;
+      mn[a] = fminf(mn[a], c);
+      mx[a] = fmaxf(mx[a], c);
+    }
+  for (int a = 0; a < 3; a++)
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  __shared__ float s_mn[3][kBlock / 32], s_mx[3][kBlock / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+    for (int a = 0; a < 3; a++) { s_mn[a][warp] = mn[a]; s_mx[a][warp] = mx[a]; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int a = threadIdx.x;
+    float lo = s_mn[a][0], hi = s_mx[a][0];
+    for (int w = 1; w < kBlock / 32; w++) { lo = fminf(lo, s_mn[a][w]); hi = fmaxf(hi, s_mx[a][w]); }
+    atomicMin(&bounds[a], f2o(lo));
+    atomicMax(&bounds[3 + a], f2o(hi));
+  }
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned v) {  // 21 bits -> every third bit of 63
+  unsigned long long x = v & 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+__global__ void __launch_bounds__(kBlock) k_morton(const float4* __restrict__ raw, int32_t n, const unsigned* __restrict__ bounds,
+                                                   unsigned long long* __restrict__ keys, int32_t* __restrict__ vals) {
+  float lo[3], scale[3];
+  for (int a = 0; a < 3; a++) {
+    lo[a] = o2f(bounds[a]);
+    const float ext = o2f(bounds[3 + a]) - lo[a];
+    scale[a] = ext > 0.0f ? 2097152.0f / ext : 0.0f;
+  }
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    unsigned q[3];
+    for (int a = 0; a < 3; a++) {
+      const float v = (raw[3 * (size_t)i + a].w - lo[a]) * scale[a];
+      q[a] = (unsigned)fminf(fmaxf(v, 0.0f), 2097151.0f);
+    }
+    keys[i] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    vals[i] = i;
+  }
+}
+
+// Length of the common prefix of keys i and j (ties extended by the indices); -1 when j is outside [0, n).
+__device__ __forceinline__ int common_prefix(const unsigned long long* __restrict__ keys, int32_t n, int32_t i, int32_t j) {
+  if (j < 0 || j >= n) return -1;
+  const unsigned long long a = keys[i], b = keys[j];
+  if (a != b) return __clzll((long long)(a ^ b));
+  return 64 + __clz(i ^ j);
+}
+
+__global__ void __launch_bounds__(kBlock) k_hierarchy(const unsigned long long* __restrict__ keys, int32_t n, int2* __restrict__ child,
+                                                      int2* __restrict__ range, int32_t* __restrict__ parent) {
+  const int32_t n_int = n - 1;
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_int; i += gridDim.x * blockDim.x) {
+    const int d = common_prefix(keys, n, i, i + 1) - common_prefix(keys, n, i, i - 1) >= 0 ? 1 : -1;
+    const int min_prefix = common_prefix(keys, n, i, i - d);
+    int32_t l_max = 2;
+    while (common_prefix(keys, n, i, i + l_max * d) > min_prefix) l_max <<= 1;
+    int32_t l = 0;
+    for (int32_t t = l_max >> 1; t >= 1; t >>= 1)
+      if (common_prefix(keys, n, i, i + (l + t) * d) > min_prefix) l += t;
+    const int32_t j = i + l * d;
+    const int node_prefix = common_prefix(keys, n, i, j);
+    int32_t s = 0;
+    for (int32_t t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+      if (common_prefix(keys, n, i, i + (s + t) * d) > node_prefix) s += t;
+      if (t == 1) break;
+    }
+    const int32_t split = i + s * d + min(d, 0);
+    const int32_t first = min(i, j), last = max(i, j);
+    const int32_t left = (first == split) ? ~split : split;
+    const int32_t right = (last == split + 1) ? ~(split + 1) : split + 1;
+    child[i] = make_int2(left, right);
+    range[i] = make_int2(first, last);
+    parent[left >= 0 ? left : n_int + ~left] = i;
+    parent[right >= 0 ? right : n_int + ~right] = i;
+    if (i == 0) parent[0] = -1;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_refit(const float4* __restrict__ raw, const int32_t* __restrict__ vals, int32_t n,
+                                                  const int2* __restrict__ child, const int32_t* __restrict__ parent, int32_t* flag,
+                                                  float4* box) {
+  const int32_t n_int = n - 1;
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int32_t src = vals[i];
+    const float4 a = raw[3 * (size_t)src], b = raw[3 * (size_t)src + 1], c = raw[3 * (size_t)src + 2];
+    float4 mn = make_float4(fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y), fminf(fminf(a.z, b.z), c.z), 0.0f);
+    float4 mx = make_float4(fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z), 0.0f);
+    box[2 * (size_t)(n_int + i)] = mn;
+    box[2 * (size_t)(n_int + i) + 1] = mx;
+    if (n_int == 0) continue;
+    int32_t node = parent[n_int + i];
+    while (node >= 0) {
+      __threadfence();
+      if (atomicAdd(&flag[node], 1) == 0) break;  // first arrival: the sibling subtree is not finished yet
+      const int2 ch = child[node];
+      const size_t li = ch.x >= 0 ? (size_t)ch.x : (size_t)(n_int + ~ch.x), ri = ch.y >= 0 ? (size_t)ch.y : (size_t)(n_int + ~ch.y);
+      const float4 lmn = __ldcg(&box[2 * li]), lmx = __ldcg(&box[2 * li + 1]), rmn = __ldcg(&box[2 * ri]), rmx = __ldcg(&box[2 * ri + 1]);
+      mn = make_float4(fminf(lmn.x, rmn.x), fminf(lmn.y, rmn.y), fminf(lmn.z, rmn.z), 0.0f);
+      mx = make_float4(fmaxf(lmx.x, rmx.x), fmaxf(lmx.y, rmx.y), fmaxf(lmx.z, rmx.z), 0.0f);
+      __stcg(&box[2 * (size_t)node], mn);
+      __stcg(&box[2 * (size_t)node + 1], mx);
+      node = parent[node];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_emit(int32_t n, const int2* __restrict__ child, const int2* __restrict__ range,
+                                                 const float4* __restrict__ box, float4* __restrict__ nodes, int32_t* __restrict__ root_out) {
+  const int32_t n_int = n - 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *root_out = (n <= RTB_LEAF_MAX) ? lbvh_leaf_ref(0, n) : 0;
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_int; i += gridDim.x * blockDim.x) {
+    const int2 rg = range[i];
+    if (rg.y - rg.x + 1 <= RTB_LEAF_MAX) continue;  // inside a collapsed leaf: never referenced
+    const int2 ch = child[i];
+    int32_t ref[2];
+    size_t bi[2];
+    const int32_t cc[2] = {ch.x, ch.y};
+    for (int k = 0; k < 2; k++) {
+      if (cc[k] < 0) { ref[k] = lbvh_leaf_ref(~cc[k], 1); bi[k] = (size_t)(n_int + ~cc[k]); }
+      else {
+        const int2 cr = range[cc[k]];
+        const int32_t cnt = cr.y - cr.x + 1;
+        ref[k] = cnt <= RTB_LEAF_MAX ? lbvh_leaf_ref(cr.x, cnt) : cc[k];
+        bi[k] = (size_t)cc[k];
+      }
+    }
+    const float4 lmn = box[2 * bi[0]], lmx = box[2 * bi[0] + 1], rmn = box[2 * bi[1]], rmx = box[2 * bi[1] + 1];
+    nodes[4 * (size_t)i] = make_float4(lmn.x, lmn.y, lmn.z, __int_as_float(ref[0]));
+    nodes[4 * (size_t)i + 1] = make_float4(lmx.x, lmx.y, lmx.z, __int_as_float(ref[1]));
+    nodes[4 * (size_t)i + 2] = make_float4(rmn.x, rmn.y, rmn.z, 0.0f);
+    nodes[4 * (size_t)i + 3] = make_float4(rmx.x, rmx.y, rmx.z, 0.0f);
+  }
+}
+
+inline int grid_for(int64_t n) {
+  const int64_t g = (n + kBlock - 1) / kBlock;
+  return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+}  // namespace
+
+size_t lbvh_workspace_bytes(int32_t n) {
+  if (n <= 0) return 256;
+  const size_t ni = (size_t)(n > 1 ? n - 1 : 1), nt = (size_t)n, na = 2 * nt;
+  return align_up(24) + 2 * align_up(nt * 8) + align_up(nt * 4) + 2 * align_up(ni * 8) + align_up(na * 4) + align_up(ni * 4) +
+         align_up(na * 2 * sizeof(float4)) + align_up(cub_temp_bytes(n)) + 256;
+}
+
+cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  Workspace w = carve(b.workspace, n);
+  k_init_bounds<<<1, 32, 0, st>>>(w.bounds);
+  k_centroid_bounds<<<grid_for(n), kBlock, 0, st>>>(raw, n, w.bounds);
+  k_morton<<<grid_for(n), kBlock, 0, st>>>(raw, n, w.bounds, w.keys, w.vals);
+  size_t temp = w.cub_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_temp, temp, (const unsigned long long*)w.keys, w.keys_sorted, (const int32_t*)w.vals,
+                                                  b.perm, n, 0, 63, st);
+  if (e != cudaSuccess) return e;
+  if (n > 1) {
+    e = cudaMemsetAsync(w.flag, 0, (size_t)(n - 1) * 4, st);
+    if (e != cudaSuccess) return e;
+    k_hierarchy<<<grid_for(n - 1), kBlock, 0, st>>>(w.keys_sorted, n, w.child, w.range, w.parent);
+  }
+  k_refit<<<grid_for(n), kBlock, 0, st>>>(raw, b.perm, n, w.child, w.parent, w.flag, w.box);
+  k_emit<<<grid_for(n > 1 ? n - 1 : 1), kBlock, 0, st>>>(n, w.child, w.range, w.box, b.nodes, b.root_out);
+  return cudaGetLastError();
+}
+
+}  // namespace rtb

@@ -1,0 +1,124 @@
+// rtb_device.cuh — shared device-side definitions: FP32 arithmetic spec helpers, frame uniforms, scene/queue views.
+//
+// Arithmetic spec: IEEE binary32, one rounding per + - * / sqrt, no contraction.  Every translation unit
+// of the library is compiled with --fmad=false --prec-div=true --prec-sqrt=true --ftz=false, so plain expressions are
+// never fused.  HLSL intrinsics are fixed as in SURVEY.md App. D: dot = (x*x' + y*y') + z*z',
+// normalize(v) = v * (1/sqrt(dot(v,v))), reflect(i,n) = i - (2*dot(n,i))*n, min/max return the non-NaN operand
+// (fminf/fmaxf), pow(x,32) = five squarings.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rtb {
+
+#define RTB_INFINITY 3.402823466e+38f /* BVHRayTracing.compute:101 */
+#define RTB_EPSILON 1e-4f             /* BVHRayTracing.compute:102 */
+#define RTB_OFFSET (1e-4f * 100.0f)   /* "Epsilon * 100.0", BVHRayTracing.compute:396,442,447,454 */
+
+#define RTB_STACK_REF 64   /* reference traversal: int stack (the reference has 32 unchecked, compute:235) */
+#define RTB_STACK_LBVH 96  /* LBVH ordered traversal: one deferred sibling per level */
+#define RTB_LEAF_MAX 4     /* LBVH leaf size */
+
+struct f3 { float x, y, z; };
+__host__ __device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__host__ __device__ __forceinline__ f3 mk3(float4 v) { return mk3(v.x, v.y, v.z); }
+__host__ __device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ __forceinline__ f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__host__ __device__ __forceinline__ f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ __forceinline__ f3 operator*(float s, f3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+__host__ __device__ __forceinline__ f3 negate(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+__host__ __device__ __forceinline__ float dot3(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__host__ __device__ __forceinline__ f3 cross3(f3 a, f3 b) {
+  return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ f3 hlsl_normalize(f3 v) { const float r = 1.0f / sqrtf(dot3(v, v)); return v * r; }
+__device__ __forceinline__ float hlsl_length(f3 v) { return sqrtf(dot3(v, v)); }
+__device__ __forceinline__ f3 hlsl_reflect(f3 i, f3 n) { const float k = 2.0f * dot3(n, i); return i - k * n; }
+__device__ __forceinline__ float hlsl_frac(float x) { return x - floorf(x); }
+__device__ __forceinline__ float pow32(float x) { x = x * x; x = x * x; x = x * x; x = x * x; x = x * x; return x; }
+// Vector3.normalized (Unity): v / |v| when |v| > 1e-5, else zero.
+__device__ __forceinline__ f3 unity_normalized(f3 v) {
+  const float mag = sqrtf((v.x * v.x + v.y * v.y) + v.z * v.z);
+  if (mag > 1e-5f) return mk3(v.x / mag, v.y / mag, v.z / mag);
+  return mk3(0.0f, 0.0f, 0.0f);
+}
+
+// Per-frame uniforms: what RayTracer.cs:302-355 uploads with ComputeShader.Set*, resolved on the host
+// (scene_host.cpp: resolve_frame) and passed by value as a kernel parameter.
+struct FrameParams {
+  float cam[12];       // _CameraToWorld rows 0..2 (row-major 3x4), RayTracer.cs:352
+  float cam_dist;      // _CameraDistance :354
+  float tan_half;      // tan(radians(_CameraFOV)*0.5), BVHRayTracing.compute:292, evaluated once on the host
+  float ortho_size;    // _OrthoSize :347-348
+  float light[3];      // _LightPosition :325-337
+  float bg[3];         // _BackgroundColor :322-323
+  float light_intensity, light_size, roughness, shutter;
+  int32_t width, height;
+  int32_t spp, grid_w, grid_h;   // max(1,_AASamples), compute:283-287
+  int32_t max_depth;
+  int32_t en_ambient, en_diffuse, en_specular, en_refraction, ortho, soft, glossy, blur, debug, srgb;
+  // tile sharding: bands of band_rows rows, band b belongs to rank b % band_world
+  int32_t band_rank, band_world, band_rows;
+  int32_t out_compact;
+};
+
+// Rows of the frame owned by rank `rank`: bands rank, rank+world, ...  Local rows are the owned rows packed in order.
+__host__ __device__ __forceinline__ int32_t band_local_rows(int32_t height, int32_t rank, int32_t world, int32_t band_rows) {
+  if (world <= 1) return height;
+  const int32_t n_bands = (height + band_rows - 1) / band_rows;
+  int32_t rows = 0;
+  // bands owned: rank, rank+world, ... < n_bands
+  const int32_t owned = n_bands > rank ? (n_bands - rank + world - 1) / world : 0;
+  if (owned == 0) return 0;
+  rows = owned * band_rows;
+  const int32_t last_band = rank + (owned - 1) * world;
+  const int32_t last_end = (last_band + 1) * band_rows;
+  if (last_end > height) rows -= last_end - height;
+  return rows;
+}
+__host__ __device__ __forceinline__ int32_t band_global_row(int32_t local_row, int32_t rank, int32_t world, int32_t band_rows) {
+  if (world <= 1) return local_row;
+  const int32_t lb = local_row / band_rows;
+  return (lb * world + rank) * band_rows + (local_row - lb * band_rows);
+}
+
+// Work decomposition of one chunk: local rows [row0, row0+rows) of this rank, as 8x4 pixel tiles, spp slots per pixel.
+// slot = ((tile * spp + sample) * 32 + lane), tile = ty * tiles_x + tx, lane = ly * 8 + lx.
+struct ChunkView {
+  int32_t row0, rows;      // local (per-rank) row range; row0 is a multiple of 4
+  int32_t tiles_x;         // ceil(width / 8)
+  int32_t n_slots;         // tiles_x * ceil(rows/4) * 32 * spp
+};
+
+// Geometry as laid out in HBM.
+struct SceneView {
+  const float4* __restrict__ tri_isect;  // 3 per triangle, leaf order: (v0, prim_id) (e1, material) (e2, 0)
+  const float4* __restrict__ tri_shade;  // 3 per triangle, leaf order: n0 n1 n2
+  const float4* __restrict__ nodes;      // reference: 2 per node (min,leftOrFirst)(max,count); LBVH: 4 per node (see lbvh.cu)
+  const float4* __restrict__ materials;  // 2 per material: (r,g,b,ka) (kd,ks,kr,ior)
+  int32_t n_tris, n_nodes, n_mats;
+  int32_t root;                          // LBVH: root reference (>= 0 internal node, < 0 leaf, see lbvh_leaf_ref)
+};
+
+// LBVH child reference: >= 0 internal node index; < 0 leaf: ~ref = (first_triangle << 3) | (count - 1).
+__host__ __device__ __forceinline__ int32_t lbvh_leaf_ref(int32_t first, int32_t count) { return ~((first << 3) | (count - 1)); }
+
+// Wavefront queues.
+// Ray queue entry: o = (origin, slot bits), d = (dir, 0), att = (attenuation, 0).
+// Shadow queue entry: o = (origin, distToLight), d = (dir, slot bits), lit / unlit = the two candidate increments of the
+// slot's sampleColor (BVHRayTracing.compute:418 evaluated for both outcomes of the shadow test).
+struct QueueView {
+  float4* ray_o[2]; float4* ray_d[2]; float4* ray_att[2];
+  float4* sh_o; float4* sh_d; float4* sh_lit; float4* sh_unlit;
+  float4* accum;          // per slot: running sampleColor
+  int32_t* counters;      // 4 blocks of depth_cap ints: ray queue sizes | shadow queue sizes | trace fetch | shadow fetch
+  unsigned long long* totals;  // [0] primary rays [1] continuation rays [2] shadow rays [3] primary hits [4] stack overflows
+  int32_t depth_cap;      // D (>= max_depth + 1)
+};
+#define RTB_CNT_RAY(q, d) ((q).counters[(d)])
+#define RTB_CNT_SHADOW(q, d) ((q).counters[(q).depth_cap + (d)])
+#define RTB_CNT_FETCH_RAY(q, d) ((q).counters[2 * (q).depth_cap + (d)])
+#define RTB_CNT_FETCH_SHADOW(q, d) ((q).counters[3 * (q).depth_cap + (d)])
+
+}  // namespace rtb

@@ -1,0 +1,261 @@
+// trace.cuh — device functions of the per-pixel path: ray generation, BVH traversal (reference-shape and LBVH),
+// Möller–Trumbore, shading and continuation.  Every function cites the lines of Assets/Shaders/BVHRayTracing.compute it
+// restates; operation order follows that file token by token because the arithmetic spec forbids re-association.
+#pragma once
+#include "rtb_device.cuh"
+
+namespace rtb {
+
+struct Ray { f3 o, d, inv; };
+// CreateRay, compute:137-144
+__device__ __forceinline__ Ray make_ray(f3 o, f3 d) {
+  Ray r; r.o = o; r.d = d; r.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); return r;
+}
+
+struct Hit { float t, u, v; int32_t tri; };  // tri: leaf-order triangle index, -1 = miss
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Hashes (compute:108-131).  cos/sin of RandomUnitVector use a fixed FP32 polynomial so that CPU checker and GPU agree
+// bit for bit; everything else is + - * floor sqrt.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hash22(float px, float py, float& ox, float& oy) {
+  float a = hlsl_frac(px * .1031f), b = hlsl_frac(py * .1030f), c = hlsl_frac(px * .0973f);
+  const float d = dot3(mk3(a, b, c), mk3(b + 33.33f, c + 33.33f, a + 33.33f));
+  a = a + d; b = b + d; c = c + d;
+  ox = hlsl_frac((a + b) * c);
+  oy = hlsl_frac((a + c) * b);
+}
+__device__ __forceinline__ f3 hash33(f3 p) {
+  p = mk3(hlsl_frac(p.x * .1031f), hlsl_frac(p.y * .1030f), hlsl_frac(p.z * .0973f));
+  const float d = dot3(p, mk3(p.y + 33.33f, p.x + 33.33f, p.z + 33.33f));
+  p = mk3(p.x + d, p.y + d, p.z + d);
+  return mk3(hlsl_frac((p.x + p.y) * p.z), hlsl_frac((p.x + p.x) * p.y), hlsl_frac((p.y + p.x) * p.x));
+}
+__device__ __forceinline__ void det_sincos(float a, float& s_out, float& c_out) {
+  const int k = (int)floorf(a * 0.63661975f);
+  const float r = a - (float)k * 1.5707964f;
+  const float r2 = r * r;
+  const float s = r * (1.0f + r2 * (-1.6666667e-1f + r2 * (8.3333338e-3f + r2 * (-1.9841270e-4f + r2 * (2.7557319e-6f + r2 * -2.5052108e-8f)))));
+  const float c = 1.0f + r2 * (-0.5f + r2 * (4.1666668e-2f + r2 * (-1.3888889e-3f + r2 * (2.4801587e-5f + r2 * (-2.7557319e-7f + r2 * 2.0876757e-9f)))));
+  switch (k & 3) {
+    case 0: s_out = s; c_out = c; break;
+    case 1: s_out = c; c_out = -s; break;
+    case 2: s_out = -s; c_out = -c; break;
+    default: s_out = -c; c_out = s; break;
+  }
+}
+__device__ __forceinline__ f3 random_unit_vector(f3 seed) {
+  const f3 h = hash33(seed);
+  const float z = h.z * 2.0f - 1.0f;
+  const float a = h.x * 6.2831853f;
+  const float r = sqrtf(1.0f - z * z);
+  float s, c;
+  det_sincos(a, s, c);
+  return mk3(r * c, r * s, z);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Ray generation, CSMain compute:283-349.  sample >= 0: AA sample (jitter + motion blur apply); sample == -1: pixel-centre
+// ray under the current projection (rtb_render_aux); sample == -2: the always-perspective centre ray of the debug views
+// (:486-489).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Ray generate_ray(const FrameParams& f, int px, int py, int sample) {
+  const float width = (float)f.width, height = (float)f.height;
+  const float aspect = width / height;
+  const float half_height = f.cam_dist * f.tan_half;
+  const float plane_height = 2.0f * half_height;
+  const float plane_width = plane_height * aspect;
+  float ox = 0.5f, oy = 0.5f;
+  if (sample >= 0 && f.spp > 1) {
+    const int gy = sample / f.grid_w, gx = sample % f.grid_w;
+    float jx, jy;
+    hash22((float)px + (float)sample * 13.0f, (float)py + (float)sample * 7.0f, jx, jy);
+    ox = ((float)gx + jx) / (float)f.grid_w;
+    oy = ((float)gy + jy) / (float)f.grid_h;
+  }
+  f3 oc, dc;
+  if (f.ortho == 1 && sample >= -1) {
+    const float ohh = f.ortho_size, ohw = ohh * aspect;
+    const float ou = ((((float)px + ox) / width - 0.5f) * 2.0f) * ohw;
+    const float ov = ((((float)py + oy) / height - 0.5f) * 2.0f) * ohh;
+    oc = mk3(ou, ov, f.cam_dist);
+    dc = mk3(0.0f, 0.0f, -1.0f);
+  } else {
+    const float u = (((float)px + ox) / width - 0.5f) * plane_width;
+    const float v = (((float)py + oy) / height - 0.5f) * plane_height;
+    oc = mk3(0.0f, 0.0f, f.cam_dist);
+    dc = hlsl_normalize(mk3(u, v, 0.0f) - oc);
+  }
+  const float* M = f.cam;
+  f3 o = mk3(((M[0] * oc.x + M[1] * oc.y) + M[2] * oc.z) + M[3] * 1.0f,
+             ((M[4] * oc.x + M[5] * oc.y) + M[6] * oc.z) + M[7] * 1.0f,
+             ((M[8] * oc.x + M[9] * oc.y) + M[10] * oc.z) + M[11] * 1.0f);
+  const f3 d = hlsl_normalize(mk3((M[0] * dc.x + M[1] * dc.y) + M[2] * dc.z, (M[4] * dc.x + M[5] * dc.y) + M[6] * dc.z,
+                                  (M[8] * dc.x + M[9] * dc.y) + M[10] * dc.z));
+  if (f.blur == 1 && sample >= 0) {  // :342-349
+    const f3 r = random_unit_vector(mk3((float)px + (float)sample, (float)py, (float)sample));
+    const f3 shake = ((r - mk3(0.5f, 0.5f, 0.5f)) * 0.2f) * f.shutter;
+    o = o + shake;
+  }
+  return make_ray(o, d);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Intersection primitives
+// ---------------------------------------------------------------------------------------------------------------------
+// IntersectAABB, compute:199-216
+__device__ __forceinline__ float slab_entry(const Ray& r, f3 mn, f3 mx) {
+  const f3 t0 = (mn - r.o) * r.inv, t1 = (mx - r.o) * r.inv;
+  const float dst_a = fmaxf(fmaxf(fminf(t0.x, t1.x), fminf(t0.y, t1.y)), fminf(t0.z, t1.z));
+  const float dst_b = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
+  if (dst_a > dst_b || dst_b < 0.0f) return RTB_INFINITY;
+  return dst_a;
+}
+
+// IntersectTriangle, compute:153-190, on the stored (v0, e1 = v1-v0, e2 = v2-v0).  Returns true and t,u,v when the
+// triangle is hit with t > Epsilon; the caller applies its own upper bound (closest: t < best.t; shadow: t <= dist).
+__device__ __forceinline__ bool moller_trumbore(const Ray& r, f3 v0, f3 e1, f3 e2, float& t, float& u, float& v) {
+  const f3 pvec = cross3(r.d, e2);
+  const float det = dot3(e1, pvec);
+  if (fabsf(det) < RTB_EPSILON) return false;
+  const float inv_det = 1.0f / det;
+  const f3 tvec = r.o - v0;
+  u = dot3(tvec, pvec) * inv_det;
+  if (u < 0.0f || u > 1.0f) return false;
+  const f3 qvec = cross3(tvec, e1);
+  v = dot3(r.d, qvec) * inv_det;
+  if (v < 0.0f || u + v > 1.0f) return false;
+  t = dot3(e2, qvec) * inv_det;
+  return t > RTB_EPSILON;
+}
+
+__device__ __forceinline__ void test_triangle_closest(const SceneView& s, const Ray& r, int32_t tri, Hit& best) {
+  const float4 a = __ldg(&s.tri_isect[3 * tri]), b = __ldg(&s.tri_isect[3 * tri + 1]), c = __ldg(&s.tri_isect[3 * tri + 2]);
+  float t, u, v;
+  if (moller_trumbore(r, mk3(a), mk3(b), mk3(c), t, u, v) && t < best.t) { best.t = t; best.u = u; best.v = v; best.tri = tri; }
+}
+__device__ __forceinline__ bool test_triangle_any(const SceneView& s, const Ray& r, int32_t tri, float t_limit) {
+  const float4 a = __ldg(&s.tri_isect[3 * tri]), b = __ldg(&s.tri_isect[3 * tri + 1]), c = __ldg(&s.tri_isect[3 * tri + 2]);
+  float t, u, v;
+  return moller_trumbore(r, mk3(a), mk3(b), mk3(c), t, u, v) && t <= t_limit;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Reference traversal, TraverseBVH compute:225-267: LIFO stack, left child first, no distance ordering, a node is culled
+// when its slab entry distance >= the best t so far.  ANY = shadow query: stops at the first triangle with
+// Epsilon < t <= t_limit, which decides "lit" exactly like the reference's closest-hit test (:403-406): lit <=> no such hit.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool ANY>
+__device__ __forceinline__ bool traverse_reference(const SceneView& s, const Ray& r, float t_limit, Hit& best, unsigned& overflow) {
+  best.t = RTB_INFINITY; best.u = 0.0f; best.v = 0.0f; best.tri = -1;
+  if (s.n_nodes == 0) return false;
+  int32_t stack[RTB_STACK_REF];
+  int sp = 0;
+  stack[sp++] = 0;
+  while (sp > 0) {
+    const int32_t ni = stack[--sp];
+    const float4 lo = __ldg(&s.nodes[2 * ni]), hi = __ldg(&s.nodes[2 * ni + 1]);
+    const float dst = slab_entry(r, mk3(lo), mk3(hi));
+    if (ANY ? (dst > t_limit) : (dst >= best.t)) continue;
+    const int32_t count = __float_as_int(hi.w), left_or_first = __float_as_int(lo.w);
+    if (count > 0) {
+      for (int32_t i = 0; i < count; i++) {
+        if (ANY) { if (test_triangle_any(s, r, left_or_first + i, t_limit)) return true; }
+        else test_triangle_closest(s, r, left_or_first + i, best);
+      }
+    } else if (sp + 2 <= RTB_STACK_REF) {
+      stack[sp++] = left_or_first + 1;
+      stack[sp++] = left_or_first;
+    } else {
+      overflow++;
+    }
+  }
+  return best.tri >= 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LBVH traversal: 64-byte nodes holding both children's boxes, near child first, deferred child kept with its entry
+// distance so it can be dropped without a fetch once a closer hit is known.  Box and triangle arithmetic is the same as
+// above, so t/u/v of a given (ray, triangle) pair are bit-identical in both modes.
+// Node layout (4 x float4): (lmin, left_ref) (lmax, right_ref) (rmin, -) (rmax, -).
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool ANY>
+__device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, float t_limit, Hit& best, unsigned& overflow) {
+  best.t = RTB_INFINITY; best.u = 0.0f; best.v = 0.0f; best.tri = -1;
+  if (s.n_tris == 0) return false;
+  int32_t stack_ref[RTB_STACK_LBVH];
+  float stack_dst[RTB_STACK_LBVH];
+  int sp = 0;
+  int32_t cur = s.root;
+  for (;;) {
+    if (cur >= 0) {
+      const float4 n0 = __ldg(&s.nodes[4 * cur]), n1 = __ldg(&s.nodes[4 * cur + 1]);
+      const float4 n2 = __ldg(&s.nodes[4 * cur + 2]), n3 = __ldg(&s.nodes[4 * cur + 3]);
+      const float dl = slab_entry(r, mk3(n0), mk3(n1));
+      const float dr = slab_entry(r, mk3(n2), mk3(n3));
+      const bool hl = ANY ? !(dl > t_limit) : !(dl >= best.t);
+      const bool hr = ANY ? !(dr > t_limit) : !(dr >= best.t);
+      const int32_t lref = __float_as_int(n0.w), rref = __float_as_int(n1.w);
+      if (hl && hr) {
+        const bool left_first = !(dr < dl);
+        const int32_t far_ref = left_first ? rref : lref;
+        const float far_dst = left_first ? dr : dl;
+        cur = left_first ? lref : rref;
+        if (sp < RTB_STACK_LBVH) { stack_ref[sp] = far_ref; stack_dst[sp] = far_dst; sp++; }
+        else overflow++;
+        continue;
+      }
+      if (hl) { cur = lref; continue; }
+      if (hr) { cur = rref; continue; }
+    } else {
+      const int32_t code = ~cur;
+      const int32_t first = code >> 3, count = (code & 7) + 1;
+      for (int32_t i = 0; i < count; i++) {
+        if (ANY) { if (test_triangle_any(s, r, first + i, t_limit)) return true; }
+        else test_triangle_closest(s, r, first + i, best);
+      }
+    }
+    // pop the next deferred child that can still matter
+    for (;;) {
+      if (sp == 0) return best.tri >= 0;
+      sp--;
+      const float d = stack_dst[sp];
+      if (ANY ? !(d > t_limit) : !(d >= best.t)) { cur = stack_ref[sp]; break; }
+    }
+  }
+}
+
+template <int BVH, bool ANY>
+__device__ __forceinline__ bool traverse(const SceneView& s, const Ray& r, float t_limit, Hit& best, unsigned& overflow) {
+  if (BVH == RTB_BVH_REFERENCE) return traverse_reference<ANY>(s, r, t_limit, best, overflow);
+  return traverse_lbvh<ANY>(s, r, t_limit, best, overflow);
+}
+
+// Interpolated normal of a hit, compute:186-187
+__device__ __forceinline__ f3 hit_normal(const SceneView& s, const Hit& h) {
+  const float4 n0 = __ldg(&s.tri_shade[3 * h.tri]), n1 = __ldg(&s.tri_shade[3 * h.tri + 1]), n2 = __ldg(&s.tri_shade[3 * h.tri + 2]);
+  const float w = 1.0f - h.u - h.v;
+  return hlsl_normalize((w * mk3(n0) + h.u * mk3(n1)) + h.v * mk3(n2));
+}
+
+struct Material { f3 color; float ka, kd, ks, kr, ior; };
+// compute:371-376; an index outside the material buffer takes the same defaults
+__device__ __forceinline__ Material fetch_material(const SceneView& s, int32_t index) {
+  Material m;
+  m.color = mk3(1.0f, 1.0f, 1.0f); m.ka = 0.1f; m.kd = 0.7f; m.ks = 0.0f; m.kr = 0.0f; m.ior = 1.0f;
+  if (index >= 0 && index < s.n_mats) {
+    const float4 a = __ldg(&s.materials[2 * index]), b = __ldg(&s.materials[2 * index + 1]);
+    m.color = mk3(a); m.ka = a.w; m.kd = b.x; m.ks = b.y; m.kr = b.z; m.ior = b.w;
+  }
+  return m;
+}
+
+// byte = floor(saturate(c) * 255 + 0.5); NaN -> 0.  srgb != 0 applies the sRGB OETF first.
+__device__ __forceinline__ unsigned quantize_unorm8(float c, int srgb) {
+  if (!(c == c)) c = 0.0f;
+  c = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
+  if (srgb) c = c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+  return (unsigned)(int)floorf(c * 255.0f + 0.5f);
+}
+
+}  // namespace rtb

@@ -177,6 +177,25 @@ void rtb_free_pinned(void* p);
  * `dst_device`.  Opened pointers are closed by rtb_destroy. */
 int rtb_frame_export(rtb_context* ctx, size_t bytes, void** dev_ptr, uint8_t handle64[64]);
 int rtb_frame_import(rtb_context* ctx, const uint8_t handle64[64], void** dev_ptr);
+/* ReadPixels (RayTracer.cs:371-375) of the context's own frame buffer — the one rtb_frame_export shares — after the
+ * peers have stored their bands into it. */
+int rtb_frame_read(rtb_context* ctx, uint8_t* rgba8, size_t bytes);
+
+/* Parity/debug access to the acceleration structure of the uploaded scene: nodes as stored on the device (reference
+ * mode: 8 words per node = GPUBVHNode, BVHBuilder.cs:27-34; LBVH mode: 16 words per node) and the
+ * leaf-order -> emission-order triangle permutation (the reference declares it as BVHResult.triangleIndices,
+ * BVHBuilder.cs:67, but never fills it). */
+int rtb_get_bvh(rtb_context* ctx, void* nodes, int64_t nodes_capacity_bytes, int64_t* n_nodes, int32_t* perm, int64_t perm_capacity);
+
+/* Host-only helpers (no CUDA device needed; used by the CPU test-suite and by hosts that want the uniforms).
+ * rtb_resolve_frame: what RayTracer.cs:221-355 resolves from (scene, settings): out25 = cameraToObject (row-major 4x4),
+ *   _CameraDistance, tan(fov/2), _OrthoSize, _LightPosition xyz, _BackgroundColor rgb; wh = width, height.
+ * rtb_build_reference_bvh: BVHBuilder.Build (BVHBuilder.cs:76-95) on caller-provided triangles, 12 floats each
+ *   (v0.xyz, c.x, v1.xyz, c.y, v2.xyz, c.z); nodes8 = 8 words per node, perm = leaf order -> input index.
+ * rtb_abi_sizes: sizeof of the 8 public structs in declaration order, for binding self-checks. */
+int rtb_resolve_frame(const rtb_scene_desc* scene, const rtb_render_params* p, float* out25, int32_t* wh);
+int rtb_build_reference_bvh(const float* raw12, int32_t n, float* nodes8, int64_t nodes_capacity, int64_t* n_nodes, int32_t* perm);
+void rtb_abi_sizes(int32_t* out, int32_t n);
 
 /* SceneService.LoadScene, Assets/Services/SceneService.cs:26-242: parses the COSIG scene text format.  The returned
  * object owns its arrays; rtb_scene_get gives a desc view valid until rtb_scene_free. */

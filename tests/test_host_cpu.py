@@ -1,0 +1,289 @@
+"""CPU-only tests: the oracle against its committed goldens, the host logic of the library (uniform resolve, reference
+BVH build, scene parser, band arithmetic) against the oracle, and that the C-ABI library loads and exports every symbol
+include/rtb.h declares.  No compute call needs a GPU here."""
+import ctypes as C
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from util import GOLDEN, REFERENCE_SCENES, abi, oracle_scene, params, scene_mod, synth, tiny_scene
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ---- the oracle is pinned by its goldens -------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", synth.SAMPLE_SCENES)
+def test_oracle_reproduces_goldens(oracle, name):
+    summary = json.load(open(os.path.join(GOLDEN, "summary.json")))[name]
+    osc, holder = oracle_scene(oracle, synth.sample_scene(name))
+    assert (osc.n_triangles, osc.n_nodes, osc.max_leaf) == (summary["n_triangles"], summary["n_nodes"], summary["max_leaf"])
+    vn, mat, cen = osc.triangles()
+    nodes, perm = osc.bvh()
+    assert sha(vn) == summary["sha_triangles"] and sha(mat) == summary["sha_materials"] and sha(cen) == summary["sha_centers"]
+    assert sha(nodes) == summary["sha_nodes"] and sha(perm) == summary["sha_perm"]
+    g = np.load(os.path.join(GOLDEN, name + "_c1.npz"))
+    r = osc.render(params(320, 240, 3), want_aux=True, want_rgbf=True)
+    assert (r["prim"] == g["prim"]).all() and (r["mat"] == g["mat"]).all()
+    assert (r["t"].view(np.uint32) == g["t"].view(np.uint32)).all()
+    assert (r["rgba8"] == g["rgba8"]).all() and sha(r["rgbf"]) == summary["sha_rgbf"]
+    c = r["counters"]
+    for k in ("rays_primary", "rays_continuation", "rays_shadow", "primary_hits", "nodes_visited", "tris_tested", "max_stack"):
+        assert getattr(c, k) == summary[k], k
+    assert (osc.render(params(320, 240, 3, 4))["rgba8"] == g["rgba8_aa4"]).all()
+
+
+def test_oracle_thread_count_does_not_change_results(oracle):
+    osc, holder = oracle_scene(oracle, synth.sample_scene("test_scene_1"))
+    a = osc.render(params(160, 120, 4, 4), threads=1)
+    b = osc.render(params(160, 120, 4, 4), threads=0)
+    assert (a["rgba8"] == b["rgba8"]).all() and a["counters"].rays == b["counters"].rays
+
+
+def test_oracle_closest_hit_agrees_with_brute_force(oracle):
+    """The BVH traversal of the oracle finds the same closest t as testing every triangle (float64-free property check)."""
+    osc, holder = oracle_scene(oracle, synth.sample_scene("eval_scene"))
+    p = params(64, 48, 1)
+    r = osc.render(p, want_aux=True)
+    for y in range(0, 48, 5):
+        for x in range(0, 64, 7):
+            o, d = osc.primary_ray(p, x, y)
+            t, ids, n = osc.brute_closest(o, d)
+            if n == 0:
+                assert r["prim"][y, x] == -1
+            else:
+                assert np.float32(t).view(np.uint32) == r["t"][y, x].view(np.uint32) and r["prim"][y, x] in ids
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_SCENES), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("name", synth.SAMPLE_SCENES)
+def test_packed_scenes_match_reference_files(oracle, name):
+    a = oracle.OracleScene.from_file(os.path.join(REFERENCE_SCENES, name + ".txt"))
+    b, holder = oracle_scene(oracle, synth.sample_scene(name))
+    for x, y in zip(a.triangles(), b.triangles()):
+        assert x.tobytes() == y.tobytes()
+    p = params(96, 72, 3)
+    assert (a.frame(p) == b.frame(p)).all()
+
+
+# ---- C ABI --------------------------------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol(pkg):
+    lib = abi.load()
+    header = open(os.path.join(ROOT, "include", "rtb.h")).read()
+    declared = set(re.findall(r"^(?:int|void\*?|const [a-z_ ]+\*)\s+(rtb_[a-z0-9_]+)\s*\(", header, re.M))
+    assert len(declared) >= 29
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in rtb.h but not exported"
+    assert declared == set(abi.SYMBOLS), declared ^ set(abi.SYMBOLS)
+    assert lib.rtb_api_version() == 1
+
+
+def test_struct_sizes_match_the_library(pkg):
+    lib = abi.load()
+    sizes = (C.c_int32 * 8)()
+    lib.rtb_abi_sizes(sizes, 8)
+    mine = [C.sizeof(t) for t in (abi.XformElem, abi.Material, abi.Triangle, abi.Mesh, abi.Prim, abi.SceneDesc, abi.RenderParams, abi.Stats)]
+    assert list(sizes) == mine
+
+
+def test_params_default_matches_reference_ui_defaults(pkg):
+    lib = abi.load()
+    p = abi.RenderParams()
+    lib.rtb_params_default(C.byref(p))
+    q = abi.default_params()
+    assert bytes(p) == bytes(q)
+    assert bytes(scene_mod.RenderSettings().to_params()) == bytes(q)
+
+
+def test_no_gpu_means_an_error_not_a_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = abi.load()
+    ctx = C.c_void_p()
+    assert lib.rtb_create(C.byref(ctx), None, 0) == abi.RTB_E_CUDA
+    assert b"no CPU fallback" in lib.rtb_last_error(None)
+    rt_mod = __import__("importlib").import_module("cosig-raytracing_b200.raytracer")
+    with pytest.raises(rt_mod.RtbError):
+        rt_mod.RayTracer()
+
+
+# ---- host logic against the oracle -----------------------------------------------------------------------------------------
+SETTINGS = [
+    dict(), dict(has_fov=1, fov_deg=47.5), dict(has_bg=1, bg=(0.3, 0.5, 0.7)),
+    dict(has_cam_pos=1, cam_pos=(3.0, -50.0, 20.0)), dict(has_cam_rot=1, cam_rot_euler_deg=(-35.0, 20.0, 170.0)),
+    dict(has_cam_pos=1, cam_pos=(1.0, 2.0, 3.0), has_cam_rot=1, cam_rot_euler_deg=(10.0, 350.0, -45.0)),
+    dict(is_orthographic=1, aa_samples=5),
+]
+
+
+@pytest.mark.parametrize("name", synth.SAMPLE_SCENES)
+@pytest.mark.parametrize("kw", SETTINGS)
+def test_resolve_frame_bit_identical_to_oracle(pkg, oracle, name, kw):
+    lib = abi.load()
+    obj = synth.sample_scene(name)
+    osc, holder = oracle_scene(oracle, obj)
+    for has_res in (1, 0):
+        p = params(**kw)
+        p.has_resolution = has_res
+        out = np.zeros(25, np.float32)
+        wh = (C.c_int32 * 2)()
+        assert lib.rtb_resolve_frame(holder.ptr(), C.byref(p), out.ctypes.data_as(C.POINTER(C.c_float)), wh) == abi.RTB_OK
+        assert out.view(np.uint32).tobytes() == osc.frame(p).view(np.uint32).tobytes()
+        assert (wh[0], wh[1]) == osc.resolve(p)
+
+
+def test_resolve_frame_defaults_without_image_camera_light(pkg, oracle):
+    lib = abi.load()
+    s = tiny_scene(3)
+    s.Image, s.Camera, s.Lights = None, None, []
+    osc, holder = oracle_scene(oracle, s)
+    p = abi.default_params()
+    out = np.zeros(25, np.float32)
+    wh = (C.c_int32 * 2)()
+    assert lib.rtb_resolve_frame(holder.ptr(), C.byref(p), out.ctypes.data_as(C.POINTER(C.c_float)), wh) == abi.RTB_OK
+    assert (wh[0], wh[1]) == (256, 256) == osc.resolve(p)
+    assert out.tobytes() == osc.frame(p).tobytes()
+    assert tuple(out[22:25]) == (np.float32(0.2),) * 3 and tuple(out[19:22]) == (0.0, 0.0, 0.0)
+
+
+def test_resolve_frame_rejects_bad_parameters(pkg):
+    lib = abi.load()
+    holder = scene_mod.pack_scene(tiny_scene(1))
+    for kw in (dict(depth=65), dict(depth=-1), dict(width=0), dict(aa=5000), dict(band_world=2, band_rank=2), dict(band_world=2, band_rows=6)):
+        assert lib.rtb_resolve_frame(holder.ptr(), C.byref(params(**kw)), None, None) == abi.RTB_E_ARG, kw
+
+
+def _raw12(vn, cen):
+    raw = np.zeros((vn.shape[0], 12), np.float32)
+    for k in range(3):
+        raw[:, 4 * k:4 * k + 3] = vn[:, 3 * k:3 * k + 3]
+        raw[:, 4 * k + 3] = cen[:, k]
+    return raw
+
+
+@pytest.mark.parametrize("scene_name", list(synth.SAMPLE_SCENES) + ["heightfield", "spheres", "tiny1", "tiny5"])
+def test_reference_bvh_builder_matches_oracle(pkg, oracle, scene_name):
+    lib = abi.load()
+    obj = {"heightfield": lambda: synth.heightfield_scene(40, 30), "spheres": lambda: synth.sphere_grid_scene(3),
+           "tiny1": lambda: tiny_scene(1), "tiny5": lambda: tiny_scene(5)}.get(scene_name, lambda: synth.sample_scene(scene_name))()
+    osc, holder = oracle_scene(oracle, obj)
+    vn, mat, cen = osc.triangles()
+    raw = _raw12(vn, cen)
+    n = raw.shape[0]
+    nodes = np.zeros((2 * n + 1, 8), np.float32)
+    perm = np.zeros(n, np.int32)
+    nn = C.c_int64()
+    assert lib.rtb_build_reference_bvh(raw.ctypes.data, n, nodes.ctypes.data, nodes.shape[0], C.byref(nn), perm.ctypes.data) == abi.RTB_OK
+    onodes, operm = osc.bvh()
+    assert nn.value == onodes.shape[0]
+    assert nodes[:nn.value].view(np.uint32).tobytes() == onodes.view(np.uint32).tobytes()
+    assert (perm == operm).all()
+
+
+# ---- scene text parser --------------------------------------------------------------------------------------------------------
+def _same_scene(a: scene_mod.ObjectData, b: scene_mod.ObjectData):
+    pa, pb = scene_mod.pack_scene(a), scene_mod.pack_scene(b)
+    assert pa.xoff.tobytes() == pb.xoff.tobytes() and bytes(pa.xel)[:20 * max(0, pa.xoff[-1])] == bytes(pb.xel)[:20 * max(0, pb.xoff[-1])]
+    assert pa.tri.tobytes() == pb.tri.tobytes() and pa.mats.tobytes() == pb.mats.tobytes()
+    assert pa.sph.tobytes() == pb.sph.tobytes() and pa.box.tobytes() == pb.box.tobytes()
+    assert pa.lxf.tobytes() == pb.lxf.tobytes() and pa.lrgb.tobytes() == pb.lrgb.tobytes()
+    for f in ("has_image", "image_w", "image_h", "has_camera", "cam_xform", "cam_distance", "cam_vfov_deg", "n_xforms", "n_lights",
+              "n_materials", "n_meshes", "n_triangles", "n_spheres", "n_boxes"):
+        assert getattr(pa.desc, f) == getattr(pb.desc, f), f
+    assert tuple(pa.desc.bg) == tuple(pb.desc.bg)
+
+
+@pytest.mark.parametrize("name", synth.SAMPLE_SCENES)
+def test_native_parser_round_trips_sample_scenes(pkg, oracle, name):
+    rt_mod = __import__("importlib").import_module("cosig-raytracing_b200.raytracer")
+    obj = synth.sample_scene(name)
+    text = synth.scene_to_text(obj).encode()
+    parsed = rt_mod.SceneService.ParseScene(text)
+    _same_scene(obj, parsed)
+    # and the oracle's own restatement of SceneService reads the same text the same way
+    a = oracle.OracleScene.from_text(text)
+    b, holder = oracle_scene(oracle, parsed)
+    for x, y in zip(a.triangles(), b.triangles()):
+        assert x.tobytes() == y.tobytes()
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_SCENES), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("name", synth.SAMPLE_SCENES)
+def test_native_parser_reads_reference_files(pkg, name):
+    rt_mod = __import__("importlib").import_module("cosig-raytracing_b200.raytracer")
+    _same_scene(rt_mod.SceneService.LoadScene(os.path.join(REFERENCE_SCENES, name + ".txt")), synth.sample_scene(name))
+
+
+def test_parser_tolerances_and_errors(pkg):
+    rt_mod = __import__("importlib").import_module("cosig-raytracing_b200.raytracer")
+    text = (b"// a comment line\r\n\r\nIMAGE\r\n\r\n{\r\n\t 32  24 // res\r\n 0.1\t0.2 0.3\r\n}\r\n"
+            b"transformation\n{\n T 1 2 3\n Bogus 1 2\n\n Rz 1e1\n}\n"
+            b"Unknown\n{\n 1 2 3\n}\n"
+            b"Camera\n{\n0\n30\n45.5\n}\nLight\n{\n0\n1 1 1\n}\nMaterial\n{\n1 0 0\n0.1 0.2 0.3 0.4 1.5\n}\n"
+            b"Triangles\n{\n0\n\n0\n0 0 0\n1 0 0\n0 1 0\n}\nSphere\n{\n0\n0\n}\nbox\n{\n0\n0\n}")
+    s = rt_mod.SceneService.ParseScene(text)
+    assert (s.Image.horizontal, s.Image.vertical) == (32, 24) and s.Image.background == pytest.approx((0.1, 0.2, 0.3))
+    assert len(s.Transformations) == 1 and [e.Type for e in s.Transformations[0].Elements] == [abi.RTB_XF_T, abi.RTB_XF_RZ]
+    assert s.Transformations[0].Elements[1].AngleDeg == 10.0
+    assert s.Camera.verticalFovDeg == 45.5 and len(s.Lights) == 1 and len(s.Materials) == 1 and s.Materials[0].ior == 1.5
+    assert s.TriangleMeshes[0].materials.tolist() == [0] and len(s.Spheres) == 1 and len(s.Boxes) == 1
+    with pytest.raises(rt_mod.RtbError) as e:
+        rt_mod.SceneService.ParseScene(b"Camera\n{\n0\nabc\n30\n}\n")
+    assert e.value.code == abi.RTB_E_PARSE
+    with pytest.raises(rt_mod.RtbError):
+        rt_mod.SceneService.ParseScene(b"Triangles\n{\n0\n1\n0 0 0\n1 0 0\n")  # truncated triangle
+    empty = rt_mod.SceneService.LoadScene("/nonexistent/scene.txt")  # missing file -> empty ObjectData (SceneService.cs:28-33)
+    assert empty.Image is None and not empty.TriangleMeshes
+    assert not rt_mod.SceneService.ParseScene(b"").Transformations
+
+
+# ---- band arithmetic and the world-size-2 gather (gloo) ------------------------------------------------------------------------
+def test_band_partition_covers_every_row_once():
+    bands = __import__("importlib").import_module("cosig-raytracing_b200.bands")
+    for h in (1, 31, 32, 33, 150, 2160, 4320):
+        for world in (1, 2, 3, 4, 8):
+            for band_rows in (4, 16, 32):
+                seen = np.zeros(h, np.int32)
+                for rank in range(world):
+                    rows = bands.owned_rows(h, rank, world, band_rows)
+                    assert len(rows) == bands.local_row_count(h, rank, world, band_rows)
+                    seen[rows] += 1
+                assert (seen == 1).all()
+
+
+def _gloo_worker(rank, world, port, h, w, out_q):
+    import importlib
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    bands = importlib.import_module("cosig-raytracing_b200.bands")
+    full = (np.arange(h * w * 4, dtype=np.int64) % 251).astype(np.uint8).reshape(h, w, 4)  # the frame every rank would render
+    mine = torch.from_numpy(full[bands.owned_rows(h, rank, world, 32)].copy())
+    frame = bands.gather_bands(mine, h, w, rank, world, 32, dst=0)
+    if rank == 0:
+        out_q.put(bool((frame.numpy() == full).all()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("h", [64, 150])
+def test_gather_bands_world_size_2_gloo(h):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + h) % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, h, 48, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
