@@ -297,7 +297,7 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
     if (f.max_depth <= 0) {  // the depth loop never runs: sampleColor stays 0
       CK(ctx, cudaMemsetAsync(qv.accum, 0, (size_t)c.n_slots * sizeof(float4), d.stream));
     } else {
-      CK(ctx, cudaMemsetAsync(d.q.counters, 0, (size_t)depth_cap * 4 * sizeof(int32_t), d.stream));
+      CK(ctx, cudaMemsetAsync(d.q.counters, 0, (size_t)d.q.depth_cap * 4 * sizeof(int32_t), d.stream));
       for (int depth = 0; depth < f.max_depth; depth++) {
         if (depth > 0 && ctx->cancel && *ctx->cancel) { cudaStreamSynchronize(d.stream); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
         timed(0, [&] { launch_trace_shade(bvh, depth == 0, f, sv, qv, c, depth, d.grid_trace[bvh][depth == 0], d.stream); });

@@ -2,7 +2,7 @@
 // (replaces SceneGeometryConverter.ExtractTriangles, Assets/Services/SceneGeometryConverter.cs:18-264, which appends to a
 // C# list on the CPU), and the gather into BVH leaf order (BVHBuilder.Flatten's triangle re-emission,
 // Assets/Services/BVH/BVHBuilder.cs:224-227).  One thread per emitted triangle; the composite matrices, inverse-transpose
-// normal matrices and the 410-vertex unit-sphere table come from the host (they need libm), everything here is
+// normal matrices and the 402-vertex unit-sphere table come from the host (they need libm), everything here is
 // + - * / sqrt in the reference's operation order, so the arrays are bit-identical to the CPU restatement's.
 #include "kernels.hpp"
 

@@ -10,7 +10,7 @@ namespace rtb {
 
 // ---- flatten.cu (K1: scene upload) ------------------------------------------------------------------------------------
 // tri_in: device copy of the caller's rtb_triangle array (10 words each); objs: device FlattenObject table;
-// sphere_table: 410 float3 on the device.  Writes, in emission order, raw[3i..] = (v0,c.x)(v1,c.y)(v2,c.z) and
+// sphere_table: 402 float3 on the device.  Writes, in emission order, raw[3i..] = (v0,c.x)(v1,c.y)(v2,c.z) and
 // nrm[3i..] = (n0,material)(n1,0)(n2,0).
 void launch_flatten(const float* tri_in, const FlattenObject* objs, int n_objs, const float* sphere_table, int32_t n_out, float4* raw,
                     float4* nrm, cudaStream_t st);

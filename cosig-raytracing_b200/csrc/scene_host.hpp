@@ -54,9 +54,9 @@ static_assert(sizeof(FlattenObject) == 112, "FlattenObject layout");
 // Builds the object table; returns the total emitted triangle count (or -1 if it exceeds int32).
 int64_t build_object_table(const rtb_scene_desc& s, std::vector<FlattenObject>& out);
 
-// The 410 unit-sphere vertices of AddSphere (SceneGeometryConverter.cs:161-190), xyz per vertex.
-const float* unit_sphere_table();  // 410 * 3 floats
-constexpr int kSphereVerts = 410;
+// The 402 unit-sphere vertices of AddSphere (SceneGeometryConverter.cs:161-190), xyz per vertex.
+const float* unit_sphere_table();  // 402 * 3 floats
+constexpr int kSphereVerts = 402;  // (24 + 1) * 16 + 2, SceneGeometryConverter.cs:168
 constexpr int kSphereTris = 768;
 constexpr int kBoxTris = 12;
 
