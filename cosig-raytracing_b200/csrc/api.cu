@@ -676,6 +676,11 @@ int rtb_synchronize(rtb_context* ctx) {
   return RTB_OK;
 }
 
+void* rtb_get_stream(rtb_context* ctx, int32_t index) {
+  if (!ctx || index < 0 || index >= (int32_t)ctx->devs.size()) return nullptr;
+  return (void*)ctx->devs[(size_t)index].stream;
+}
+
 void* rtb_alloc_pinned(size_t bytes) {
   void* p = nullptr;
   if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -243,6 +243,10 @@ class RayTracer:
     def set_profiling(self, on: bool):
         self._check(self._lib.rtb_set_profiling(self._ctx, 1 if on else 0))
 
+    def stream(self, index: int = 0) -> int:
+        """cudaStream_t of device `index` (wrap with torch.cuda.ExternalStream to record events on it)."""
+        return self._lib.rtb_get_stream(self._ctx, index)
+
     def synchronize(self):
         self._check(self._lib.rtb_synchronize(self._ctx))
 

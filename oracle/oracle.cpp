@@ -573,6 +573,7 @@ struct Hit { bool hit; float t; int tri; float u, v; };  // HitRecord :22-29 (po
 
 struct Counters {
   int64_t rays_primary = 0, rays_continuation = 0, rays_shadow = 0, nodes_visited = 0, tris_tested = 0, closest_hits = 0, primary_hits = 0;
+  int64_t nodes_visited_shadow = 0, tris_tested_shadow = 0;  // the share of nodes_visited / tris_tested spent in shadow queries
   int max_stack = 0;
 };
 
@@ -757,7 +758,10 @@ static V3 trace_sample(const Scene& sc, const Frame& f, int px, int py, int i, C
       Ray sr; sr.o = pos + n * kOffset; sr.d = lightDir; sr.inv = v3(1.0f / lightDir.x, 1.0f / lightDir.y, 1.0f / lightDir.z);
       float dist = hlsl_length(toL);
       c.rays_shadow++;
+      const int64_t n0 = c.nodes_visited, t0 = c.tris_tested;
       Hit sh = TraverseBVH(sc, sr, c);
+      c.nodes_visited_shadow += c.nodes_visited - n0;
+      c.tris_tested_shadow += c.tris_tested - t0;
       if (!sh.hit || sh.t > dist) {
         local = local + (col * kd) * NdotL;
         if (f.spec == 1 && ks > 0.0f) {
@@ -822,6 +826,7 @@ typedef struct orc_counters {
   int64_t rays_primary, rays_continuation, rays_shadow, nodes_visited, tris_tested, closest_hits, primary_hits;
   int32_t max_stack, threads;
   double seconds;
+  int64_t nodes_visited_shadow, tris_tested_shadow;
 } orc_counters;
 
 int orc_build(const rtb_scene_desc* d, orc_scene** out) {
@@ -951,6 +956,7 @@ int orc_render(const orc_scene* s, const rtb_render_params* p, int32_t row_begin
       cnt->rays_primary += c.rays_primary; cnt->rays_continuation += c.rays_continuation; cnt->rays_shadow += c.rays_shadow;
       cnt->nodes_visited += c.nodes_visited; cnt->tris_tested += c.tris_tested; cnt->closest_hits += c.closest_hits;
       cnt->primary_hits += c.primary_hits; cnt->max_stack = std::max(cnt->max_stack, c.max_stack);
+      cnt->nodes_visited_shadow += c.nodes_visited_shadow; cnt->tris_tested_shadow += c.tris_tested_shadow;
     }
     cnt->threads = nthreads;
     cnt->seconds = t1 - t0;

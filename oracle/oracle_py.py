@@ -18,7 +18,8 @@ _abi = importlib.import_module("cosig-raytracing_b200.abi")
 class Counters(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("rays_primary", "rays_continuation", "rays_shadow", "nodes_visited", "tris_tested",
                                          "closest_hits", "primary_hits")] + [("max_stack", C.c_int32), ("threads", C.c_int32),
-                                                                             ("seconds", C.c_double)]
+                                                                             ("seconds", C.c_double), ("nodes_visited_shadow", C.c_int64),
+                                                                             ("tris_tested_shadow", C.c_int64)]
 
     @property
     def rays(self):
