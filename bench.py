@@ -314,14 +314,14 @@ def main():
     for _ in range(n_prof):
         step_device(sync=True)
         sp = rt.stats()
-        fam += [sp.ms_trace, sp.ms_shadow, sp.ms_resolve]
+        fam += [sp.ms_traverse, sp.ms_shade, sp.ms_resolve]
     fam /= n_prof
     rt.set_profiling(False)
     sl = rt.stats()
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        roof = {"bound": "hbm", "kernel": "k_trace_shade (closest-hit + shade + queue compaction), all depths of one frame", "achieved": None,
+        roof = {"bound": "hbm", "kernel": "k_traverse (every BVH query of the frame: closest-hit and shadow rays), all depths", "achieved": None,
                 "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -358,7 +358,7 @@ def main():
                             "(RayTracer.cs:118-123); uniforms travel as kernel parameters"},
             "e2e_cold": cold,
             "gpu_launches": launches_frame * args.steps,
-            "kernel_ms_per_frame": {"trace_shade": float(fam[0]), "shadow": float(fam[1]), "resolve": float(fam[2])},
+            "kernel_ms_per_frame": {"traverse": float(fam[0]), "shade": float(fam[1]), "resolve": float(fam[2])},
             "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

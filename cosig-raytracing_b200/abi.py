@@ -89,7 +89,7 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_int32), ("n_devices", C.c_int32),
         ("ms_upload", C.c_float), ("ms_build", C.c_float),
         ("ms_render_device", C.c_float),
-        ("ms_trace", C.c_float), ("ms_shadow", C.c_float), ("ms_resolve", C.c_float),
+        ("ms_traverse", C.c_float), ("ms_shade", C.c_float), ("ms_resolve", C.c_float),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("reserved", C.c_int64 * 4),
     ]

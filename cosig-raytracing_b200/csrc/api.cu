@@ -29,7 +29,7 @@ struct DeviceScene {
 };
 
 struct Queues {
-  float4* base = nullptr;      // one allocation: 11 arrays of capacity slots
+  float4* base = nullptr;      // one allocation: 12 arrays of capacity slots
   int32_t* counters = nullptr;
   unsigned long long* totals = nullptr;
   int32_t capacity = 0, depth_cap = 0;
@@ -48,7 +48,7 @@ struct DeviceState {
   int32_t *aux_prim = nullptr, *aux_mat = nullptr;
   float* aux_t = nullptr;
   size_t aux_px = 0;
-  int grid_trace[2][2] = {{0, 0}, {0, 0}}, grid_shadow[2] = {0, 0};
+  int grid_traverse[2][2] = {{0, 0}, {0, 0}};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_trace, prof_shadow, prof_resolve;
   size_t prof_used[3] = {0, 0, 0};
 };
@@ -113,7 +113,7 @@ int ensure_queues(rtb_context* ctx, DeviceState& d, int32_t capacity, int32_t de
   if (d.q.capacity >= capacity && d.q.depth_cap >= depth_cap) return RTB_OK;
   dfree(d.q.base); dfree(d.q.counters); dfree(d.q.totals);
   d.q = Queues();
-  CK(ctx, cudaMalloc(&d.q.base, (size_t)capacity * 11 * sizeof(float4)));
+  CK(ctx, cudaMalloc(&d.q.base, (size_t)capacity * 12 * sizeof(float4)));
   CK(ctx, cudaMalloc(&d.q.counters, (size_t)depth_cap * 4 * sizeof(int32_t)));
   CK(ctx, cudaMalloc(&d.q.totals, 8 * sizeof(unsigned long long)));
   d.q.capacity = capacity;
@@ -127,7 +127,8 @@ QueueView queue_view(const Queues& q) {
   const size_t c = (size_t)q.capacity;
   v.ray_o[0] = p; v.ray_o[1] = p + c; v.ray_d[0] = p + 2 * c; v.ray_d[1] = p + 3 * c; v.ray_att[0] = p + 4 * c; v.ray_att[1] = p + 5 * c;
   v.sh_o = p + 6 * c; v.sh_d = p + 7 * c; v.sh_lit = p + 8 * c; v.sh_unlit = p + 9 * c;
-  v.accum = p + 10 * c;
+  v.hits = p + 10 * c;
+  v.accum = p + 11 * c;
   v.counters = q.counters;
   v.totals = q.totals;
   v.depth_cap = q.depth_cap;
@@ -265,11 +266,11 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
     const int rc = ensure_queues(ctx, d, capacity, depth_cap);
     if (rc != RTB_OK) return rc;
   }
-  if (!d.grid_trace[bvh][0]) {
-    d.grid_trace[bvh][0] = d.sm_count * trace_blocks_per_sm(bvh, false);
-    d.grid_trace[bvh][1] = d.sm_count * trace_blocks_per_sm(bvh, true);
-    d.grid_shadow[bvh] = d.sm_count * shadow_blocks_per_sm(bvh);
+  if (!d.grid_traverse[bvh][0]) {
+    d.grid_traverse[bvh][0] = d.sm_count * traverse_blocks_per_sm(bvh, false);
+    d.grid_traverse[bvh][1] = d.sm_count * traverse_blocks_per_sm(bvh, true);
   }
+  const int shade_grid = d.sm_count * 8;
   const QueueView qv = queue_view(d.q);
   CK(ctx, cudaEventRecord(d.ev_begin, d.stream));
   if (local_rows > 0) CK(ctx, cudaMemsetAsync(d.q.totals, 0, 8 * sizeof(unsigned long long), d.stream));
@@ -298,10 +299,13 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
       CK(ctx, cudaMemsetAsync(qv.accum, 0, (size_t)c.n_slots * sizeof(float4), d.stream));
     } else {
       CK(ctx, cudaMemsetAsync(d.q.counters, 0, (size_t)d.q.depth_cap * 4 * sizeof(int32_t), d.stream));
-      for (int depth = 0; depth < f.max_depth; depth++) {
+      // depth d: traverse (closest-hit rays of depth d + shadow rays emitted at depth d-1), then shade.  One more traverse
+      // at the end serves the last depth's shadow rays.
+      for (int depth = 0; depth <= f.max_depth; depth++) {
         if (depth > 0 && ctx->cancel && *ctx->cancel) { cudaStreamSynchronize(d.stream); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
-        timed(0, [&] { launch_trace_shade(bvh, depth == 0, f, sv, qv, c, depth, d.grid_trace[bvh][depth == 0], d.stream); });
-        if (f.en_diffuse == 1) timed(1, [&] { launch_shadow(bvh, f, sv, qv, depth, d.grid_shadow[bvh], d.stream); });
+        if (depth < f.max_depth || f.en_diffuse == 1)
+          timed(0, [&] { launch_traverse(bvh, depth == 0, f, sv, qv, c, depth, d.grid_traverse[bvh][depth == 0], d.stream); });
+        if (depth < f.max_depth) timed(1, [&] { launch_shade(depth == 0, f, sv, qv, c, depth, shade_grid, d.stream); });
       }
     }
     timed(2, [&] { launch_resolve(f, qv, c, dst, resolve_grid, d.stream); });
@@ -374,7 +378,7 @@ int collect_stats(rtb_context* ctx) {
   rtb_stats& st = ctx->stats;
   st.rays_primary = st.rays_continuation = st.rays_shadow = st.paths_hit_primary = 0;
   st.ms_render_device = 0.0f;
-  st.ms_trace = st.ms_shadow = st.ms_resolve = 0.0f;
+  st.ms_traverse = st.ms_shade = st.ms_resolve = 0.0f;
   int64_t overflow = 0;
   for (auto& d : ctx->devs) {
     CK(ctx, cudaSetDevice(d.device));
@@ -389,8 +393,8 @@ int collect_stats(rtb_context* ctx) {
     if (cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end) == cudaSuccess) st.ms_render_device = std::max(st.ms_render_device, ms);
     else cudaGetLastError();
     if (ctx->profiling && &d == &ctx->devs[0]) {
-      st.ms_trace = sum_pairs(d.prof_trace, d.prof_used[0]);
-      st.ms_shadow = sum_pairs(d.prof_shadow, d.prof_used[1]);
+      st.ms_traverse = sum_pairs(d.prof_trace, d.prof_used[0]);
+      st.ms_shade = sum_pairs(d.prof_shadow, d.prof_used[1]);
       st.ms_resolve = sum_pairs(d.prof_resolve, d.prof_used[2]);
     }
   }

@@ -194,9 +194,18 @@ __global__ void __launch_bounds__(kBlock) k_refit(const float4* __restrict__ raw
   }
 }
 
+// Outward padding of an emitted box face: the traversal's FMA slab test (trace.cuh: slab_entry_fma) rounds differently
+// from the exact (bound - origin) * inv form by a few ulp of |origin * inv|, i.e. ~1e-7 * |origin| in space; 1e-6 of
+// (|coordinate| + scene radius) covers cameras within several scene radii and grows boxes by far less than a triangle.
+__device__ __forceinline__ float pad_lo(float v, float radius) { return v - 1e-6f * (fabsf(v) + radius); }
+__device__ __forceinline__ float pad_hi(float v, float radius) { return v + 1e-6f * (fabsf(v) + radius); }
+
 __global__ void __launch_bounds__(kBlock) k_emit(int32_t n, const int2* __restrict__ child, const int2* __restrict__ range,
-                                                 const float4* __restrict__ box, float4* __restrict__ nodes, int32_t* __restrict__ root_out) {
+                                                 const float4* __restrict__ box, const unsigned* __restrict__ bounds, float4* __restrict__ nodes,
+                                                 int32_t* __restrict__ root_out) {
   const int32_t n_int = n - 1;
+  float radius = 0.0f;
+  for (int a = 0; a < 6; a++) radius = fmaxf(radius, fabsf(o2f(bounds[a])));
   if (blockIdx.x == 0 && threadIdx.x == 0) *root_out = (n <= RTB_LEAF_MAX) ? lbvh_leaf_ref(0, n) : 0;
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_int; i += gridDim.x * blockDim.x) {
     const int2 rg = range[i];
@@ -215,10 +224,10 @@ __global__ void __launch_bounds__(kBlock) k_emit(int32_t n, const int2* __restri
       }
     }
     const float4 lmn = box[2 * bi[0]], lmx = box[2 * bi[0] + 1], rmn = box[2 * bi[1]], rmx = box[2 * bi[1] + 1];
-    nodes[4 * (size_t)i] = make_float4(lmn.x, lmn.y, lmn.z, __int_as_float(ref[0]));
-    nodes[4 * (size_t)i + 1] = make_float4(lmx.x, lmx.y, lmx.z, __int_as_float(ref[1]));
-    nodes[4 * (size_t)i + 2] = make_float4(rmn.x, rmn.y, rmn.z, 0.0f);
-    nodes[4 * (size_t)i + 3] = make_float4(rmx.x, rmx.y, rmx.z, 0.0f);
+    nodes[4 * (size_t)i] = make_float4(pad_lo(lmn.x, radius), pad_lo(lmn.y, radius), pad_lo(lmn.z, radius), __int_as_float(ref[0]));
+    nodes[4 * (size_t)i + 1] = make_float4(pad_hi(lmx.x, radius), pad_hi(lmx.y, radius), pad_hi(lmx.z, radius), __int_as_float(ref[1]));
+    nodes[4 * (size_t)i + 2] = make_float4(pad_lo(rmn.x, radius), pad_lo(rmn.y, radius), pad_lo(rmn.z, radius), 0.0f);
+    nodes[4 * (size_t)i + 3] = make_float4(pad_hi(rmx.x, radius), pad_hi(rmx.y, radius), pad_hi(rmx.z, radius), 0.0f);
   }
 }
 
@@ -252,7 +261,7 @@ cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaS
     k_hierarchy<<<grid_for(n - 1), kBlock, 0, st>>>(w.keys_sorted, n, w.child, w.range, w.parent);
   }
   k_refit<<<grid_for(n), kBlock, 0, st>>>(raw, b.perm, n, w.child, w.parent, w.flag, w.box);
-  k_emit<<<grid_for(n > 1 ? n - 1 : 1), kBlock, 0, st>>>(n, w.child, w.range, w.box, b.nodes, b.root_out);
+  k_emit<<<grid_for(n > 1 ? n - 1 : 1), kBlock, 0, st>>>(n, w.child, w.range, w.box, w.bounds, b.nodes, b.root_out);
   return cudaGetLastError();
 }
 

@@ -17,7 +17,10 @@ namespace rtb {
 
 #define RTB_STACK_REF 64   /* reference traversal: int stack (the reference has 32 unchecked, compute:235) */
 #define RTB_STACK_LBVH 96  /* LBVH ordered traversal: one deferred sibling per level */
-#define RTB_LEAF_MAX 4     /* LBVH leaf size */
+#ifndef RTB_LEAF_MAX
+#define RTB_LEAF_MAX 4     /* LBVH leaf size (<= 8) */
+#endif
+#define RTB_REF_DONE ((int32_t)0x80000000) /* LBVH traversal: "no more work" reference (never a valid leaf: n < 2^28) */
 
 struct f3 { float x, y, z; };
 __host__ __device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -96,6 +99,7 @@ struct SceneView {
   const float4* __restrict__ tri_isect;  // 3 per triangle, leaf order: (v0, prim_id) (e1, material) (e2, 0)
   const float4* __restrict__ tri_shade;  // 3 per triangle, leaf order: n0 n1 n2
   const float4* __restrict__ nodes;      // reference: 2 per node (min,leftOrFirst)(max,count); LBVH: 4 per node (see lbvh.cu)
+                                         //   LBVH boxes are padded outward (lbvh.cu: k_emit) so the FMA slab test stays conservative
   const float4* __restrict__ materials;  // 2 per material: (r,g,b,ka) (kd,ks,kr,ior)
   int32_t n_tris, n_nodes, n_mats;
   int32_t root;                          // LBVH: root reference (>= 0 internal node, < 0 leaf, see lbvh_leaf_ref)
@@ -111,14 +115,14 @@ __host__ __device__ __forceinline__ int32_t lbvh_leaf_ref(int32_t first, int32_t
 struct QueueView {
   float4* ray_o[2]; float4* ray_d[2]; float4* ray_att[2];
   float4* sh_o; float4* sh_d; float4* sh_lit; float4* sh_unlit;
+  float4* hits;           // per ray-queue entry of the current depth: (t, u, v, leaf-order triangle index bits; -1 = miss)
   float4* accum;          // per slot: running sampleColor
-  int32_t* counters;      // 4 blocks of depth_cap ints: ray queue sizes | shadow queue sizes | trace fetch | shadow fetch
+  int32_t* counters;      // 4 blocks of depth_cap ints: ray queue sizes | shadow queue sizes | traverse fetch | (spare)
   unsigned long long* totals;  // [0] primary rays [1] continuation rays [2] shadow rays [3] primary hits [4] stack overflows
   int32_t depth_cap;      // D (>= max_depth + 1)
 };
 #define RTB_CNT_RAY(q, d) ((q).counters[(d)])
 #define RTB_CNT_SHADOW(q, d) ((q).counters[(q).depth_cap + (d)])
-#define RTB_CNT_FETCH_RAY(q, d) ((q).counters[2 * (q).depth_cap + (d)])
-#define RTB_CNT_FETCH_SHADOW(q, d) ((q).counters[3 * (q).depth_cap + (d)])
+#define RTB_CNT_FETCH(q, d) ((q).counters[2 * (q).depth_cap + (d)])
 
 }  // namespace rtb

@@ -1,18 +1,24 @@
 // trace.cu — the wavefront kernels of the per-pixel path (replaces CSMain, Assets/Shaders/BVHRayTracing.compute:273-511).
 //
-//   k_trace_shade<BVH, PRIMARY>   one depth of the reference's `for depth` loop (:360-473) for every live path:
-//                                 [PRIMARY: ray generation :283-349] -> closest hit :362 -> miss/background :364-368 ->
-//                                 shading :370-418 (the shadow test is deferred to k_shadow through the shadow queue) ->
-//                                 continuation :420-473, compacted into the next depth's ray queue with one
-//                                 ballot + one atomicAdd per warp.
-//   k_shadow<BVH>                 the shadow query :395-406 as an any-hit traversal; adds the lit or unlit increment of
-//                                 :418 to the slot's sampleColor.
-//   k_resolve                     :475-478,510: average the spp slots of a pixel, saturate, UNORM8, store (possibly into
-//                                 a peer GPU's frame: the NVLink gather is this store).
-//   k_debug<BVH>, k_aux<BVH>      debug views :484-508 and the primary-hit maps used by the parity tests.
+// One depth d of the reference's `for depth` loop (:360-473) is two launches:
 //
-// All kernels are persistent: a fixed grid (a multiple of the SM count) whose warps claim 32 queue entries at a time with
-// one atomicAdd, so queue sizes never travel to the host and a frame is a fixed launch sequence.
+//   k_traverse<BVH, PRIMARY>   every BVH query pending at this point, in ONE persistent kernel: the closest-hit rays of
+//                              depth d (:362; for d = 0 they are generated in-kernel from the pixel index, :283-349) and the
+//                              shadow rays emitted at depth d-1 (:395-406, as any-hit queries).  Lanes are refilled
+//                              individually from a per-warp pool (one atomicAdd per 32 work items), so a long ray never
+//                              idles the other 31 lanes; traversal is "while-while": all lanes descend inner nodes, then
+//                              all lanes intersect their leaf.  A closest-hit ray ends by writing a 16-byte hit record,
+//                              a shadow ray by adding the lit or unlit increment of :418 to its slot's sampleColor.
+//   k_shade<PRIMARY>           miss/background :364-368, shading :370-418 (emits the shadow ray with both candidate
+//                              increments), continuation :420-473, compacted into the next depth's ray queue with one
+//                              ballot + one atomicAdd per warp and queue.
+//
+//   k_resolve                  :475-478,510: average the spp slots of a pixel, saturate, UNORM8, store (possibly into a peer
+//                              GPU's frame: the NVLink gather is this store).
+//   k_debug<BVH>, k_aux<BVH>   debug views :484-508 and the primary-hit maps used by the parity tests.
+//
+// Queue sizes stay on the device (kernels read the counters the previous launch filled), so a frame is a fixed launch
+// sequence with no host round trip.
 #include "kernels.hpp"
 #include "trace.cuh"
 
@@ -21,12 +27,7 @@ namespace rtb {
 namespace {
 
 constexpr int kBlock = 256;
-
-__device__ __forceinline__ int32_t warp_claim(int32_t* counter, int lane) {
-  int32_t base = 0;
-  if (lane == 0) base = atomicAdd(counter, 32);
-  return __shfl_sync(0xffffffffu, base, 0);
-}
+constexpr unsigned kFull = 0xffffffffu;
 
 // slot -> pixel of the chunk.  Returns false for padding slots (outside the image or the chunk's rows).
 __device__ __forceinline__ bool slot_to_pixel(const FrameParams& f, const ChunkView& c, int32_t slot, int& px, int& local_row, int& sample) {
@@ -44,18 +45,292 @@ __device__ __forceinline__ int32_t pixel_to_slot(const FrameParams& f, const Chu
   const int tile = (r >> 2) * c.tiles_x + (px >> 3);
   return ((tile * f.spp + sample) << 5) + ((r & 3) << 3) + (px & 7);
 }
+__device__ __forceinline__ bool primary_ray_of_slot(const FrameParams& f, const ChunkView& c, int32_t slot, Ray& ray, int& px, int& py, int& sample) {
+  int local_row;
+  if (!slot_to_pixel(f, c, slot, px, local_row, sample)) return false;
+  py = band_global_row(local_row, f.band_rank, f.band_world, f.band_rows);
+  ray = generate_ray(f, px, py, sample);
+  return true;
+}
 
-template <int BVH, bool PRIMARY>
-__global__ void __launch_bounds__(kBlock) k_trace_shade(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth) {
+// ---------------------------------------------------------------------------------------------------------------------
+// Work distribution of k_traverse: work items [0, n_closest) are closest-hit rays, [n_closest, n_closest + n_shadow) are
+// shadow rays.  A warp owns a pool [pool_at, pool_end) claimed 32 items at a time; idle lanes take consecutive items.
+// ---------------------------------------------------------------------------------------------------------------------
+struct WorkPool {
+  int32_t at = 0, end = 0;
+  bool exhausted = false;
+};
+// Gives every lane with `want` an item index (or -1 when the work list is drained).  Warp-uniform control flow.
+__device__ __forceinline__ int32_t pool_take(WorkPool& pool, int32_t* fetch_counter, int32_t total, bool want, int lane) {
+  const unsigned m = __ballot_sync(kFull, want);
+  const int need = __popc(m);
+  if (need == 0) return -1;
+  int32_t item = -1;
+  const int rank = __popc(m & ((1u << lane) - 1u));
+  // first serve from what is left of the pool, then claim a fresh batch for the remainder
+  const int have = pool.end - pool.at;
+  if (want && rank < have) item = pool.at + rank;
+  if (need > have) {
+    pool.at = pool.end;
+    if (!pool.exhausted) {
+      int32_t base = 0;
+      if (lane == 0) base = atomicAdd(fetch_counter, 32);
+      base = __shfl_sync(kFull, base, 0);
+      if (base >= total) pool.exhausted = true;
+      else {
+        pool.at = base;
+        pool.end = min(base + 32, total);
+        const int r2 = rank - have;
+        if (want && r2 >= 0 && pool.at + r2 < pool.end) item = pool.at + r2;
+        pool.at = min(pool.at + (need - have), pool.end);
+      }
+    }
+  } else {
+    pool.at += need;
+  }
+  return item;
+}
+
+// Lane state shared by both traversal flavours.
+struct Lane {
+  f3 o, d, inv;       // inv: exact reciprocal (reference mode) or safe_inverse (LBVH mode)
+  float t, u, v;      // closest hit so far; for shadow rays t holds distToLight (the acceptance bound)
+  int32_t tri;        // closest: leaf-order triangle or -1; shadow: 0 when an occluder was found, -1 otherwise
+  int32_t item;       // work item, -1 = idle
+  bool shadow;
+};
+
+// Loads work item `item` into the lane.  Returns false when the item needs no traversal (padding slot).
+template <bool PRIMARY>
+__device__ __forceinline__ bool lane_load(Lane& L, const FrameParams& f, const QueueView& q, const ChunkView& c, int32_t item, int32_t n_closest, int in_q) {
+  L.item = item;
+  L.u = 0.0f; L.v = 0.0f; L.tri = -1;
+  if (PRIMARY || item < n_closest) {
+    L.shadow = false;
+    L.t = RTB_INFINITY;
+    if (PRIMARY) {
+      Ray r;
+      int px, py, sample;
+      if (!primary_ray_of_slot(f, c, item, r, px, py, sample)) { L.item = -1; return false; }
+      L.o = r.o; L.d = r.d;
+    } else {
+      const float4 o = __ldcs(&q.ray_o[in_q][item]), d = __ldcs(&q.ray_d[in_q][item]);
+      L.o = mk3(o); L.d = mk3(d);
+    }
+  } else {
+    const int32_t j = item - n_closest;
+    const float4 o = __ldcs(&q.sh_o[j]), d = __ldcs(&q.sh_d[j]);
+    L.shadow = true;
+    L.o = mk3(o); L.d = mk3(d);
+    L.t = o.w;
+  }
+  return true;
+}
+
+// A finished lane publishes its result.
+__device__ __forceinline__ void lane_finish(Lane& L, const QueueView& q, int32_t n_closest) {
+  if (!L.shadow) {
+    __stcs(&q.hits[L.item], make_float4(L.t, L.u, L.v, __int_as_float(L.tri)));
+  } else {  // lit <=> no occluder with Epsilon < t <= distToLight (compute:406)
+    const int32_t j = L.item - n_closest;
+    const float4 inc = (L.tri == 0) ? __ldcs(&q.sh_unlit[j]) : __ldcs(&q.sh_lit[j]);
+    const int32_t slot = __float_as_int(__ldcs(&q.sh_d[j]).w);
+    const float4 prev = q.accum[slot];
+    q.accum[slot] = make_float4(prev.x + inc.x, prev.y + inc.y, prev.z + inc.z, 0.0f);
+  }
+  L.item = -1;
+}
+
+// Triangle test shared by both flavours.  Returns true when a shadow ray found its occluder.
+__device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, int32_t tri) {
+  const float4 a = __ldg(&s.tri_isect[3 * tri]), b = __ldg(&s.tri_isect[3 * tri + 1]), c = __ldg(&s.tri_isect[3 * tri + 2]);
+  Ray r; r.o = L.o; r.d = L.d;
+  float t, u, v;
+  if (!moller_trumbore(r, mk3(a), mk3(b), mk3(c), t, u, v)) return false;
+  if (L.shadow) {
+    if (t <= L.t) { L.tri = 0; return true; }
+  } else if (t < L.t) { L.t = t; L.u = u; L.v = v; L.tri = tri; }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_traverse, LBVH flavour: ordered traversal over 64-byte two-box nodes (see lbvh.cu for the layout).
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool PRIMARY>
+__global__ void __launch_bounds__(kBlock) k_traverse_lbvh(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth) {
+  const int lane = threadIdx.x & 31;
+  const int32_t n_closest = PRIMARY ? c.n_slots : RTB_CNT_RAY(q, depth);
+  const int32_t n_shadow = (PRIMARY || depth == 0) ? 0 : RTB_CNT_SHADOW(q, depth - 1);
+  const int32_t total = n_closest + n_shadow;
+  const int in_q = depth & 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (!PRIMARY && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
+    if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
+  }
+  int32_t stack_ref[RTB_STACK_LBVH];
+  float stack_dst[RTB_STACK_LBVH];
+  int sp = 0;
+  int32_t cur = RTB_REF_DONE;
+  f3 ood = mk3(0.0f, 0.0f, 0.0f);
+  Lane L;
+  L.item = -1; L.shadow = false; L.t = 0.0f; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
+  L.o = L.d = L.inv = mk3(0.0f, 0.0f, 0.0f);
+  WorkPool pool;
+  unsigned n_primary = 0, overflow = 0;
+
+  for (;;) {
+    // ---- refill idle lanes ----
+    const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, L.item < 0, lane);
+    if (item >= 0 && lane_load<PRIMARY>(L, f, q, c, item, n_closest, in_q)) {
+      if (PRIMARY) n_primary++;
+      L.inv = safe_inverse(L.d);
+      ood = L.o * L.inv;
+      sp = 0;
+      cur = s.n_tris > 0 ? s.root : RTB_REF_DONE;
+      if (cur == RTB_REF_DONE) lane_finish(L, q, n_closest);
+    }
+    if (__ballot_sync(kFull, L.item >= 0) == 0) {
+      if (pool.exhausted) break;
+      continue;  // only padding slots were drawn: take more
+    }
+
+    // ---- inner nodes: descend until this lane holds a leaf (or runs out of work) ----
+    while (cur >= 0) {
+      const float4 n0 = __ldg(&s.nodes[4 * cur]), n1 = __ldg(&s.nodes[4 * cur + 1]);
+      const float4 n2 = __ldg(&s.nodes[4 * cur + 2]), n3 = __ldg(&s.nodes[4 * cur + 3]);
+      const float dl = slab_entry_fma(L.inv, ood, mk3(n0), mk3(n1));
+      const float dr = slab_entry_fma(L.inv, ood, mk3(n2), mk3(n3));
+      // closest: a box is skipped when entry >= best t (compute:246); shadow: when entry > distToLight
+      const bool hl = L.shadow ? !(dl > L.t) : !(dl >= L.t);
+      const bool hr = L.shadow ? !(dr > L.t) : !(dr >= L.t);
+      const int32_t lref = __float_as_int(n0.w), rref = __float_as_int(n1.w);
+      if (hl && hr) {
+        const bool left_first = !(dr < dl);
+        if (sp < RTB_STACK_LBVH) { stack_ref[sp] = left_first ? rref : lref; stack_dst[sp] = left_first ? dr : dl; sp++; }
+        else overflow++;
+        cur = left_first ? lref : rref;
+      } else if (hl) cur = lref;
+      else if (hr) cur = rref;
+      else {
+        cur = RTB_REF_DONE;
+        while (sp > 0) {
+          sp--;
+          const float dd = stack_dst[sp];
+          if (L.shadow ? !(dd > L.t) : !(dd >= L.t)) { cur = stack_ref[sp]; break; }
+        }
+      }
+    }
+
+    // ---- leaf ----
+    if (cur != RTB_REF_DONE) {
+      const int32_t code = ~cur;
+      const int32_t first = code >> 3, count = (code & 7) + 1;
+      bool occluded = false;
+      for (int32_t i = 0; i < count && !occluded; i++) occluded = lane_test_triangle(L, s, first + i);
+      cur = RTB_REF_DONE;
+      if (!occluded)
+        while (sp > 0) {
+          sp--;
+          const float dd = stack_dst[sp];
+          if (L.shadow ? !(dd > L.t) : !(dd >= L.t)) { cur = stack_ref[sp]; break; }
+        }
+    }
+    if (cur == RTB_REF_DONE && L.item >= 0) { sp = 0; lane_finish(L, q, n_closest); }
+  }
+
+  for (int o = 16; o > 0; o >>= 1) {
+    n_primary += __shfl_xor_sync(kFull, n_primary, o);
+    overflow += __shfl_xor_sync(kFull, overflow, o);
+  }
+  if (lane == 0) {
+    if (PRIMARY && n_primary) atomicAdd(&q.totals[0], (unsigned long long)n_primary);
+    if (overflow) atomicAdd(&q.totals[4], (unsigned long long)overflow);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_traverse, reference flavour: TraverseBVH compute:225-267 — LIFO stack, left child first, no distance ordering, node
+// culled when its own slab entry >= best t; leaves of any size.  Same results as the reference for every ray.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool PRIMARY>
+__global__ void __launch_bounds__(kBlock) k_traverse_ref(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth) {
+  const int lane = threadIdx.x & 31;
+  const int32_t n_closest = PRIMARY ? c.n_slots : RTB_CNT_RAY(q, depth);
+  const int32_t n_shadow = (PRIMARY || depth == 0) ? 0 : RTB_CNT_SHADOW(q, depth - 1);
+  const int32_t total = n_closest + n_shadow;
+  const int in_q = depth & 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (!PRIMARY && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
+    if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
+  }
+  int32_t stack[RTB_STACK_REF];
+  int sp = 0;
+  int32_t leaf_first = 0, leaf_count = 0;
+  Lane L;
+  L.item = -1; L.shadow = false; L.t = 0.0f; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
+  L.o = L.d = L.inv = mk3(0.0f, 0.0f, 0.0f);
+  WorkPool pool;
+  unsigned n_primary = 0, overflow = 0;
+
+  for (;;) {
+    const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, L.item < 0, lane);
+    if (item >= 0 && lane_load<PRIMARY>(L, f, q, c, item, n_closest, in_q)) {
+      if (PRIMARY) n_primary++;
+      L.inv = mk3(1.0f / L.d.x, 1.0f / L.d.y, 1.0f / L.d.z);  // CreateRay :142 / :398
+      sp = 0; leaf_count = 0;
+      if (s.n_nodes > 0) stack[sp++] = 0;
+      else lane_finish(L, q, n_closest);
+    }
+    if (__ballot_sync(kFull, L.item >= 0) == 0) {
+      if (pool.exhausted) break;
+      continue;
+    }
+
+    while (leaf_count == 0 && sp > 0) {
+      const int32_t ni = stack[--sp];
+      const float4 lo = __ldg(&s.nodes[2 * ni]), hi = __ldg(&s.nodes[2 * ni + 1]);
+      Ray r; r.o = L.o; r.d = L.d; r.inv = L.inv;
+      const float dst = slab_entry(r, mk3(lo), mk3(hi));
+      if (L.shadow ? (dst > L.t) : (dst >= L.t)) continue;
+      const int32_t count = __float_as_int(hi.w), left_or_first = __float_as_int(lo.w);
+      if (count > 0) { leaf_first = left_or_first; leaf_count = count; }
+      else if (sp + 2 <= RTB_STACK_REF) { stack[sp++] = left_or_first + 1; stack[sp++] = left_or_first; }
+      else overflow++;
+    }
+    if (leaf_count > 0) {
+      bool occluded = false;
+      for (int32_t i = 0; i < leaf_count && !occluded; i++) occluded = lane_test_triangle(L, s, leaf_first + i);
+      leaf_count = 0;
+      if (occluded) sp = 0;
+    }
+    if (sp == 0 && leaf_count == 0 && L.item >= 0) lane_finish(L, q, n_closest);
+  }
+
+  for (int o = 16; o > 0; o >>= 1) {
+    n_primary += __shfl_xor_sync(kFull, n_primary, o);
+    overflow += __shfl_xor_sync(kFull, overflow, o);
+  }
+  if (lane == 0) {
+    if (PRIMARY && n_primary) atomicAdd(&q.totals[0], (unsigned long long)n_primary);
+    if (overflow) atomicAdd(&q.totals[4], (unsigned long long)overflow);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_shade: everything the reference does with a closest-hit result at one depth.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool PRIMARY>
+__global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth) {
   const int lane = threadIdx.x & 31;
   const int32_t n = PRIMARY ? c.n_slots : RTB_CNT_RAY(q, depth);
   const int in_q = depth & 1, out_q = in_q ^ 1;
-  unsigned n_rays = 0, n_hits = 0, overflow = 0;
-  if (!PRIMARY && blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(&q.totals[1], (unsigned long long)n);
+  const int32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned below = (1u << lane) - 1u;
+  unsigned n_hits = 0;
 
-  for (;;) {
-    const int32_t base = warp_claim(&RTB_CNT_FETCH_RAY(q, depth), lane);
-    if (base >= n) break;
+  for (int32_t base = warp_id * 32; base < n; base += warps_total * 32) {
     const int32_t idx = base + lane;
     bool active = idx < n;
     int32_t slot = idx;
@@ -63,14 +338,11 @@ __global__ void __launch_bounds__(kBlock) k_trace_shade(const FrameParams f, con
     Ray ray;
     f3 att = mk3(1.0f, 1.0f, 1.0f);
     if (PRIMARY) {
-      int local_row;
-      active = active && slot_to_pixel(f, c, slot, px, local_row, sample);
-      py = band_global_row(local_row, f.band_rank, f.band_world, f.band_rows);
-      if (active) ray = generate_ray(f, px, py, sample);
+      active = active && primary_ray_of_slot(f, c, slot, ray, px, py, sample);
     } else if (active) {
       const float4 o = __ldcs(&q.ray_o[in_q][idx]), d = __ldcs(&q.ray_d[in_q][idx]), a = __ldcs(&q.ray_att[in_q][idx]);
       slot = __float_as_int(o.w);
-      ray = make_ray(mk3(o), mk3(d));
+      ray.o = mk3(o); ray.d = mk3(d);
       att = mk3(a);
       if (f.soft == 1 || f.glossy == 1) {  // the jitter hashes are seeded with the pixel and sample (:386,462)
         int local_row;
@@ -78,150 +350,126 @@ __global__ void __launch_bounds__(kBlock) k_trace_shade(const FrameParams f, con
         py = band_global_row(local_row, f.band_rank, f.band_world, f.band_rows);
       }
     }
+    float4 hrec = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+    if (active) hrec = __ldcs(&q.hits[idx]);
+    Hit hit; hit.t = hrec.x; hit.u = hrec.y; hit.v = hrec.z; hit.tri = __float_as_int(hrec.w);
+    const bool found = active && hit.tri >= 0;
+    f3 prev = mk3(0.0f, 0.0f, 0.0f);
+    if (!PRIMARY && active) prev = mk3(q.accum[slot]);
 
-    bool emit_shadow = false, emit_ray = false;
-    float4 sh_o, sh_d, sh_lit, sh_unlit, nx_o, nx_d, nx_att;
-    if (active) {
-      n_rays++;
-      Hit hit;
-      const bool found = traverse<BVH, false>(s, ray, 0.0f, hit, overflow);
-      f3 prev = mk3(0.0f, 0.0f, 0.0f);
-      if (!PRIMARY) prev = mk3(q.accum[slot]);
-      if (!found) {  // :364-368
-        const f3 sum = prev + att * mk3(f.bg[0], f.bg[1], f.bg[2]);
-        q.accum[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f);
+    f3 pos = mk3(0.0f, 0.0f, 0.0f), nrm = pos;
+    Material m;
+    m.color = pos; m.ka = m.kd = m.ks = m.kr = 0.0f; m.ior = 1.0f;
+    bool emit_shadow = false;
+    f3 sh_origin = pos, sh_dir = pos, lit = pos, unlit = pos;
+    float sh_dist = 0.0f;
+    if (active && !found) {  // :364-368
+      const f3 sum = prev + att * mk3(f.bg[0], f.bg[1], f.bg[2]);
+      q.accum[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f);
+    }
+    if (found) {
+      if (PRIMARY) n_hits++;
+      pos = ray.o + hit.t * ray.d;  // :183
+      nrm = hit_normal(s, hit);
+      m = fetch_material(s, __float_as_int(__ldg(&s.tri_isect[3 * hit.tri + 1]).w));
+      f3 local = mk3(0.0f, 0.0f, 0.0f);
+      if (f.en_ambient == 1) local = local + m.color * m.ka;  // :379
+      f3 light_pos = mk3(f.light[0], f.light[1], f.light[2]);
+      if (f.soft == 1) {  // :383-388
+        const f3 j = random_unit_vector(mk3((float)px + (float)sample * 9.0f, ((float)py + (float)sample * 4.0f) + (float)depth, (float)sample)) * f.light_size;
+        light_pos = light_pos + j;
+      }
+      const f3 to_light = light_pos - pos;
+      sh_dir = hlsl_normalize(to_light);
+      const float n_dot_l = fmaxf(0.0f, dot3(nrm, sh_dir));
+      unlit = (att * local) * f.light_intensity;          // :418 when the shadow test fails or is not made
+      emit_shadow = f.en_diffuse == 1 && n_dot_l > 0.0f;  // :393
+      if (emit_shadow) {
+        f3 lit_local = local + (m.color * m.kd) * n_dot_l;  // :408
+        if (f.en_specular == 1 && m.ks > 0.0f) {            // :409-414
+          const f3 view_dir = hlsl_normalize(negate(ray.d));
+          const f3 half_vec = hlsl_normalize(sh_dir + view_dir);
+          const float k = m.ks * pow32(fmaxf(dot3(nrm, half_vec), 0.0f));
+          lit_local = lit_local + mk3(k, k, k);
+        }
+        lit = (att * lit_local) * f.light_intensity;
+        sh_origin = pos + nrm * RTB_OFFSET;  // :396
+        sh_dist = hlsl_length(to_light);      // :401
+        if (PRIMARY) q.accum[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // k_traverse adds the increment later
       } else {
-        if (PRIMARY) n_hits++;
-        const f3 pos = ray.o + hit.t * ray.d;  // :183
-        const f3 nrm = hit_normal(s, hit);
-        const Material m = fetch_material(s, __float_as_int(__ldg(&s.tri_isect[3 * hit.tri + 1]).w));
-        f3 local = mk3(0.0f, 0.0f, 0.0f);
-        if (f.en_ambient == 1) local = local + m.color * m.ka;  // :379
-        f3 light_pos = mk3(f.light[0], f.light[1], f.light[2]);
-        if (f.soft == 1) {  // :383-388
-          const f3 j = random_unit_vector(mk3((float)px + (float)sample * 9.0f, ((float)py + (float)sample * 4.0f) + (float)depth, (float)sample)) * f.light_size;
-          light_pos = light_pos + j;
-        }
-        const f3 to_light = light_pos - pos;
-        const f3 light_dir = hlsl_normalize(to_light);
-        const float n_dot_l = fmaxf(0.0f, dot3(nrm, light_dir));
-        const f3 unlit = (att * local) * f.light_intensity;  // :418 when the shadow test fails or is not made
-        if (f.en_diffuse == 1 && n_dot_l > 0.0f) {  // :393-416
-          f3 lit_local = local + (m.color * m.kd) * n_dot_l;
-          if (f.en_specular == 1 && m.ks > 0.0f) {
-            const f3 view_dir = hlsl_normalize(negate(ray.d));
-            const f3 half_vec = hlsl_normalize(light_dir + view_dir);
-            const float k = m.ks * pow32(fmaxf(dot3(nrm, half_vec), 0.0f));
-            lit_local = lit_local + mk3(k, k, k);
-          }
-          const f3 lit = (att * lit_local) * f.light_intensity;
-          const f3 so = pos + nrm * RTB_OFFSET;
-          emit_shadow = true;
-          sh_o = make_float4(so.x, so.y, so.z, hlsl_length(to_light));
-          sh_d = make_float4(light_dir.x, light_dir.y, light_dir.z, __int_as_float(slot));
-          sh_lit = make_float4(lit.x, lit.y, lit.z, 0.0f);
-          sh_unlit = make_float4(unlit.x, unlit.y, unlit.z, 0.0f);
-          if (PRIMARY) q.accum[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        } else {
-          const f3 sum = prev + unlit;
-          q.accum[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f);
-        }
-        // continuation, :420-473
-        const bool should_reflect = m.ks > 0.0f;
-        const bool should_refract = (f.en_refraction == 1 && m.kr > 0.0f);
-        if ((should_reflect || should_refract) && depth + 1 < f.max_depth) {
-          f3 next_dir, start = pos;
-          if (should_refract) {
-            const f3 I = hlsl_normalize(ray.d);
-            f3 N = nrm;
-            float eta = 1.0f / m.ior;
-            if (dot3(I, N) > 0.0f) { N = negate(N); eta = m.ior; }
-            const float cosi = dot3(negate(I), N);
-            const float k = 1.0f - (eta * eta) * (1.0f - cosi * cosi);
-            if (k >= 0.0f) {
-              next_dir = eta * I + (eta * cosi - sqrtf(k)) * N;
-              att = att * (m.color * m.kr);
-              start = start + next_dir * RTB_OFFSET;
-            } else {  // total internal reflection
-              next_dir = hlsl_reflect(I, N);
-              att = att * (m.color * m.ks);
-              start = start + N * RTB_OFFSET;
-            }
-          } else {
-            next_dir = hlsl_reflect(hlsl_normalize(ray.d), nrm);
-            att = att * (m.color * m.ks);
-            start = start + nrm * RTB_OFFSET;
-          }
-          if (f.glossy == 1 && f.roughness > 0.0f) {  // :459-470
-            const f3 j = random_unit_vector(mk3(((float)px + (float)sample * 55.0f) + (float)depth, (float)py + (float)sample * 22.0f, (float)(depth * 13))) * f.roughness;
-            next_dir = hlsl_normalize(next_dir + j);
-          }
-          const f3 nd = hlsl_normalize(next_dir);  // :472
-          emit_ray = true;
-          nx_o = make_float4(start.x, start.y, start.z, __int_as_float(slot));
-          nx_d = make_float4(nd.x, nd.y, nd.z, 0.0f);
-          nx_att = make_float4(att.x, att.y, att.z, 0.0f);
-        }
+        const f3 sum = prev + unlit;
+        q.accum[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f);
       }
     }
 
-    // queue compaction: one atomicAdd per warp and queue
-    const unsigned m_sh = __ballot_sync(0xffffffffu, emit_shadow);
-    const unsigned m_nx = __ballot_sync(0xffffffffu, emit_ray);
-    int32_t b_sh = 0, b_nx = 0;
-    if (lane == 0) {
-      if (m_sh) b_sh = atomicAdd(&RTB_CNT_SHADOW(q, depth), __popc(m_sh));
-      if (m_nx) b_nx = atomicAdd(&RTB_CNT_RAY(q, depth + 1), __popc(m_nx));
+    // ---- shadow queue compaction: one atomicAdd per warp ----
+    {
+      const unsigned m_sh = __ballot_sync(kFull, emit_shadow);
+      int32_t b_sh = 0;
+      if (lane == 0 && m_sh) b_sh = atomicAdd(&RTB_CNT_SHADOW(q, depth), __popc(m_sh));
+      b_sh = __shfl_sync(kFull, b_sh, 0);
+      if (emit_shadow) {
+        const int32_t at = b_sh + __popc(m_sh & below);
+        __stcs(&q.sh_o[at], make_float4(sh_origin.x, sh_origin.y, sh_origin.z, sh_dist));
+        __stcs(&q.sh_d[at], make_float4(sh_dir.x, sh_dir.y, sh_dir.z, __int_as_float(slot)));
+        __stcs(&q.sh_lit[at], make_float4(lit.x, lit.y, lit.z, 0.0f));
+        __stcs(&q.sh_unlit[at], make_float4(unlit.x, unlit.y, unlit.z, 0.0f));
+      }
     }
-    b_sh = __shfl_sync(0xffffffffu, b_sh, 0);
-    b_nx = __shfl_sync(0xffffffffu, b_nx, 0);
-    const unsigned below = (1u << lane) - 1u;
-    if (emit_shadow) {
-      const int32_t at = b_sh + __popc(m_sh & below);
-      __stcs(&q.sh_o[at], sh_o); __stcs(&q.sh_d[at], sh_d); __stcs(&q.sh_lit[at], sh_lit); __stcs(&q.sh_unlit[at], sh_unlit);
+
+    // ---- continuation, :420-473 ----
+    bool emit_ray = false;
+    f3 start = pos, nd = mk3(0.0f, 0.0f, 0.0f);
+    if (found && depth + 1 < f.max_depth) {
+      const bool should_reflect = m.ks > 0.0f;
+      const bool should_refract = (f.en_refraction == 1 && m.kr > 0.0f);
+      if (should_reflect || should_refract) {
+        f3 next_dir;
+        if (should_refract) {
+          const f3 I = hlsl_normalize(ray.d);
+          f3 N = nrm;
+          float eta = 1.0f / m.ior;
+          if (dot3(I, N) > 0.0f) { N = negate(N); eta = m.ior; }
+          const float cosi = dot3(negate(I), N);
+          const float k = 1.0f - (eta * eta) * (1.0f - cosi * cosi);
+          if (k >= 0.0f) {
+            next_dir = eta * I + (eta * cosi - sqrtf(k)) * N;
+            att = att * (m.color * m.kr);
+            start = start + next_dir * RTB_OFFSET;
+          } else {  // total internal reflection
+            next_dir = hlsl_reflect(I, N);
+            att = att * (m.color * m.ks);
+            start = start + N * RTB_OFFSET;
+          }
+        } else {
+          next_dir = hlsl_reflect(hlsl_normalize(ray.d), nrm);
+          att = att * (m.color * m.ks);
+          start = start + nrm * RTB_OFFSET;
+        }
+        if (f.glossy == 1 && f.roughness > 0.0f) {  // :459-470
+          const f3 j = random_unit_vector(mk3(((float)px + (float)sample * 55.0f) + (float)depth, (float)py + (float)sample * 22.0f, (float)(depth * 13))) * f.roughness;
+          next_dir = hlsl_normalize(next_dir + j);
+        }
+        nd = hlsl_normalize(next_dir);  // :472
+        emit_ray = true;
+      }
     }
-    if (emit_ray) {
-      const int32_t at = b_nx + __popc(m_nx & below);
-      __stcs(&q.ray_o[out_q][at], nx_o); __stcs(&q.ray_d[out_q][at], nx_d); __stcs(&q.ray_att[out_q][at], nx_att);
+    {
+      const unsigned m_nx = __ballot_sync(kFull, emit_ray);
+      int32_t b_nx = 0;
+      if (lane == 0 && m_nx) b_nx = atomicAdd(&RTB_CNT_RAY(q, depth + 1), __popc(m_nx));
+      b_nx = __shfl_sync(kFull, b_nx, 0);
+      if (emit_ray) {
+        const int32_t at = b_nx + __popc(m_nx & below);
+        __stcs(&q.ray_o[out_q][at], make_float4(start.x, start.y, start.z, __int_as_float(slot)));
+        __stcs(&q.ray_d[out_q][at], make_float4(nd.x, nd.y, nd.z, 0.0f));
+        __stcs(&q.ray_att[out_q][at], make_float4(att.x, att.y, att.z, 0.0f));
+      }
     }
   }
 
-  // per-warp totals
-  for (int o = 16; o > 0; o >>= 1) {
-    n_rays += __shfl_xor_sync(0xffffffffu, n_rays, o);
-    n_hits += __shfl_xor_sync(0xffffffffu, n_hits, o);
-    overflow += __shfl_xor_sync(0xffffffffu, overflow, o);
-  }
-  if (lane == 0) {
-    if (PRIMARY && n_rays) atomicAdd(&q.totals[0], (unsigned long long)n_rays);
-    if (PRIMARY && n_hits) atomicAdd(&q.totals[3], (unsigned long long)n_hits);
-    if (overflow) atomicAdd(&q.totals[4], (unsigned long long)overflow);
-  }
-}
-
-template <int BVH>
-__global__ void __launch_bounds__(kBlock) k_shadow(const FrameParams f, const SceneView s, const QueueView q, const int depth) {
-  const int lane = threadIdx.x & 31;
-  const int32_t n = RTB_CNT_SHADOW(q, depth);
-  unsigned overflow = 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(&q.totals[2], (unsigned long long)n);
-  for (;;) {
-    const int32_t base = warp_claim(&RTB_CNT_FETCH_SHADOW(q, depth), lane);
-    if (base >= n) break;
-    const int32_t idx = base + lane;
-    if (idx < n) {
-      const float4 o = __ldcs(&q.sh_o[idx]), d = __ldcs(&q.sh_d[idx]);
-      Ray ray; ray.o = mk3(o); ray.d = mk3(d); ray.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // :395-398
-      Hit hit;
-      const bool shadowed = traverse<BVH, true>(s, ray, o.w, hit, overflow);  // lit <=> !hit || t > distToLight, :406
-      const float4 inc = shadowed ? __ldcs(&q.sh_unlit[idx]) : __ldcs(&q.sh_lit[idx]);
-      const int32_t slot = __float_as_int(d.w);
-      const float4 prev = q.accum[slot];
-      q.accum[slot] = make_float4(prev.x + inc.x, prev.y + inc.y, prev.z + inc.z, 0.0f);
-    }
-  }
-  for (int o = 16; o > 0; o >>= 1) overflow += __shfl_xor_sync(0xffffffffu, overflow, o);
-  if (lane == 0 && overflow) atomicAdd(&q.totals[4], (unsigned long long)overflow);
+  for (int o = 16; o > 0; o >>= 1) n_hits += __shfl_xor_sync(kFull, n_hits, o);
+  if (PRIMARY && lane == 0 && n_hits) atomicAdd(&q.totals[3], (unsigned long long)n_hits);
 }
 
 // Output row of a local row: the full frame (RTB_OUT_FRAME) or this rank's packed rows (RTB_OUT_COMPACT).
@@ -291,28 +539,25 @@ int blocks_per_sm(K kernel) {
 
 }  // namespace
 
-int trace_blocks_per_sm(int bvh, bool primary) {
-  if (bvh == RTB_BVH_REFERENCE) return primary ? blocks_per_sm(k_trace_shade<RTB_BVH_REFERENCE, true>) : blocks_per_sm(k_trace_shade<RTB_BVH_REFERENCE, false>);
-  return primary ? blocks_per_sm(k_trace_shade<RTB_BVH_LBVH, true>) : blocks_per_sm(k_trace_shade<RTB_BVH_LBVH, false>);
-}
-int shadow_blocks_per_sm(int bvh) {
-  return bvh == RTB_BVH_REFERENCE ? blocks_per_sm(k_shadow<RTB_BVH_REFERENCE>) : blocks_per_sm(k_shadow<RTB_BVH_LBVH>);
+int traverse_blocks_per_sm(int bvh, bool primary) {
+  if (bvh == RTB_BVH_REFERENCE) return primary ? blocks_per_sm(k_traverse_ref<true>) : blocks_per_sm(k_traverse_ref<false>);
+  return primary ? blocks_per_sm(k_traverse_lbvh<true>) : blocks_per_sm(k_traverse_lbvh<false>);
 }
 
-void launch_trace_shade(int bvh, bool primary, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth,
-                        int grid, cudaStream_t st) {
+void launch_traverse(int bvh, bool primary, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int grid,
+                     cudaStream_t st) {
   if (bvh == RTB_BVH_REFERENCE) {
-    if (primary) k_trace_shade<RTB_BVH_REFERENCE, true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
-    else k_trace_shade<RTB_BVH_REFERENCE, false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
+    if (primary) k_traverse_ref<true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
+    else k_traverse_ref<false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
   } else {
-    if (primary) k_trace_shade<RTB_BVH_LBVH, true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
-    else k_trace_shade<RTB_BVH_LBVH, false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
+    if (primary) k_traverse_lbvh<true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
+    else k_traverse_lbvh<false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
   }
 }
 
-void launch_shadow(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, int depth, int grid, cudaStream_t st) {
-  if (bvh == RTB_BVH_REFERENCE) k_shadow<RTB_BVH_REFERENCE><<<grid, kBlock, 0, st>>>(f, s, q, depth);
-  else k_shadow<RTB_BVH_LBVH><<<grid, kBlock, 0, st>>>(f, s, q, depth);
+void launch_shade(bool primary, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int grid, cudaStream_t st) {
+  if (primary) k_shade<true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
+  else k_shade<false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
 }
 
 void launch_resolve(const FrameParams& f, const QueueView& q, const ChunkView& c, void* dst, int grid, cudaStream_t st) {

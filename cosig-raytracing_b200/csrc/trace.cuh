@@ -112,6 +112,23 @@ __device__ __forceinline__ float slab_entry(const Ray& r, f3 mn, f3 mx) {
   return dst_a;
 }
 
+// Slab test of the LBVH traversal: same semantics as slab_entry, evaluated as fma(bound, inv, -origin*inv).  The rounding
+// differs from IntersectAABB's by a few ulp of |origin*inv|; LBVH boxes are padded outward at build time by more than
+// that (lbvh.cu: k_emit), so every box the exact test would enter is still entered.  It never decides t, u, v or ids.
+__device__ __forceinline__ float slab_entry_fma(f3 inv, f3 ood, f3 mn, f3 mx) {
+  const float t0x = __fmaf_rn(mn.x, inv.x, -ood.x), t1x = __fmaf_rn(mx.x, inv.x, -ood.x);
+  const float t0y = __fmaf_rn(mn.y, inv.y, -ood.y), t1y = __fmaf_rn(mx.y, inv.y, -ood.y);
+  const float t0z = __fmaf_rn(mn.z, inv.z, -ood.z), t1z = __fmaf_rn(mx.z, inv.z, -ood.z);
+  const float dst_a = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+  const float dst_b = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+  if (dst_a > dst_b || dst_b < 0.0f) return RTB_INFINITY;
+  return dst_a;
+}
+// Reciprocal direction for the FMA slab test: finite even for axis-parallel rays (a +-inf reciprocal would turn
+// fma(bound, inf, -origin*inf) into inf - inf = NaN), so such rays see slabs at +-1e18 * (bound - origin).
+__device__ __forceinline__ float safe_rcp(float d) { return fabsf(d) > 1e-18f ? 1.0f / d : copysignf(1e18f, d); }
+__device__ __forceinline__ f3 safe_inverse(f3 d) { return mk3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)); }
+
 // IntersectTriangle, compute:153-190, on the stored (v0, e1 = v1-v0, e2 = v2-v0).  Returns true and t,u,v when the
 // triangle is hit with t > Epsilon; the caller applies its own upper bound (closest: t < best.t; shadow: t <= dist).
 __device__ __forceinline__ bool moller_trumbore(const Ray& r, f3 v0, f3 e1, f3 e2, float& t, float& u, float& v) {
@@ -175,8 +192,9 @@ __device__ __forceinline__ bool traverse_reference(const SceneView& s, const Ray
 
 // ---------------------------------------------------------------------------------------------------------------------
 // LBVH traversal: 64-byte nodes holding both children's boxes, near child first, deferred child kept with its entry
-// distance so it can be dropped without a fetch once a closer hit is known.  Box and triangle arithmetic is the same as
-// above, so t/u/v of a given (ray, triangle) pair are bit-identical in both modes.
+// distance so it can be dropped without a fetch once a closer hit is known.  Triangle arithmetic is the same as above,
+// so t/u/v of a given (ray, triangle) pair are bit-identical in both modes; the box test is the FMA form over padded
+// boxes.  (This per-thread form serves the aux / debug kernels; the wavefront uses the persistent form in trace.cu.)
 // Node layout (4 x float4): (lmin, left_ref) (lmax, right_ref) (rmin, -) (rmax, -).
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool ANY>
@@ -187,12 +205,14 @@ __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, 
   float stack_dst[RTB_STACK_LBVH];
   int sp = 0;
   int32_t cur = s.root;
+  const f3 inv = safe_inverse(r.d);
+  const f3 ood = r.o * inv;
   for (;;) {
     if (cur >= 0) {
       const float4 n0 = __ldg(&s.nodes[4 * cur]), n1 = __ldg(&s.nodes[4 * cur + 1]);
       const float4 n2 = __ldg(&s.nodes[4 * cur + 2]), n3 = __ldg(&s.nodes[4 * cur + 3]);
-      const float dl = slab_entry(r, mk3(n0), mk3(n1));
-      const float dr = slab_entry(r, mk3(n2), mk3(n3));
+      const float dl = slab_entry_fma(inv, ood, mk3(n0), mk3(n1));
+      const float dr = slab_entry_fma(inv, ood, mk3(n2), mk3(n3));
       const bool hl = ANY ? !(dl > t_limit) : !(dl >= best.t);
       const bool hr = ANY ? !(dr > t_limit) : !(dr >= best.t);
       const int32_t lref = __float_as_int(n0.w), rref = __float_as_int(n1.w);

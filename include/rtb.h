@@ -113,7 +113,8 @@ typedef struct rtb_stats {
   int32_t n_devices;
   float ms_upload, ms_build;      /* last rtb_upload_scene: host prep + H2D, device build (flatten + BVH) */
   float ms_render_device;         /* last render: first launch -> last kernel, CUDA events, max over devices */
-  float ms_trace, ms_shadow, ms_resolve; /* per kernel family, summed over depths/chunks on device 0 (only when profiling enabled) */
+  float ms_traverse, ms_shade, ms_resolve; /* per kernel family (k_traverse = all BVH queries, k_shade, k_resolve), summed over
+                                             depths/chunks on device 0; only when profiling is enabled */
   int64_t h2d_bytes, d2h_bytes;   /* bytes copied across PCIe by the last render call */
   int64_t reserved[4];
 } rtb_stats;
