@@ -379,7 +379,7 @@ int collect_stats(rtb_context* ctx) {
   st.rays_primary = st.rays_continuation = st.rays_shadow = st.paths_hit_primary = 0;
   st.ms_render_device = 0.0f;
   st.ms_traverse = st.ms_shade = st.ms_resolve = 0.0f;
-  int64_t overflow = 0;
+  int64_t overflow = 0, nodes = 0, tris = 0;
   for (auto& d : ctx->devs) {
     CK(ctx, cudaSetDevice(d.device));
     CK(ctx, cudaStreamSynchronize(d.stream));
@@ -387,7 +387,7 @@ int collect_stats(rtb_context* ctx) {
       unsigned long long t[8];
       CK(ctx, cudaMemcpy(t, d.q.totals, sizeof t, cudaMemcpyDeviceToHost));
       st.rays_primary += (int64_t)t[0]; st.rays_continuation += (int64_t)t[1]; st.rays_shadow += (int64_t)t[2];
-      st.paths_hit_primary += (int64_t)t[3]; overflow += (int64_t)t[4];
+      st.paths_hit_primary += (int64_t)t[3]; overflow += (int64_t)t[4]; nodes += (int64_t)t[5]; tris += (int64_t)t[6];
     }
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end) == cudaSuccess) st.ms_render_device = std::max(st.ms_render_device, ms);
@@ -399,6 +399,8 @@ int collect_stats(rtb_context* ctx) {
     }
   }
   st.reserved[0] = overflow;
+  st.reserved[1] = nodes;
+  st.reserved[2] = tris;
   cudaSetDevice(ctx->devs[0].device);
   return RTB_OK;
 }

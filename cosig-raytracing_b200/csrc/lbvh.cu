@@ -4,7 +4,7 @@
 //
 // Pipeline (all on one stream, no host round trip):
 //   k_centroid_bounds   min/max of the triangle centroids (warp shuffles + one atomic per block and component)
-//   k_morton            63-bit Morton key (21 bits per axis) of each centroid, value = emission index
+//   k_morton            63-bit Morton key (21 bits per axis, one scale: the centroids' bounding cube), value = emission index
 //   cub radix sort      keys + values
 //   k_hierarchy         Karras 2012 binary radix tree over the sorted keys (ties broken by index), parent links, ranges
 //   k_refit             bottom-up AABBs: each leaf thread climbs, the second arrival at a node merges its children
@@ -111,12 +111,14 @@ __device__ __forceinline__ unsigned long long spread21(unsigned v) {  // 21 bits
 
 __global__ void __launch_bounds__(kBlock) k_morton(const float4* __restrict__ raw, int32_t n, const unsigned* __restrict__ bounds,
                                                    unsigned long long* __restrict__ keys, int32_t* __restrict__ vals) {
-  float lo[3], scale[3];
+  // One scale for all three axes (the bounding CUBE of the centroids): Morton cells stay cubical, so a flat scene does not
+  // spend a third of its split planes on its thin axis.
+  float lo[3], scale[3], ext_max = 0.0f;
   for (int a = 0; a < 3; a++) {
     lo[a] = o2f(bounds[a]);
-    const float ext = o2f(bounds[3 + a]) - lo[a];
-    scale[a] = ext > 0.0f ? 2097152.0f / ext : 0.0f;
+    ext_max = fmaxf(ext_max, o2f(bounds[3 + a]) - lo[a]);
   }
+  for (int a = 0; a < 3; a++) scale[a] = ext_max > 0.0f ? 2097152.0f / ext_max : 0.0f;
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     unsigned q[3];
     for (int a = 0; a < 3; a++) {

@@ -119,6 +119,7 @@ struct QueueView {
   float4* accum;          // per slot: running sampleColor
   int32_t* counters;      // 4 blocks of depth_cap ints: ray queue sizes | shadow queue sizes | traverse fetch | (spare)
   unsigned long long* totals;  // [0] primary rays [1] continuation rays [2] shadow rays [3] primary hits [4] stack overflows
+                               // [5] BVH nodes fetched [6] triangles tested (all rays of the frame)
   int32_t depth_cap;      // D (>= max_depth + 1)
 };
 #define RTB_CNT_RAY(q, d) ((q).counters[(d)])

@@ -99,12 +99,20 @@ struct Lane {
   int32_t tri;        // closest: leaf-order triangle or -1; shadow: 0 when an occluder was found, -1 otherwise
   int32_t item;       // work item, -1 = idle
   bool shadow;
+  bool done;          // traversal finished, result not yet published (published in batches, see RTB_REFILL_MIN)
 };
+
+// Lanes are refilled (and finished lanes published) only when at least this many of the warp's 32 lanes are out of work:
+// the refill path (queue loads or in-kernel ray generation) then runs with a well-filled warp instead of 1-2 lanes.
+#ifndef RTB_REFILL_MIN
+#define RTB_REFILL_MIN 8
+#endif
 
 // Loads work item `item` into the lane.  Returns false when the item needs no traversal (padding slot).
 template <bool PRIMARY>
 __device__ __forceinline__ bool lane_load(Lane& L, const FrameParams& f, const QueueView& q, const ChunkView& c, int32_t item, int32_t n_closest, int in_q) {
   L.item = item;
+  L.done = false;
   L.u = 0.0f; L.v = 0.0f; L.tri = -1;
   if (PRIMARY || item < n_closest) {
     L.shadow = false;
@@ -140,6 +148,7 @@ __device__ __forceinline__ void lane_finish(Lane& L, const QueueView& q, int32_t
     q.accum[slot] = make_float4(prev.x + inc.x, prev.y + inc.y, prev.z + inc.z, 0.0f);
   }
   L.item = -1;
+  L.done = false;
 }
 
 // Triangle test shared by both flavours.  Returns true when a shadow ray found its occluder.
@@ -158,7 +167,7 @@ __device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, 
 // k_traverse, LBVH flavour: ordered traversal over 64-byte two-box nodes (see lbvh.cu for the layout).
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool PRIMARY>
-__global__ void __launch_bounds__(kBlock) k_traverse_lbvh(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth) {
+__global__ void __launch_bounds__(kBlock, 4) k_traverse_lbvh(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth) {
   const int lane = threadIdx.x & 31;
   const int32_t n_closest = PRIMARY ? c.n_slots : RTB_CNT_RAY(q, depth);
   const int32_t n_shadow = (PRIMARY || depth == 0) ? 0 : RTB_CNT_SHADOW(q, depth - 1);
@@ -174,29 +183,34 @@ __global__ void __launch_bounds__(kBlock) k_traverse_lbvh(const FrameParams f, c
   int32_t cur = RTB_REF_DONE;
   f3 ood = mk3(0.0f, 0.0f, 0.0f);
   Lane L;
-  L.item = -1; L.shadow = false; L.t = 0.0f; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
+  L.item = -1; L.shadow = false; L.done = false; L.t = 0.0f; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
   L.o = L.d = L.inv = mk3(0.0f, 0.0f, 0.0f);
   WorkPool pool;
-  unsigned n_primary = 0, overflow = 0;
+  unsigned n_primary = 0, overflow = 0, n_nodes = 0, n_tris = 0;
 
   for (;;) {
-    // ---- refill idle lanes ----
-    const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, L.item < 0, lane);
-    if (item >= 0 && lane_load<PRIMARY>(L, f, q, c, item, n_closest, in_q)) {
-      if (PRIMARY) n_primary++;
-      L.inv = safe_inverse(L.d);
-      ood = L.o * L.inv;
-      sp = 0;
-      cur = s.n_tris > 0 ? s.root : RTB_REF_DONE;
-      if (cur == RTB_REF_DONE) lane_finish(L, q, n_closest);
-    }
-    if (__ballot_sync(kFull, L.item >= 0) == 0) {
-      if (pool.exhausted) break;
-      continue;  // only padding slots were drawn: take more
+    // ---- publish finished lanes and refill, in batches ----
+    const int n_out = __popc(__ballot_sync(kFull, L.item < 0 || L.done));
+    if (n_out >= RTB_REFILL_MIN) {
+      if (L.item >= 0 && L.done) lane_finish(L, q, n_closest);
+      const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, L.item < 0, lane);
+      if (item >= 0 && lane_load<PRIMARY>(L, f, q, c, item, n_closest, in_q)) {
+        if (PRIMARY) n_primary++;
+        L.inv = safe_inverse(L.d);
+        ood = L.o * L.inv;
+        sp = 0;
+        cur = s.n_tris > 0 ? s.root : RTB_REF_DONE;
+        L.done = cur == RTB_REF_DONE;
+      }
+      if (__ballot_sync(kFull, L.item >= 0 && !L.done) == 0) {
+        if (__ballot_sync(kFull, L.item >= 0) == 0 && pool.exhausted) break;
+        continue;  // only padding slots / trivially finished items were drawn: publish and take more
+      }
     }
 
     // ---- inner nodes: descend until this lane holds a leaf (or runs out of work) ----
     while (cur >= 0) {
+      n_nodes++;
       const float4 n0 = __ldg(&s.nodes[4 * cur]), n1 = __ldg(&s.nodes[4 * cur + 1]);
       const float4 n2 = __ldg(&s.nodes[4 * cur + 2]), n3 = __ldg(&s.nodes[4 * cur + 3]);
       const float dl = slab_entry_fma(L.inv, ood, mk3(n0), mk3(n1));
@@ -227,6 +241,7 @@ __global__ void __launch_bounds__(kBlock) k_traverse_lbvh(const FrameParams f, c
       const int32_t code = ~cur;
       const int32_t first = code >> 3, count = (code & 7) + 1;
       bool occluded = false;
+      n_tris += count;
       for (int32_t i = 0; i < count && !occluded; i++) occluded = lane_test_triangle(L, s, first + i);
       cur = RTB_REF_DONE;
       if (!occluded)
@@ -236,16 +251,20 @@ __global__ void __launch_bounds__(kBlock) k_traverse_lbvh(const FrameParams f, c
           if (L.shadow ? !(dd > L.t) : !(dd >= L.t)) { cur = stack_ref[sp]; break; }
         }
     }
-    if (cur == RTB_REF_DONE && L.item >= 0) { sp = 0; lane_finish(L, q, n_closest); }
+    if (cur == RTB_REF_DONE && L.item >= 0) { sp = 0; L.done = true; }
   }
 
   for (int o = 16; o > 0; o >>= 1) {
     n_primary += __shfl_xor_sync(kFull, n_primary, o);
     overflow += __shfl_xor_sync(kFull, overflow, o);
+    n_nodes += __shfl_xor_sync(kFull, n_nodes, o);
+    n_tris += __shfl_xor_sync(kFull, n_tris, o);
   }
   if (lane == 0) {
     if (PRIMARY && n_primary) atomicAdd(&q.totals[0], (unsigned long long)n_primary);
     if (overflow) atomicAdd(&q.totals[4], (unsigned long long)overflow);
+    if (n_nodes) atomicAdd(&q.totals[5], (unsigned long long)n_nodes);
+    if (n_tris) atomicAdd(&q.totals[6], (unsigned long long)n_tris);
   }
 }
 
@@ -254,7 +273,7 @@ __global__ void __launch_bounds__(kBlock) k_traverse_lbvh(const FrameParams f, c
 // culled when its own slab entry >= best t; leaves of any size.  Same results as the reference for every ray.
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool PRIMARY>
-__global__ void __launch_bounds__(kBlock) k_traverse_ref(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth) {
+__global__ void __launch_bounds__(kBlock, 4) k_traverse_ref(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth) {
   const int lane = threadIdx.x & 31;
   const int32_t n_closest = PRIMARY ? c.n_slots : RTB_CNT_RAY(q, depth);
   const int32_t n_shadow = (PRIMARY || depth == 0) ? 0 : RTB_CNT_SHADOW(q, depth - 1);
@@ -268,27 +287,32 @@ __global__ void __launch_bounds__(kBlock) k_traverse_ref(const FrameParams f, co
   int sp = 0;
   int32_t leaf_first = 0, leaf_count = 0;
   Lane L;
-  L.item = -1; L.shadow = false; L.t = 0.0f; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
+  L.item = -1; L.shadow = false; L.done = false; L.t = 0.0f; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
   L.o = L.d = L.inv = mk3(0.0f, 0.0f, 0.0f);
   WorkPool pool;
-  unsigned n_primary = 0, overflow = 0;
+  unsigned n_primary = 0, overflow = 0, n_nodes = 0, n_tris = 0;
 
   for (;;) {
-    const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, L.item < 0, lane);
-    if (item >= 0 && lane_load<PRIMARY>(L, f, q, c, item, n_closest, in_q)) {
-      if (PRIMARY) n_primary++;
-      L.inv = mk3(1.0f / L.d.x, 1.0f / L.d.y, 1.0f / L.d.z);  // CreateRay :142 / :398
-      sp = 0; leaf_count = 0;
-      if (s.n_nodes > 0) stack[sp++] = 0;
-      else lane_finish(L, q, n_closest);
-    }
-    if (__ballot_sync(kFull, L.item >= 0) == 0) {
-      if (pool.exhausted) break;
-      continue;
+    const int n_out = __popc(__ballot_sync(kFull, L.item < 0 || L.done));
+    if (n_out >= RTB_REFILL_MIN) {
+      if (L.item >= 0 && L.done) lane_finish(L, q, n_closest);
+      const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, L.item < 0, lane);
+      if (item >= 0 && lane_load<PRIMARY>(L, f, q, c, item, n_closest, in_q)) {
+        if (PRIMARY) n_primary++;
+        L.inv = mk3(1.0f / L.d.x, 1.0f / L.d.y, 1.0f / L.d.z);  // CreateRay :142 / :398
+        sp = 0; leaf_count = 0;
+        if (s.n_nodes > 0) stack[sp++] = 0;
+        else L.done = true;
+      }
+      if (__ballot_sync(kFull, L.item >= 0 && !L.done) == 0) {
+        if (__ballot_sync(kFull, L.item >= 0) == 0 && pool.exhausted) break;
+        continue;
+      }
     }
 
     while (leaf_count == 0 && sp > 0) {
       const int32_t ni = stack[--sp];
+      n_nodes++;
       const float4 lo = __ldg(&s.nodes[2 * ni]), hi = __ldg(&s.nodes[2 * ni + 1]);
       Ray r; r.o = L.o; r.d = L.d; r.inv = L.inv;
       const float dst = slab_entry(r, mk3(lo), mk3(hi));
@@ -300,20 +324,25 @@ __global__ void __launch_bounds__(kBlock) k_traverse_ref(const FrameParams f, co
     }
     if (leaf_count > 0) {
       bool occluded = false;
+      n_tris += leaf_count;
       for (int32_t i = 0; i < leaf_count && !occluded; i++) occluded = lane_test_triangle(L, s, leaf_first + i);
       leaf_count = 0;
       if (occluded) sp = 0;
     }
-    if (sp == 0 && leaf_count == 0 && L.item >= 0) lane_finish(L, q, n_closest);
+    if (sp == 0 && leaf_count == 0 && L.item >= 0) L.done = true;
   }
 
   for (int o = 16; o > 0; o >>= 1) {
     n_primary += __shfl_xor_sync(kFull, n_primary, o);
     overflow += __shfl_xor_sync(kFull, overflow, o);
+    n_nodes += __shfl_xor_sync(kFull, n_nodes, o);
+    n_tris += __shfl_xor_sync(kFull, n_tris, o);
   }
   if (lane == 0) {
     if (PRIMARY && n_primary) atomicAdd(&q.totals[0], (unsigned long long)n_primary);
     if (overflow) atomicAdd(&q.totals[4], (unsigned long long)overflow);
+    if (n_nodes) atomicAdd(&q.totals[5], (unsigned long long)n_nodes);
+    if (n_tris) atomicAdd(&q.totals[6], (unsigned long long)n_tris);
   }
 }
 

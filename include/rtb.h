@@ -116,7 +116,7 @@ typedef struct rtb_stats {
   float ms_traverse, ms_shade, ms_resolve; /* per kernel family (k_traverse = all BVH queries, k_shade, k_resolve), summed over
                                              depths/chunks on device 0; only when profiling is enabled */
   int64_t h2d_bytes, d2h_bytes;   /* bytes copied across PCIe by the last render call */
-  int64_t reserved[4];
+  int64_t reserved[4];            /* [0] traversal-stack overflows (must be 0) [1] BVH nodes fetched [2] triangles tested */
 } rtb_stats;
 
 /* new RayTracer() + SetComputeShader, RayTracer.cs:17-32.  device_ids == NULL -> {0}.  With n_devices > 1 the frame is
