@@ -355,3 +355,17 @@ def test_c4_full_size_properties(tracers, oracle):
     rows = np.arange(0, 2160, 16)
     assert (tex_r[rows] == ref["rgba8"][rows]).all()
     assert_rgb_parity(tex_l[rows], ref["rgba8"][rows], "C4 LBVH vs oracle rows")
+
+
+# ---- the C++ host mirror drives the same path -----------------------------------------------------------------------------------
+def test_cpp_host_mirror_render_matches_oracle(samples, tmp_path):
+    import subprocess
+    from test_host_cpu import build_cpp_test
+    exe = build_cpp_test()
+    obj, osc, _ = samples["test_scene_1"]
+    scene_file, out = tmp_path / "scene.txt", tmp_path / "out.rgba"
+    scene_file.write_bytes(synth.scene_to_text(obj).encode())
+    r = subprocess.run([exe, "render", str(scene_file), str(out), "160", "120", "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(out, np.uint8).reshape(120, 160, 4)
+    assert (got == osc.render(params(160, 120, 4))["rgba8"]).all()

@@ -287,3 +287,20 @@ def test_gather_bands_world_size_2_gloo(h):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+# ---- the C++ host mirror (include/rtb_raytracer.hpp) --------------------------------------------------------------------------
+def build_cpp_test():
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp")], stdout=subprocess.DEVNULL)
+    return os.path.join(ROOT, "tests", "cpp", "host_mirror_test")
+
+
+def test_cpp_host_mirror_builds_and_runs_host_checks(pkg, tmp_path):
+    import subprocess
+    exe = build_cpp_test()
+    scene_file = tmp_path / "scene.txt"
+    scene_file.write_bytes(synth.scene_to_text(synth.sample_scene("test_scene_2")).encode())
+    r = subprocess.run([exe, "host", str(scene_file)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "host OK 8 transformations" in r.stdout
