@@ -48,7 +48,7 @@ struct DeviceState {
   int32_t *aux_prim = nullptr, *aux_mat = nullptr;
   float* aux_t = nullptr;
   size_t aux_px = 0;
-  int grid_traverse[2][2] = {{0, 0}, {0, 0}};
+  int grid_traverse[2] = {0, 0};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_trace, prof_shadow, prof_resolve;
   size_t prof_used[3] = {0, 0, 0};
 };
@@ -266,10 +266,7 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
     const int rc = ensure_queues(ctx, d, capacity, depth_cap);
     if (rc != RTB_OK) return rc;
   }
-  if (!d.grid_traverse[bvh][0]) {
-    d.grid_traverse[bvh][0] = d.sm_count * traverse_blocks_per_sm(bvh, false);
-    d.grid_traverse[bvh][1] = d.sm_count * traverse_blocks_per_sm(bvh, true);
-  }
+  if (!d.grid_traverse[bvh]) d.grid_traverse[bvh] = d.sm_count * traverse_blocks_per_sm(bvh);
   const int shade_grid = d.sm_count * 8;
   const QueueView qv = queue_view(d.q);
   CK(ctx, cudaEventRecord(d.ev_begin, d.stream));
@@ -299,13 +296,13 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
       CK(ctx, cudaMemsetAsync(qv.accum, 0, (size_t)c.n_slots * sizeof(float4), d.stream));
     } else {
       CK(ctx, cudaMemsetAsync(d.q.counters, 0, (size_t)d.q.depth_cap * 4 * sizeof(int32_t), d.stream));
-      // depth d: traverse (closest-hit rays of depth d + shadow rays emitted at depth d-1), then shade.  One more traverse
+      // raygen fills the depth-0 queue; depth d: traverse (closest-hit rays of depth d + shadow rays emitted at depth d-1), then shade.  One more traverse
       // at the end serves the last depth's shadow rays.
+      timed(1, [&] { launch_raygen(bvh, f, sv, qv, c, shade_grid, d.stream); });
       for (int depth = 0; depth <= f.max_depth; depth++) {
         if (depth > 0 && ctx->cancel && *ctx->cancel) { cudaStreamSynchronize(d.stream); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
-        if (depth < f.max_depth || f.en_diffuse == 1)
-          timed(0, [&] { launch_traverse(bvh, depth == 0, f, sv, qv, c, depth, d.grid_traverse[bvh][depth == 0], d.stream); });
-        if (depth < f.max_depth) timed(1, [&] { launch_shade(depth == 0, f, sv, qv, c, depth, shade_grid, d.stream); });
+        if (depth < f.max_depth || f.en_diffuse == 1) timed(0, [&] { launch_traverse(bvh, sv, qv, depth, d.grid_traverse[bvh], d.stream); });
+        if (depth < f.max_depth) timed(1, [&] { launch_shade(f, sv, qv, c, depth, shade_grid, d.stream); });
       }
     }
     timed(2, [&] { launch_resolve(f, qv, c, dst, resolve_grid, d.stream); });

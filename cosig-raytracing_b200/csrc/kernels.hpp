@@ -30,14 +30,14 @@ size_t lbvh_workspace_bytes(int32_t n);
 cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaStream_t st);
 
 // ---- trace.cu (K3-K8: the per-pixel wavefront) --------------------------------------------------------------------------
-// `grid` = number of persistent blocks (sm_count * traverse_blocks_per_sm for k_traverse).
-void launch_traverse(int bvh, bool primary, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int grid,
-                     cudaStream_t st);
-void launch_shade(bool primary, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int grid, cudaStream_t st);
+void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st);
+// `grid` = number of persistent blocks (sm_count * traverse_blocks_per_sm).
+void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int grid, cudaStream_t st);
+void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int grid, cudaStream_t st);
 void launch_resolve(const FrameParams& f, const QueueView& q, const ChunkView& c, void* dst, int grid, cudaStream_t st);
 void launch_debug(int bvh, const FrameParams& f, const SceneView& s, const ChunkView& c, void* dst, int grid, cudaStream_t st);
 void launch_aux(int bvh, const FrameParams& f, const SceneView& s, int32_t* prim, float* t, int32_t* mat, int grid, cudaStream_t st);
 // Resident blocks per SM of the persistent traversal kernel (occupancy query), by variant.
-int traverse_blocks_per_sm(int bvh, bool primary);
+int traverse_blocks_per_sm(int bvh);
 
 }  // namespace rtb

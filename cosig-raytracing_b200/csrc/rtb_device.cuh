@@ -21,6 +21,7 @@ namespace rtb {
 #define RTB_LEAF_MAX 4     /* LBVH leaf size (<= 8) */
 #endif
 #define RTB_REF_DONE ((int32_t)0x80000000) /* LBVH traversal: "no more work" reference (never a valid leaf: n < 2^28) */
+#define RTB_REF_LEAF ((int32_t)0x80000001) /* LBVH traversal: the lane is inside a leaf (triangle cursor in registers) */
 
 struct f3 { float x, y, z; };
 __host__ __device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }

@@ -1,15 +1,18 @@
 // trace.cu — the wavefront kernels of the per-pixel path (replaces CSMain, Assets/Shaders/BVHRayTracing.compute:273-511).
 //
-// One depth d of the reference's `for depth` loop (:360-473) is two launches:
+//   k_raygen<BVH>              primary rays :283-349, one warp per 8x4 pixel tile at full SIMD width; rays that miss the
+//                              scene's root box get the background at once (:364-368), the others are compacted into
+//                              the depth-0 ray queue.
 //
-//   k_traverse<BVH, PRIMARY>   every BVH query pending at this point, in ONE persistent kernel: the closest-hit rays of
-//                              depth d (:362; for d = 0 they are generated in-kernel from the pixel index, :283-349) and the
-//                              shadow rays emitted at depth d-1 (:395-406, as any-hit queries).  Lanes are refilled
-//                              individually from a per-warp pool (one atomicAdd per 32 work items), so a long ray never
-//                              idles the other 31 lanes; traversal is "while-while": all lanes descend inner nodes, then
-//                              all lanes intersect their leaf.  A closest-hit ray ends by writing a 16-byte hit record,
-//                              a shadow ray by adding the lit or unlit increment of :418 to its slot's sampleColor.
-//   k_shade<PRIMARY>           miss/background :364-368, shading :370-418 (emits the shadow ray with both candidate
+// One depth d of the reference's `for depth` loop (:360-473) is then two launches:
+//
+//   k_traverse_{ref,lbvh}      every BVH query pending at this point, in ONE persistent kernel: the closest-hit rays of
+//                              depth d (:362) and the shadow rays emitted at depth d-1 (:395-406, as any-hit queries).
+//                              Warps claim 32 work items with one atomicAdd (RTB_REFILL_MIN < 32 additionally refills
+//                              individual lanes); traversal is "while-while": all lanes descend inner nodes, then all
+//                              lanes intersect their leaf.  A closest-hit ray ends by writing a 16-byte hit record, a
+//                              shadow ray by adding the lit or unlit increment of :418 to its slot's sampleColor.
+//   k_shade                    miss/background :364-368, shading :370-418 (emits the shadow ray with both candidate
 //                              increments), continuation :420-473, compacted into the next depth's ray queue with one
 //                              ballot + one atomicAdd per warp and queue.
 //
@@ -95,45 +98,39 @@ __device__ __forceinline__ int32_t pool_take(WorkPool& pool, int32_t* fetch_coun
 // Lane state shared by both traversal flavours.
 struct Lane {
   f3 o, d, inv;       // inv: exact reciprocal (reference mode) or safe_inverse (LBVH mode)
-  float t, u, v;      // closest hit so far; for shadow rays t holds distToLight (the acceptance bound)
+  float t, u, v;      // closest hit so far; for shadow rays t = nextafter(distToLight): "t < L.t" <=> "t <= distToLight"
   int32_t tri;        // closest: leaf-order triangle or -1; shadow: 0 when an occluder was found, -1 otherwise
   int32_t item;       // work item, -1 = idle
   bool shadow;
   bool done;          // traversal finished, result not yet published (published in batches, see RTB_REFILL_MIN)
 };
 
-// Lanes are refilled (and finished lanes published) only when at least this many of the warp's 32 lanes are out of work:
-// the refill path (queue loads or in-kernel ray generation) then runs with a well-filled warp instead of 1-2 lanes.
+// Lanes are refilled (and finished lanes published) only when at least this many of the warp's 32 lanes are out of work.
+// Measured on the B200 (C4): 32 — i.e. a warp takes 32 fresh rays when all of its lanes are done — beats 8 / 16 / 24 by
+// 4-20 %: rays that start together descend the upper tree in lockstep and share its cache lines.
 #ifndef RTB_REFILL_MIN
-#define RTB_REFILL_MIN 8
+#define RTB_REFILL_MIN 32
 #endif
 
-// Loads work item `item` into the lane.  Returns false when the item needs no traversal (padding slot).
-template <bool PRIMARY>
-__device__ __forceinline__ bool lane_load(Lane& L, const FrameParams& f, const QueueView& q, const ChunkView& c, int32_t item, int32_t n_closest, int in_q) {
+// Loads work item `item` into the lane.
+__device__ __forceinline__ void lane_load(Lane& L, const QueueView& q, int32_t item, int32_t n_closest, int in_q) {
   L.item = item;
   L.done = false;
   L.u = 0.0f; L.v = 0.0f; L.tri = -1;
-  if (PRIMARY || item < n_closest) {
+  if (item < n_closest) {
+    const float4 o = __ldcs(&q.ray_o[in_q][item]), d = __ldcs(&q.ray_d[in_q][item]);
     L.shadow = false;
     L.t = RTB_INFINITY;
-    if (PRIMARY) {
-      Ray r;
-      int px, py, sample;
-      if (!primary_ray_of_slot(f, c, item, r, px, py, sample)) { L.item = -1; return false; }
-      L.o = r.o; L.d = r.d;
-    } else {
-      const float4 o = __ldcs(&q.ray_o[in_q][item]), d = __ldcs(&q.ray_d[in_q][item]);
-      L.o = mk3(o); L.d = mk3(d);
-    }
+    L.o = mk3(o); L.d = mk3(d);
   } else {
     const int32_t j = item - n_closest;
     const float4 o = __ldcs(&q.sh_o[j]), d = __ldcs(&q.sh_d[j]);
     L.shadow = true;
     L.o = mk3(o); L.d = mk3(d);
-    L.t = o.w;
+    // compute:406 shadows iff hit.t <= distToLight; with the bound one ulp up, the closest-hit comparisons ("entry >= bound"
+    // skips a box, "t < bound" accepts a triangle) decide exactly that.
+    L.t = nextafterf(o.w, INFINITY);
   }
-  return true;
 }
 
 // A finished lane publishes its result.
@@ -157,24 +154,23 @@ __device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, 
   Ray r; r.o = L.o; r.d = L.d;
   float t, u, v;
   if (!moller_trumbore(r, mk3(a), mk3(b), mk3(c), t, u, v)) return false;
-  if (L.shadow) {
-    if (t <= L.t) { L.tri = 0; return true; }
-  } else if (t < L.t) { L.t = t; L.u = u; L.v = v; L.tri = tri; }
+  if (!(t < L.t)) return false;
+  if (L.shadow) { L.tri = 0; return true; }
+  L.t = t; L.u = u; L.v = v; L.tri = tri;
   return false;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_traverse, LBVH flavour: ordered traversal over 64-byte two-box nodes (see lbvh.cu for the layout).
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool PRIMARY>
-__global__ void __launch_bounds__(kBlock, 4) k_traverse_lbvh(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth) {
+__global__ void __launch_bounds__(kBlock, 4) k_traverse_lbvh(const SceneView s, const QueueView q, const int depth) {
   const int lane = threadIdx.x & 31;
-  const int32_t n_closest = PRIMARY ? c.n_slots : RTB_CNT_RAY(q, depth);
-  const int32_t n_shadow = (PRIMARY || depth == 0) ? 0 : RTB_CNT_SHADOW(q, depth - 1);
+  const int32_t n_closest = RTB_CNT_RAY(q, depth);
+  const int32_t n_shadow = depth == 0 ? 0 : RTB_CNT_SHADOW(q, depth - 1);
   const int32_t total = n_closest + n_shadow;
   const int in_q = depth & 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    if (!PRIMARY && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
+    if (depth > 0 && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
     if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
   }
   int32_t stack_ref[RTB_STACK_LBVH];
@@ -186,7 +182,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_lbvh(const FrameParams f
   L.item = -1; L.shadow = false; L.done = false; L.t = 0.0f; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
   L.o = L.d = L.inv = mk3(0.0f, 0.0f, 0.0f);
   WorkPool pool;
-  unsigned n_primary = 0, overflow = 0, n_nodes = 0, n_tris = 0;
+  unsigned overflow = 0, n_nodes = 0, n_tris = 0;
 
   for (;;) {
     // ---- publish finished lanes and refill, in batches ----
@@ -194,8 +190,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_lbvh(const FrameParams f
     if (n_out >= RTB_REFILL_MIN) {
       if (L.item >= 0 && L.done) lane_finish(L, q, n_closest);
       const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, L.item < 0, lane);
-      if (item >= 0 && lane_load<PRIMARY>(L, f, q, c, item, n_closest, in_q)) {
-        if (PRIMARY) n_primary++;
+      if (item >= 0) {
+        lane_load(L, q, item, n_closest, in_q);
         L.inv = safe_inverse(L.d);
         ood = L.o * L.inv;
         sp = 0;
@@ -213,11 +209,9 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_lbvh(const FrameParams f
       n_nodes++;
       const float4 n0 = __ldg(&s.nodes[4 * cur]), n1 = __ldg(&s.nodes[4 * cur + 1]);
       const float4 n2 = __ldg(&s.nodes[4 * cur + 2]), n3 = __ldg(&s.nodes[4 * cur + 3]);
-      const float dl = slab_entry_fma(L.inv, ood, mk3(n0), mk3(n1));
-      const float dr = slab_entry_fma(L.inv, ood, mk3(n2), mk3(n3));
-      // closest: a box is skipped when entry >= best t (compute:246); shadow: when entry > distToLight
-      const bool hl = L.shadow ? !(dl > L.t) : !(dl >= L.t);
-      const bool hr = L.shadow ? !(dr > L.t) : !(dr >= L.t);
+      float dl, dr;
+      const bool hl = slab_hit_fma(L.inv, ood, mk3(n0), mk3(n1), L.t, dl);
+      const bool hr = slab_hit_fma(L.inv, ood, mk3(n2), mk3(n3), L.t, dr);
       const int32_t lref = __float_as_int(n0.w), rref = __float_as_int(n1.w);
       if (hl && hr) {
         const bool left_first = !(dr < dl);
@@ -231,7 +225,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_lbvh(const FrameParams f
         while (sp > 0) {
           sp--;
           const float dd = stack_dst[sp];
-          if (L.shadow ? !(dd > L.t) : !(dd >= L.t)) { cur = stack_ref[sp]; break; }
+          if (!(dd >= L.t)) { cur = stack_ref[sp]; break; }
         }
       }
     }
@@ -248,20 +242,18 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_lbvh(const FrameParams f
         while (sp > 0) {
           sp--;
           const float dd = stack_dst[sp];
-          if (L.shadow ? !(dd > L.t) : !(dd >= L.t)) { cur = stack_ref[sp]; break; }
+          if (!(dd >= L.t)) { cur = stack_ref[sp]; break; }
         }
     }
     if (cur == RTB_REF_DONE && L.item >= 0) { sp = 0; L.done = true; }
   }
 
   for (int o = 16; o > 0; o >>= 1) {
-    n_primary += __shfl_xor_sync(kFull, n_primary, o);
     overflow += __shfl_xor_sync(kFull, overflow, o);
     n_nodes += __shfl_xor_sync(kFull, n_nodes, o);
     n_tris += __shfl_xor_sync(kFull, n_tris, o);
   }
   if (lane == 0) {
-    if (PRIMARY && n_primary) atomicAdd(&q.totals[0], (unsigned long long)n_primary);
     if (overflow) atomicAdd(&q.totals[4], (unsigned long long)overflow);
     if (n_nodes) atomicAdd(&q.totals[5], (unsigned long long)n_nodes);
     if (n_tris) atomicAdd(&q.totals[6], (unsigned long long)n_tris);
@@ -272,15 +264,14 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_lbvh(const FrameParams f
 // k_traverse, reference flavour: TraverseBVH compute:225-267 — LIFO stack, left child first, no distance ordering, node
 // culled when its own slab entry >= best t; leaves of any size.  Same results as the reference for every ray.
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool PRIMARY>
-__global__ void __launch_bounds__(kBlock, 4) k_traverse_ref(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth) {
+__global__ void __launch_bounds__(kBlock, 4) k_traverse_ref(const SceneView s, const QueueView q, const int depth) {
   const int lane = threadIdx.x & 31;
-  const int32_t n_closest = PRIMARY ? c.n_slots : RTB_CNT_RAY(q, depth);
-  const int32_t n_shadow = (PRIMARY || depth == 0) ? 0 : RTB_CNT_SHADOW(q, depth - 1);
+  const int32_t n_closest = RTB_CNT_RAY(q, depth);
+  const int32_t n_shadow = depth == 0 ? 0 : RTB_CNT_SHADOW(q, depth - 1);
   const int32_t total = n_closest + n_shadow;
   const int in_q = depth & 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    if (!PRIMARY && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
+    if (depth > 0 && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
     if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
   }
   int32_t stack[RTB_STACK_REF];
@@ -290,15 +281,15 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_ref(const FrameParams f,
   L.item = -1; L.shadow = false; L.done = false; L.t = 0.0f; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
   L.o = L.d = L.inv = mk3(0.0f, 0.0f, 0.0f);
   WorkPool pool;
-  unsigned n_primary = 0, overflow = 0, n_nodes = 0, n_tris = 0;
+  unsigned overflow = 0, n_nodes = 0, n_tris = 0;
 
   for (;;) {
     const int n_out = __popc(__ballot_sync(kFull, L.item < 0 || L.done));
     if (n_out >= RTB_REFILL_MIN) {
       if (L.item >= 0 && L.done) lane_finish(L, q, n_closest);
       const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, L.item < 0, lane);
-      if (item >= 0 && lane_load<PRIMARY>(L, f, q, c, item, n_closest, in_q)) {
-        if (PRIMARY) n_primary++;
+      if (item >= 0) {
+        lane_load(L, q, item, n_closest, in_q);
         L.inv = mk3(1.0f / L.d.x, 1.0f / L.d.y, 1.0f / L.d.z);  // CreateRay :142 / :398
         sp = 0; leaf_count = 0;
         if (s.n_nodes > 0) stack[sp++] = 0;
@@ -316,7 +307,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_ref(const FrameParams f,
       const float4 lo = __ldg(&s.nodes[2 * ni]), hi = __ldg(&s.nodes[2 * ni + 1]);
       Ray r; r.o = L.o; r.d = L.d; r.inv = L.inv;
       const float dst = slab_entry(r, mk3(lo), mk3(hi));
-      if (L.shadow ? (dst > L.t) : (dst >= L.t)) continue;
+      if (dst >= L.t) continue;  // compute:246
       const int32_t count = __float_as_int(hi.w), left_or_first = __float_as_int(lo.w);
       if (count > 0) { leaf_first = left_or_first; leaf_count = count; }
       else if (sp + 2 <= RTB_STACK_REF) { stack[sp++] = left_or_first + 1; stack[sp++] = left_or_first; }
@@ -333,13 +324,11 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_ref(const FrameParams f,
   }
 
   for (int o = 16; o > 0; o >>= 1) {
-    n_primary += __shfl_xor_sync(kFull, n_primary, o);
     overflow += __shfl_xor_sync(kFull, overflow, o);
     n_nodes += __shfl_xor_sync(kFull, n_nodes, o);
     n_tris += __shfl_xor_sync(kFull, n_tris, o);
   }
   if (lane == 0) {
-    if (PRIMARY && n_primary) atomicAdd(&q.totals[0], (unsigned long long)n_primary);
     if (overflow) atomicAdd(&q.totals[4], (unsigned long long)overflow);
     if (n_nodes) atomicAdd(&q.totals[5], (unsigned long long)n_nodes);
     if (n_tris) atomicAdd(&q.totals[6], (unsigned long long)n_tris);
@@ -347,12 +336,71 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_ref(const FrameParams f,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// k_raygen (K3): primary rays of the chunk, CSMain compute:283-349.  A warp covers an 8x4 pixel tile of one sample.  The
+// scene's root box is tested here: a ray that misses it would be culled at the first traversal step anyway (compute:245-246),
+// so it takes the background now (:364-368) and never enters the queue.  sampleColor starts at 0 (:356).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int BVH>
+__global__ void __launch_bounds__(kBlock) k_raygen(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c) {
+  const int lane = threadIdx.x & 31;
+  const int32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned below = (1u << lane) - 1u;
+  // root box: reference BVH = node 0's own box; LBVH = union of the root record's two (padded) child boxes
+  f3 rmn = mk3(0.0f, 0.0f, 0.0f), rmx = rmn;
+  bool have_box = false;
+  if (BVH == RTB_BVH_REFERENCE) {
+    if (s.n_nodes > 0) { rmn = mk3(__ldg(&s.nodes[0])); rmx = mk3(__ldg(&s.nodes[1])); have_box = true; }
+  } else if (s.n_tris > 0 && s.root >= 0) {
+    const float4 n0 = __ldg(&s.nodes[4 * s.root]), n1 = __ldg(&s.nodes[4 * s.root + 1]);
+    const float4 n2 = __ldg(&s.nodes[4 * s.root + 2]), n3 = __ldg(&s.nodes[4 * s.root + 3]);
+    rmn = mk3(fminf(n0.x, n2.x), fminf(n0.y, n2.y), fminf(n0.z, n2.z));
+    rmx = mk3(fmaxf(n1.x, n3.x), fmaxf(n1.y, n3.y), fmaxf(n1.z, n3.z));
+    have_box = true;
+  }
+  const bool empty = (BVH == RTB_BVH_REFERENCE) ? s.n_nodes == 0 : s.n_tris == 0;
+  unsigned n_valid = 0;
+  for (int32_t base = warp_id * 32; base < c.n_slots; base += warps_total * 32) {
+    const int32_t slot = base + lane;
+    Ray ray;
+    int px, py, sample;
+    const bool valid = primary_ray_of_slot(f, c, slot, ray, px, py, sample);
+    bool survives = valid && !empty;
+    if (survives && have_box) {
+      if (BVH == RTB_BVH_REFERENCE) survives = !(slab_entry(ray, rmn, rmx) >= RTB_INFINITY);
+      else {
+        const f3 inv = safe_inverse(ray.d);
+        float entry;
+        survives = slab_hit_fma(inv, ray.o * inv, rmn, rmx, RTB_INFINITY, entry);
+      }
+    }
+    if (valid) {
+      n_valid++;
+      const f3 bg = mk3(1.0f, 1.0f, 1.0f) * mk3(f.bg[0], f.bg[1], f.bg[2]);  // attenuation (1,1,1) * _BackgroundColor
+      const f3 first = survives ? mk3(0.0f, 0.0f, 0.0f) : mk3(0.0f, 0.0f, 0.0f) + bg;
+      q.accum[slot] = make_float4(first.x, first.y, first.z, 0.0f);
+    }
+    const unsigned m = __ballot_sync(kFull, survives);
+    int32_t b = 0;
+    if (lane == 0 && m) b = atomicAdd(&RTB_CNT_RAY(q, 0), __popc(m));
+    b = __shfl_sync(kFull, b, 0);
+    if (survives) {
+      const int32_t at = b + __popc(m & below);
+      __stcs(&q.ray_o[0][at], make_float4(ray.o.x, ray.o.y, ray.o.z, __int_as_float(slot)));
+      __stcs(&q.ray_d[0][at], make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f));
+      __stcs(&q.ray_att[0][at], make_float4(1.0f, 1.0f, 1.0f, 0.0f));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) n_valid += __shfl_xor_sync(kFull, n_valid, o);
+  if (lane == 0 && n_valid) atomicAdd(&q.totals[0], (unsigned long long)n_valid);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // k_shade: everything the reference does with a closest-hit result at one depth.
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool PRIMARY>
 __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth) {
   const int lane = threadIdx.x & 31;
-  const int32_t n = PRIMARY ? c.n_slots : RTB_CNT_RAY(q, depth);
+  const int32_t n = RTB_CNT_RAY(q, depth);
   const int in_q = depth & 1, out_q = in_q ^ 1;
   const int32_t warps_total = (gridDim.x * blockDim.x) >> 5;
   const int32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -366,9 +414,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const Sce
     int px = 0, py = 0, sample = 0;
     Ray ray;
     f3 att = mk3(1.0f, 1.0f, 1.0f);
-    if (PRIMARY) {
-      active = active && primary_ray_of_slot(f, c, slot, ray, px, py, sample);
-    } else if (active) {
+    if (active) {
       const float4 o = __ldcs(&q.ray_o[in_q][idx]), d = __ldcs(&q.ray_d[in_q][idx]), a = __ldcs(&q.ray_att[in_q][idx]);
       slot = __float_as_int(o.w);
       ray.o = mk3(o); ray.d = mk3(d);
@@ -384,7 +430,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const Sce
     Hit hit; hit.t = hrec.x; hit.u = hrec.y; hit.v = hrec.z; hit.tri = __float_as_int(hrec.w);
     const bool found = active && hit.tri >= 0;
     f3 prev = mk3(0.0f, 0.0f, 0.0f);
-    if (!PRIMARY && active) prev = mk3(q.accum[slot]);
+    if (active) prev = mk3(q.accum[slot]);
 
     f3 pos = mk3(0.0f, 0.0f, 0.0f), nrm = pos;
     Material m;
@@ -397,7 +443,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const Sce
       q.accum[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f);
     }
     if (found) {
-      if (PRIMARY) n_hits++;
+      if (depth == 0) n_hits++;
       pos = ray.o + hit.t * ray.d;  // :183
       nrm = hit_normal(s, hit);
       m = fetch_material(s, __float_as_int(__ldg(&s.tri_isect[3 * hit.tri + 1]).w));
@@ -424,7 +470,6 @@ __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const Sce
         lit = (att * lit_local) * f.light_intensity;
         sh_origin = pos + nrm * RTB_OFFSET;  // :396
         sh_dist = hlsl_length(to_light);      // :401
-        if (PRIMARY) q.accum[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // k_traverse adds the increment later
       } else {
         const f3 sum = prev + unlit;
         q.accum[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f);
@@ -498,7 +543,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const Sce
   }
 
   for (int o = 16; o > 0; o >>= 1) n_hits += __shfl_xor_sync(kFull, n_hits, o);
-  if (PRIMARY && lane == 0 && n_hits) atomicAdd(&q.totals[3], (unsigned long long)n_hits);
+  if (lane == 0 && n_hits) atomicAdd(&q.totals[3], (unsigned long long)n_hits);
 }
 
 // Output row of a local row: the full frame (RTB_OUT_FRAME) or this rank's packed rows (RTB_OUT_COMPACT).
@@ -568,25 +613,22 @@ int blocks_per_sm(K kernel) {
 
 }  // namespace
 
-int traverse_blocks_per_sm(int bvh, bool primary) {
-  if (bvh == RTB_BVH_REFERENCE) return primary ? blocks_per_sm(k_traverse_ref<true>) : blocks_per_sm(k_traverse_ref<false>);
-  return primary ? blocks_per_sm(k_traverse_lbvh<true>) : blocks_per_sm(k_traverse_lbvh<false>);
+int traverse_blocks_per_sm(int bvh) {
+  return bvh == RTB_BVH_REFERENCE ? blocks_per_sm(k_traverse_ref) : blocks_per_sm(k_traverse_lbvh);
 }
 
-void launch_traverse(int bvh, bool primary, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int grid,
-                     cudaStream_t st) {
-  if (bvh == RTB_BVH_REFERENCE) {
-    if (primary) k_traverse_ref<true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
-    else k_traverse_ref<false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
-  } else {
-    if (primary) k_traverse_lbvh<true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
-    else k_traverse_lbvh<false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
-  }
+void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st) {
+  if (bvh == RTB_BVH_REFERENCE) k_raygen<RTB_BVH_REFERENCE><<<grid, kBlock, 0, st>>>(f, s, q, c);
+  else k_raygen<RTB_BVH_LBVH><<<grid, kBlock, 0, st>>>(f, s, q, c);
 }
 
-void launch_shade(bool primary, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int grid, cudaStream_t st) {
-  if (primary) k_shade<true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
-  else k_shade<false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
+void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int grid, cudaStream_t st) {
+  if (bvh == RTB_BVH_REFERENCE) k_traverse_ref<<<grid, kBlock, 0, st>>>(s, q, depth);
+  else k_traverse_lbvh<<<grid, kBlock, 0, st>>>(s, q, depth);
+}
+
+void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int grid, cudaStream_t st) {
+  k_shade<<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
 }
 
 void launch_resolve(const FrameParams& f, const QueueView& q, const ChunkView& c, void* dst, int grid, cudaStream_t st) {

@@ -124,6 +124,18 @@ __device__ __forceinline__ float slab_entry_fma(f3 inv, f3 ood, f3 mn, f3 mx) {
   if (dst_a > dst_b || dst_b < 0.0f) return RTB_INFINITY;
   return dst_a;
 }
+// The form the persistent LBVH traversal uses: entry = max(slab entries, 0), exit = min(slab exits, bound); the box is opened
+// iff entry <= exit.  Compared with "skip when entry >= bound" (compute:246) this also opens a box whose entry equals the
+// bound exactly — a superset, so no hit can be lost, and a triangle there cannot pass the strict "t < bound" test.
+__device__ __forceinline__ bool slab_hit_fma(f3 inv, f3 ood, f3 mn, f3 mx, float bound, float& entry) {
+  const float t0x = __fmaf_rn(mn.x, inv.x, -ood.x), t1x = __fmaf_rn(mx.x, inv.x, -ood.x);
+  const float t0y = __fmaf_rn(mn.y, inv.y, -ood.y), t1y = __fmaf_rn(mx.y, inv.y, -ood.y);
+  const float t0z = __fmaf_rn(mn.z, inv.z, -ood.z), t1z = __fmaf_rn(mx.z, inv.z, -ood.z);
+  entry = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+  const float exit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), bound));
+  return entry <= exit;
+}
+
 // Reciprocal direction for the FMA slab test: finite even for axis-parallel rays (a +-inf reciprocal would turn
 // fma(bound, inf, -origin*inf) into inf - inf = NaN), so such rays see slabs at +-1e18 * (bound - origin).
 __device__ __forceinline__ float safe_rcp(float d) { return fabsf(d) > 1e-18f ? 1.0f / d : copysignf(1e18f, d); }

@@ -369,3 +369,20 @@ def test_cpp_host_mirror_render_matches_oracle(samples, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     got = np.fromfile(out, np.uint8).reshape(120, 160, 4)
     assert (got == osc.render(params(160, 120, 4))["rgba8"]).all()
+
+
+def test_multi_device_context_matches_single(samples):
+    """One process driving two GPUs: bands over the devices, peers store into device 0's frame (needs >= 2 GPUs)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    obj = samples["test_scene_1"][0]
+    p = params(640, 360, 4)
+    one = rt_mod.RayTracer(devices=[0])
+    ref = one.RenderAsync(obj, p).pixels
+    one.close()
+    two = rt_mod.RayTracer(devices=[0, 1])
+    got = two.RenderAsync(obj, p).pixels
+    st = two.stats()
+    two.close()
+    assert st.n_devices == 2 and (got == ref).all()
