@@ -65,6 +65,7 @@ struct rtb_context {
   const volatile int32_t* cancel = nullptr;
   bool profiling = false;
   int64_t chunk_slots = 1 << 23;
+  int32_t tail_max = 196608;  // queues smaller than this finish in k_tail (RTB_TAIL_MAX; 0 = pure wavefront)
   std::vector<void*> ipc_opened;
 };
 
@@ -302,7 +303,10 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
       for (int depth = 0; depth <= f.max_depth; depth++) {
         if (depth > 0 && ctx->cancel && *ctx->cancel) { cudaStreamSynchronize(d.stream); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
         if (depth < f.max_depth || f.en_diffuse == 1) timed(0, [&] { launch_traverse(bvh, sv, qv, depth, d.grid_traverse[bvh], d.stream); });
-        if (depth < f.max_depth) timed(1, [&] { launch_shade(f, sv, qv, c, depth, shade_grid, d.stream); });
+        if (depth < f.max_depth) {
+          timed(1, [&] { launch_shade(f, sv, qv, c, depth, ctx->tail_max, shade_grid, d.stream); });
+          if (ctx->tail_max > 0) timed(0, [&] { launch_tail(bvh, f, sv, qv, c, depth, ctx->tail_max, d.sm_count * 4, d.stream); });
+        }
       }
     }
     timed(2, [&] { launch_resolve(f, qv, c, dst, resolve_grid, d.stream); });
@@ -445,6 +449,7 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
     const long long v = std::atoll(env);
     if (v >= 1024) ctx->chunk_slots = v;
   }
+  if (const char* env = std::getenv("RTB_TAIL_MAX")) ctx->tail_max = (int32_t)std::max(0LL, std::atoll(env));
   ctx->devs.resize(ids.size());
   for (size_t k = 0; k < ids.size(); k++) {
     DeviceState& d = ctx->devs[k];

@@ -33,7 +33,12 @@ cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaS
 void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st);
 // `grid` = number of persistent blocks (sm_count * traverse_blocks_per_sm).
 void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int grid, cudaStream_t st);
-void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int grid, cudaStream_t st);
+// k_shade handles depth `depth` when its queue holds >= tail_max rays; otherwise k_tail runs the remaining paths to their
+// end in one launch (both are launched every depth: the queue size lives on the device).
+void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,
+                  cudaStream_t st);
+void launch_tail(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,
+                 cudaStream_t st);
 void launch_resolve(const FrameParams& f, const QueueView& q, const ChunkView& c, void* dst, int grid, cudaStream_t st);
 void launch_debug(int bvh, const FrameParams& f, const SceneView& s, const ChunkView& c, void* dst, int grid, cudaStream_t st);
 void launch_aux(int bvh, const FrameParams& f, const SceneView& s, int32_t* prim, float* t, int32_t* mat, int grid, cudaStream_t st);

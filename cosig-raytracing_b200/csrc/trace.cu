@@ -396,11 +396,94 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const FrameParams f, const Sc
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k_shade: everything the reference does with a closest-hit result at one depth.
+// Shading of one closest hit, compute:370-473: what k_shade (wavefront) and k_tail (fused) have in common.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth) {
+struct Shaded {
+  bool emit_shadow;            // :393 — a shadow query decides between `lit` and `unlit`
+  f3 sh_origin, sh_dir;        // :395-398
+  float sh_dist;               // :401
+  f3 lit, unlit;               // the increment of sampleColor (:418) with / without the diffuse + specular terms
+  bool emit_ray;               // :424 — the path continues
+  f3 start, dir, att;          // :472 and the attenuation after :440/446/453
+};
+
+__device__ __forceinline__ void shade_hit(const FrameParams& f, const SceneView& s, const Ray& ray, f3 att, const Hit& hit, int px, int py, int sample,
+                                          int depth, Shaded& o) {
+  const f3 pos = ray.o + hit.t * ray.d;  // :183
+  const f3 nrm = hit_normal(s, hit);
+  const Material m = fetch_material(s, __float_as_int(__ldg(&s.tri_isect[3 * hit.tri + 1]).w));
+  f3 local = mk3(0.0f, 0.0f, 0.0f);
+  if (f.en_ambient == 1) local = local + m.color * m.ka;  // :379
+  f3 light_pos = mk3(f.light[0], f.light[1], f.light[2]);
+  if (f.soft == 1) {  // :383-388
+    const f3 j = random_unit_vector(mk3((float)px + (float)sample * 9.0f, ((float)py + (float)sample * 4.0f) + (float)depth, (float)sample)) * f.light_size;
+    light_pos = light_pos + j;
+  }
+  const f3 to_light = light_pos - pos;
+  o.sh_dir = hlsl_normalize(to_light);
+  const float n_dot_l = fmaxf(0.0f, dot3(nrm, o.sh_dir));
+  o.unlit = (att * local) * f.light_intensity;          // :418 when the shadow test fails or is not made
+  o.lit = o.unlit;
+  o.sh_origin = pos;
+  o.sh_dist = 0.0f;
+  o.emit_shadow = f.en_diffuse == 1 && n_dot_l > 0.0f;  // :393
+  if (o.emit_shadow) {
+    f3 lit_local = local + (m.color * m.kd) * n_dot_l;  // :408
+    if (f.en_specular == 1 && m.ks > 0.0f) {            // :409-414
+      const f3 view_dir = hlsl_normalize(negate(ray.d));
+      const f3 half_vec = hlsl_normalize(o.sh_dir + view_dir);
+      const float k = m.ks * pow32(fmaxf(dot3(nrm, half_vec), 0.0f));
+      lit_local = lit_local + mk3(k, k, k);
+    }
+    o.lit = (att * lit_local) * f.light_intensity;
+    o.sh_origin = pos + nrm * RTB_OFFSET;  // :396
+    o.sh_dist = hlsl_length(to_light);      // :401
+  }
+  // continuation, :420-473
+  o.emit_ray = false;
+  o.start = pos; o.dir = mk3(0.0f, 0.0f, 0.0f); o.att = att;
+  const bool should_reflect = m.ks > 0.0f;
+  const bool should_refract = (f.en_refraction == 1 && m.kr > 0.0f);
+  if ((should_reflect || should_refract) && depth + 1 < f.max_depth) {
+    f3 next_dir;
+    if (should_refract) {
+      const f3 I = hlsl_normalize(ray.d);
+      f3 N = nrm;
+      float eta = 1.0f / m.ior;
+      if (dot3(I, N) > 0.0f) { N = negate(N); eta = m.ior; }
+      const float cosi = dot3(negate(I), N);
+      const float k = 1.0f - (eta * eta) * (1.0f - cosi * cosi);
+      if (k >= 0.0f) {
+        next_dir = eta * I + (eta * cosi - sqrtf(k)) * N;
+        o.att = att * (m.color * m.kr);
+        o.start = pos + next_dir * RTB_OFFSET;
+      } else {  // total internal reflection
+        next_dir = hlsl_reflect(I, N);
+        o.att = att * (m.color * m.ks);
+        o.start = pos + N * RTB_OFFSET;
+      }
+    } else {
+      next_dir = hlsl_reflect(hlsl_normalize(ray.d), nrm);
+      o.att = att * (m.color * m.ks);
+      o.start = pos + nrm * RTB_OFFSET;
+    }
+    if (f.glossy == 1 && f.roughness > 0.0f) {  // :459-470
+      const f3 j = random_unit_vector(mk3(((float)px + (float)sample * 55.0f) + (float)depth, (float)py + (float)sample * 22.0f, (float)(depth * 13))) * f.roughness;
+      next_dir = hlsl_normalize(next_dir + j);
+    }
+    o.dir = hlsl_normalize(next_dir);  // :472
+    o.emit_ray = true;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_shade: everything the reference does with a closest-hit result at one depth, for queues of at least `tail_max` rays.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth,
+                                                  const int32_t tail_max) {
   const int lane = threadIdx.x & 31;
   const int32_t n = RTB_CNT_RAY(q, depth);
+  if (n < tail_max) return;  // k_tail finishes these paths
   const int in_q = depth & 1, out_q = in_q ^ 1;
   const int32_t warps_total = (gridDim.x * blockDim.x) >> 5;
   const int32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -409,141 +492,132 @@ __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const Sce
 
   for (int32_t base = warp_id * 32; base < n; base += warps_total * 32) {
     const int32_t idx = base + lane;
-    bool active = idx < n;
+    const bool active = idx < n;
     int32_t slot = idx;
     int px = 0, py = 0, sample = 0;
     Ray ray;
-    f3 att = mk3(1.0f, 1.0f, 1.0f);
+    ray.o = ray.d = ray.inv = mk3(0.0f, 0.0f, 0.0f);
+    f3 att = mk3(1.0f, 1.0f, 1.0f), prev = mk3(0.0f, 0.0f, 0.0f);
+    Hit hit; hit.t = 0.0f; hit.u = 0.0f; hit.v = 0.0f; hit.tri = -1;
     if (active) {
       const float4 o = __ldcs(&q.ray_o[in_q][idx]), d = __ldcs(&q.ray_d[in_q][idx]), a = __ldcs(&q.ray_att[in_q][idx]);
+      const float4 hrec = __ldcs(&q.hits[idx]);
       slot = __float_as_int(o.w);
       ray.o = mk3(o); ray.d = mk3(d);
       att = mk3(a);
+      hit.t = hrec.x; hit.u = hrec.y; hit.v = hrec.z; hit.tri = __float_as_int(hrec.w);
+      prev = mk3(q.accum[slot]);
       if (f.soft == 1 || f.glossy == 1) {  // the jitter hashes are seeded with the pixel and sample (:386,462)
         int local_row;
         slot_to_pixel(f, c, slot, px, local_row, sample);
         py = band_global_row(local_row, f.band_rank, f.band_world, f.band_rows);
       }
     }
-    float4 hrec = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
-    if (active) hrec = __ldcs(&q.hits[idx]);
-    Hit hit; hit.t = hrec.x; hit.u = hrec.y; hit.v = hrec.z; hit.tri = __float_as_int(hrec.w);
     const bool found = active && hit.tri >= 0;
-    f3 prev = mk3(0.0f, 0.0f, 0.0f);
-    if (active) prev = mk3(q.accum[slot]);
-
-    f3 pos = mk3(0.0f, 0.0f, 0.0f), nrm = pos;
-    Material m;
-    m.color = pos; m.ka = m.kd = m.ks = m.kr = 0.0f; m.ior = 1.0f;
-    bool emit_shadow = false;
-    f3 sh_origin = pos, sh_dir = pos, lit = pos, unlit = pos;
-    float sh_dist = 0.0f;
+    Shaded o;
+    o.emit_shadow = false; o.emit_ray = false;
     if (active && !found) {  // :364-368
       const f3 sum = prev + att * mk3(f.bg[0], f.bg[1], f.bg[2]);
       q.accum[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f);
     }
     if (found) {
       if (depth == 0) n_hits++;
-      pos = ray.o + hit.t * ray.d;  // :183
-      nrm = hit_normal(s, hit);
-      m = fetch_material(s, __float_as_int(__ldg(&s.tri_isect[3 * hit.tri + 1]).w));
-      f3 local = mk3(0.0f, 0.0f, 0.0f);
-      if (f.en_ambient == 1) local = local + m.color * m.ka;  // :379
-      f3 light_pos = mk3(f.light[0], f.light[1], f.light[2]);
-      if (f.soft == 1) {  // :383-388
-        const f3 j = random_unit_vector(mk3((float)px + (float)sample * 9.0f, ((float)py + (float)sample * 4.0f) + (float)depth, (float)sample)) * f.light_size;
-        light_pos = light_pos + j;
-      }
-      const f3 to_light = light_pos - pos;
-      sh_dir = hlsl_normalize(to_light);
-      const float n_dot_l = fmaxf(0.0f, dot3(nrm, sh_dir));
-      unlit = (att * local) * f.light_intensity;          // :418 when the shadow test fails or is not made
-      emit_shadow = f.en_diffuse == 1 && n_dot_l > 0.0f;  // :393
-      if (emit_shadow) {
-        f3 lit_local = local + (m.color * m.kd) * n_dot_l;  // :408
-        if (f.en_specular == 1 && m.ks > 0.0f) {            // :409-414
-          const f3 view_dir = hlsl_normalize(negate(ray.d));
-          const f3 half_vec = hlsl_normalize(sh_dir + view_dir);
-          const float k = m.ks * pow32(fmaxf(dot3(nrm, half_vec), 0.0f));
-          lit_local = lit_local + mk3(k, k, k);
-        }
-        lit = (att * lit_local) * f.light_intensity;
-        sh_origin = pos + nrm * RTB_OFFSET;  // :396
-        sh_dist = hlsl_length(to_light);      // :401
-      } else {
-        const f3 sum = prev + unlit;
+      shade_hit(f, s, ray, att, hit, px, py, sample, depth, o);
+      if (!o.emit_shadow) {  // otherwise k_traverse adds the lit or unlit increment once the shadow query is decided
+        const f3 sum = prev + o.unlit;
         q.accum[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f);
       }
     }
-
-    // ---- shadow queue compaction: one atomicAdd per warp ----
-    {
-      const unsigned m_sh = __ballot_sync(kFull, emit_shadow);
-      int32_t b_sh = 0;
-      if (lane == 0 && m_sh) b_sh = atomicAdd(&RTB_CNT_SHADOW(q, depth), __popc(m_sh));
-      b_sh = __shfl_sync(kFull, b_sh, 0);
-      if (emit_shadow) {
-        const int32_t at = b_sh + __popc(m_sh & below);
-        __stcs(&q.sh_o[at], make_float4(sh_origin.x, sh_origin.y, sh_origin.z, sh_dist));
-        __stcs(&q.sh_d[at], make_float4(sh_dir.x, sh_dir.y, sh_dir.z, __int_as_float(slot)));
-        __stcs(&q.sh_lit[at], make_float4(lit.x, lit.y, lit.z, 0.0f));
-        __stcs(&q.sh_unlit[at], make_float4(unlit.x, unlit.y, unlit.z, 0.0f));
-      }
+    // queue compaction: one atomicAdd per warp and queue
+    const unsigned m_sh = __ballot_sync(kFull, o.emit_shadow);
+    const unsigned m_nx = __ballot_sync(kFull, o.emit_ray);
+    int32_t b_sh = 0, b_nx = 0;
+    if (lane == 0) {
+      if (m_sh) b_sh = atomicAdd(&RTB_CNT_SHADOW(q, depth), __popc(m_sh));
+      if (m_nx) b_nx = atomicAdd(&RTB_CNT_RAY(q, depth + 1), __popc(m_nx));
     }
-
-    // ---- continuation, :420-473 ----
-    bool emit_ray = false;
-    f3 start = pos, nd = mk3(0.0f, 0.0f, 0.0f);
-    if (found && depth + 1 < f.max_depth) {
-      const bool should_reflect = m.ks > 0.0f;
-      const bool should_refract = (f.en_refraction == 1 && m.kr > 0.0f);
-      if (should_reflect || should_refract) {
-        f3 next_dir;
-        if (should_refract) {
-          const f3 I = hlsl_normalize(ray.d);
-          f3 N = nrm;
-          float eta = 1.0f / m.ior;
-          if (dot3(I, N) > 0.0f) { N = negate(N); eta = m.ior; }
-          const float cosi = dot3(negate(I), N);
-          const float k = 1.0f - (eta * eta) * (1.0f - cosi * cosi);
-          if (k >= 0.0f) {
-            next_dir = eta * I + (eta * cosi - sqrtf(k)) * N;
-            att = att * (m.color * m.kr);
-            start = start + next_dir * RTB_OFFSET;
-          } else {  // total internal reflection
-            next_dir = hlsl_reflect(I, N);
-            att = att * (m.color * m.ks);
-            start = start + N * RTB_OFFSET;
-          }
-        } else {
-          next_dir = hlsl_reflect(hlsl_normalize(ray.d), nrm);
-          att = att * (m.color * m.ks);
-          start = start + nrm * RTB_OFFSET;
-        }
-        if (f.glossy == 1 && f.roughness > 0.0f) {  // :459-470
-          const f3 j = random_unit_vector(mk3(((float)px + (float)sample * 55.0f) + (float)depth, (float)py + (float)sample * 22.0f, (float)(depth * 13))) * f.roughness;
-          next_dir = hlsl_normalize(next_dir + j);
-        }
-        nd = hlsl_normalize(next_dir);  // :472
-        emit_ray = true;
-      }
+    b_sh = __shfl_sync(kFull, b_sh, 0);
+    b_nx = __shfl_sync(kFull, b_nx, 0);
+    if (o.emit_shadow) {
+      const int32_t at = b_sh + __popc(m_sh & below);
+      __stcs(&q.sh_o[at], make_float4(o.sh_origin.x, o.sh_origin.y, o.sh_origin.z, o.sh_dist));
+      __stcs(&q.sh_d[at], make_float4(o.sh_dir.x, o.sh_dir.y, o.sh_dir.z, __int_as_float(slot)));
+      __stcs(&q.sh_lit[at], make_float4(o.lit.x, o.lit.y, o.lit.z, 0.0f));
+      __stcs(&q.sh_unlit[at], make_float4(o.unlit.x, o.unlit.y, o.unlit.z, 0.0f));
     }
-    {
-      const unsigned m_nx = __ballot_sync(kFull, emit_ray);
-      int32_t b_nx = 0;
-      if (lane == 0 && m_nx) b_nx = atomicAdd(&RTB_CNT_RAY(q, depth + 1), __popc(m_nx));
-      b_nx = __shfl_sync(kFull, b_nx, 0);
-      if (emit_ray) {
-        const int32_t at = b_nx + __popc(m_nx & below);
-        __stcs(&q.ray_o[out_q][at], make_float4(start.x, start.y, start.z, __int_as_float(slot)));
-        __stcs(&q.ray_d[out_q][at], make_float4(nd.x, nd.y, nd.z, 0.0f));
-        __stcs(&q.ray_att[out_q][at], make_float4(att.x, att.y, att.z, 0.0f));
-      }
+    if (o.emit_ray) {
+      const int32_t at = b_nx + __popc(m_nx & below);
+      __stcs(&q.ray_o[out_q][at], make_float4(o.start.x, o.start.y, o.start.z, __int_as_float(slot)));
+      __stcs(&q.ray_d[out_q][at], make_float4(o.dir.x, o.dir.y, o.dir.z, 0.0f));
+      __stcs(&q.ray_att[out_q][at], make_float4(o.att.x, o.att.y, o.att.z, 0.0f));
     }
   }
 
   for (int o = 16; o > 0; o >>= 1) n_hits += __shfl_xor_sync(kFull, n_hits, o);
   if (lane == 0 && n_hits) atomicAdd(&q.totals[3], (unsigned long long)n_hits);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_tail: once a depth's ray queue has fewer than `tail_max` entries the remaining paths no longer fill the GPU, and one
+// launch per depth would cost the latency of its slowest ray every time.  k_tail instead runs each remaining path to its
+// end in one thread — shade, shadow query, next closest hit, shade, ... — so slow rays of different depths overlap.  Same
+// per-slot operation order as the wavefront (and as the reference's depth loop), hence the same bits.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int BVH>
+__global__ void __launch_bounds__(kBlock) k_tail(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth0,
+                                                 const int32_t tail_max) {
+  const int32_t n = RTB_CNT_RAY(q, depth0);
+  if (n >= tail_max) return;  // k_shade handled this depth
+  const int in_q = depth0 & 1;
+  unsigned n_hits = 0, n_cont = 0, n_shadow = 0, overflow = 0;
+  for (int32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const float4 o4 = __ldcs(&q.ray_o[in_q][idx]), d4 = __ldcs(&q.ray_d[in_q][idx]), a4 = __ldcs(&q.ray_att[in_q][idx]);
+    const float4 hrec = __ldcs(&q.hits[idx]);
+    const int32_t slot = __float_as_int(o4.w);
+    Ray ray = make_ray(mk3(o4), mk3(d4));
+    f3 att = mk3(a4);
+    Hit hit; hit.t = hrec.x; hit.u = hrec.y; hit.v = hrec.z; hit.tri = __float_as_int(hrec.w);
+    f3 acc = mk3(q.accum[slot]);
+    int px = 0, py = 0, sample = 0;
+    if (f.soft == 1 || f.glossy == 1) {
+      int local_row;
+      slot_to_pixel(f, c, slot, px, local_row, sample);
+      py = band_global_row(local_row, f.band_rank, f.band_world, f.band_rows);
+    }
+    for (int depth = depth0;; depth++) {
+      if (hit.tri < 0) { acc = acc + att * mk3(f.bg[0], f.bg[1], f.bg[2]); break; }  // :364-368
+      if (depth == 0) n_hits++;
+      Shaded o;
+      shade_hit(f, s, ray, att, hit, px, py, sample, depth, o);
+      if (o.emit_shadow) {
+        n_shadow++;
+        Ray sr; sr.o = o.sh_origin; sr.d = o.sh_dir; sr.inv = mk3(1.0f / o.sh_dir.x, 1.0f / o.sh_dir.y, 1.0f / o.sh_dir.z);  // :395-398
+        Hit sh;
+        const bool occluded = traverse<BVH, true>(s, sr, o.sh_dist, sh, overflow);
+        acc = acc + (occluded ? o.unlit : o.lit);  // :406-418
+      } else {
+        acc = acc + o.unlit;
+      }
+      if (!o.emit_ray) break;
+      n_cont++;
+      ray = make_ray(o.start, o.dir);
+      att = o.att;
+      traverse<BVH, false>(s, ray, 0.0f, hit, overflow);
+    }
+    q.accum[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n_hits += __shfl_xor_sync(kFull, n_hits, o);
+    n_cont += __shfl_xor_sync(kFull, n_cont, o);
+    n_shadow += __shfl_xor_sync(kFull, n_shadow, o);
+    overflow += __shfl_xor_sync(kFull, overflow, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (n_hits) atomicAdd(&q.totals[3], (unsigned long long)n_hits);
+    if (n_cont) atomicAdd(&q.totals[1], (unsigned long long)n_cont);
+    if (n_shadow) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
+    if (overflow) atomicAdd(&q.totals[4], (unsigned long long)overflow);
+  }
 }
 
 // Output row of a local row: the full frame (RTB_OUT_FRAME) or this rank's packed rows (RTB_OUT_COMPACT).
@@ -627,8 +701,15 @@ void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth,
   else k_traverse_lbvh<<<grid, kBlock, 0, st>>>(s, q, depth);
 }
 
-void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int grid, cudaStream_t st) {
-  k_shade<<<grid, kBlock, 0, st>>>(f, s, q, c, depth);
+void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,
+                  cudaStream_t st) {
+  k_shade<<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+}
+
+void launch_tail(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,
+                 cudaStream_t st) {
+  if (bvh == RTB_BVH_REFERENCE) k_tail<RTB_BVH_REFERENCE><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+  else k_tail<RTB_BVH_LBVH><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
 }
 
 void launch_resolve(const FrameParams& f, const QueueView& q, const ChunkView& c, void* dst, int grid, cudaStream_t st) {

@@ -223,10 +223,11 @@ __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, 
     if (cur >= 0) {
       const float4 n0 = __ldg(&s.nodes[4 * cur]), n1 = __ldg(&s.nodes[4 * cur + 1]);
       const float4 n2 = __ldg(&s.nodes[4 * cur + 2]), n3 = __ldg(&s.nodes[4 * cur + 3]);
-      const float dl = slab_entry_fma(inv, ood, mk3(n0), mk3(n1));
-      const float dr = slab_entry_fma(inv, ood, mk3(n2), mk3(n3));
-      const bool hl = ANY ? !(dl > t_limit) : !(dl >= best.t);
-      const bool hr = ANY ? !(dr > t_limit) : !(dr >= best.t);
+      // same box test, bound and child order as k_traverse_lbvh, so both forms pick the same winner among equal t
+      const float bound = ANY ? nextafterf(t_limit, INFINITY) : best.t;
+      float dl, dr;
+      const bool hl = slab_hit_fma(inv, ood, mk3(n0), mk3(n1), bound, dl);
+      const bool hr = slab_hit_fma(inv, ood, mk3(n2), mk3(n3), bound, dr);
       const int32_t lref = __float_as_int(n0.w), rref = __float_as_int(n1.w);
       if (hl && hr) {
         const bool left_first = !(dr < dl);

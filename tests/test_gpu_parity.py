@@ -386,3 +386,23 @@ def test_multi_device_context_matches_single(samples):
     st = two.stats()
     two.close()
     assert st.n_devices == 2 and (got == ref).all()
+
+
+# ---- wavefront (one launch pair per depth) and fused tail (k_tail) are two schedules of the same arithmetic ---------------------
+@pytest.mark.parametrize("tail_max", ["0", "1073741824", "20000"])
+def test_wavefront_and_tail_schedules_agree_with_oracle(samples, monkeypatch, tail_max):
+    monkeypatch.setenv("RTB_TAIL_MAX", tail_max)  # 0: pure wavefront; 2^30: every path in k_tail from depth 0; 20000: switch mid-frame
+    for mode in (abi.RTB_BVH_REFERENCE, abi.RTB_BVH_LBVH):
+        rt = rt_mod.RayTracer(bvh_mode=mode)
+        for name, kw in (("test_scene_1", dict()), ("test_scene_2", dict(soft_shadows=1, light_size=3.0, glossy=1, roughness=0.05)), ("eval_scene", dict(aa_samples=2))):
+            obj, osc, _ = samples[name]
+            p = params(320, 240, 6, **kw)
+            tex = rt.RenderAsync(obj, p)
+            ref = osc.render(p)
+            within, same, worst = assert_rgb_parity(tex.pixels, ref["rgba8"], f"{name} tail_max={tail_max} mode={mode}")
+            s, c = rt.stats(), ref["counters"]
+            if mode == abi.RTB_BVH_REFERENCE:
+                assert same == 1.0
+                assert (s.rays_primary, s.rays_continuation, s.rays_shadow, s.paths_hit_primary) == (c.rays_primary, c.rays_continuation, c.rays_shadow, c.primary_hits)
+            assert s.reserved[0] == 0
+        rt.close()
