@@ -49,6 +49,7 @@ struct DeviceState {
   float* aux_t = nullptr;
   size_t aux_px = 0;
   int grid_traverse[2] = {0, 0};
+  size_t smem_limit = 0;       // opt-in dynamic shared memory per block
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_trace, prof_shadow, prof_resolve;
   size_t prof_used[3] = {0, 0, 0};
 };
@@ -65,6 +66,7 @@ struct rtb_context {
   const volatile int32_t* cancel = nullptr;
   bool profiling = false;
   int64_t chunk_slots = 1 << 23;
+  int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
   int32_t tail_max = 196608;  // queues smaller than this finish in k_tail (RTB_TAIL_MAX; 0 = pure wavefront)
   std::vector<void*> ipc_opened;
 };
@@ -269,6 +271,14 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
   }
   if (!d.grid_traverse[bvh]) d.grid_traverse[bvh] = d.sm_count * traverse_blocks_per_sm(bvh);
   const int shade_grid = d.sm_count * 8;
+  size_t smem_bytes = 0;  // small scenes: k_traverse works out of a shared-memory copy of nodes + triangles
+  if (ctx->smem_mode != 0 && d.scene.n_tris > 0) {
+    const size_t need = traverse_smem_bytes(bvh, sv);
+    if (need + 1024 <= d.smem_limit) {
+      CK(ctx, traverse_enable_smem(bvh, need));
+      smem_bytes = need;
+    }
+  }
   const QueueView qv = queue_view(d.q);
   CK(ctx, cudaEventRecord(d.ev_begin, d.stream));
   if (local_rows > 0) CK(ctx, cudaMemsetAsync(d.q.totals, 0, 8 * sizeof(unsigned long long), d.stream));
@@ -302,7 +312,7 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
       timed(1, [&] { launch_raygen(bvh, f, sv, qv, c, shade_grid, d.stream); });
       for (int depth = 0; depth <= f.max_depth; depth++) {
         if (depth > 0 && ctx->cancel && *ctx->cancel) { cudaStreamSynchronize(d.stream); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
-        if (depth < f.max_depth || f.en_diffuse == 1) timed(0, [&] { launch_traverse(bvh, sv, qv, depth, d.grid_traverse[bvh], d.stream); });
+        if (depth < f.max_depth || f.en_diffuse == 1) timed(0, [&] { launch_traverse(bvh, sv, qv, depth, smem_bytes ? d.sm_count : d.grid_traverse[bvh], smem_bytes, d.stream); });
         if (depth < f.max_depth) {
           timed(1, [&] { launch_shade(f, sv, qv, c, depth, ctx->tail_max, shade_grid, d.stream); });
           if (ctx->tail_max > 0) timed(0, [&] { launch_tail(bvh, f, sv, qv, c, depth, ctx->tail_max, d.sm_count * 4, d.stream); });
@@ -449,6 +459,7 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
     const long long v = std::atoll(env);
     if (v >= 1024) ctx->chunk_slots = v;
   }
+  if (const char* env = std::getenv("RTB_SMEM")) ctx->smem_mode = std::atoi(env);
   if (const char* env = std::getenv("RTB_TAIL_MAX")) ctx->tail_max = (int32_t)std::max(0LL, std::atoll(env));
   ctx->devs.resize(ids.size());
   for (size_t k = 0; k < ids.size(); k++) {
@@ -459,6 +470,7 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
     CK(nullptr, cudaGetDeviceProperties(&prop, d.device));
     if (prop.major < 10) return fail(nullptr, RTB_E_CUDA, "librtb200 is built for sm_100a (B200) only");
     d.sm_count = prop.multiProcessorCount;
+    d.smem_limit = prop.sharedMemPerBlockOptin;
     CK(nullptr, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     CK(nullptr, cudaEventCreate(&d.ev_begin));
     CK(nullptr, cudaEventCreate(&d.ev_end));

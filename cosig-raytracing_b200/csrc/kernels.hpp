@@ -32,7 +32,11 @@ cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaS
 // ---- trace.cu (K3-K8: the per-pixel wavefront) --------------------------------------------------------------------------
 void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st);
 // `grid` = number of persistent blocks (sm_count * traverse_blocks_per_sm).
-void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int grid, cudaStream_t st);
+// smem_bytes > 0 selects the shared-memory staged variant (grid = sm_count blocks of 1024 threads); it must have been
+// enabled for that size with traverse_enable_smem and equal traverse_smem_bytes(bvh, s).
+void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int grid, size_t smem_bytes, cudaStream_t st);
+size_t traverse_smem_bytes(int bvh, const SceneView& s);
+cudaError_t traverse_enable_smem(int bvh, size_t bytes);
 // k_shade handles depth `depth` when its queue holds >= tail_max rays; otherwise k_tail runs the remaining paths to their
 // end in one launch (both are launched every depth: the queue size lives on the device).
 void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,

@@ -30,6 +30,7 @@ namespace rtb {
 namespace {
 
 constexpr int kBlock = 256;
+constexpr int kBlockSmem = 1024;  // shared-memory staged k_traverse: one block per SM
 constexpr unsigned kFull = 0xffffffffu;
 
 // slot -> pixel of the chunk.  Returns false for padding slots (outside the image or the chunk's rows).
@@ -148,9 +149,25 @@ __device__ __forceinline__ void lane_finish(Lane& L, const QueueView& q, int32_t
   L.done = false;
 }
 
+// Scene data of k_traverse comes either from global memory through the read-only path, or — small scenes — from the
+// copy the block staged in shared memory (SMEM).
+template <bool SMEM>
+__device__ __forceinline__ float4 ld4(const float4* p) { return SMEM ? *p : __ldg(p); }
+
+// Stages the traversal arrays (nodes, then tri_isect) into dynamic shared memory; returns the two base pointers.
+__device__ __forceinline__ void stage_scene(const SceneView& s, int node_f4, float4* sm, const float4*& nodes, const float4*& tris) {
+  const int n_node = s.n_nodes * node_f4, n_tri = s.n_tris * 3;
+  for (int i = threadIdx.x; i < n_node; i += blockDim.x) sm[i] = __ldg(&s.nodes[i]);
+  for (int i = threadIdx.x; i < n_tri; i += blockDim.x) sm[n_node + i] = __ldg(&s.tri_isect[i]);
+  __syncthreads();
+  nodes = sm;
+  tris = sm + n_node;
+}
+
 // Triangle test shared by both flavours.  Returns true when a shadow ray found its occluder.
-__device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, int32_t tri) {
-  const float4 a = __ldg(&s.tri_isect[3 * tri]), b = __ldg(&s.tri_isect[3 * tri + 1]), c = __ldg(&s.tri_isect[3 * tri + 2]);
+template <bool SMEM>
+__device__ __forceinline__ bool lane_test_triangle(Lane& L, const float4* tri_isect, int32_t tri) {
+  const float4 a = ld4<SMEM>(&tri_isect[3 * tri]), b = ld4<SMEM>(&tri_isect[3 * tri + 1]), c = ld4<SMEM>(&tri_isect[3 * tri + 2]);
   Ray r; r.o = L.o; r.d = L.d;
   float t, u, v;
   if (!moller_trumbore(r, mk3(a), mk3(b), mk3(c), t, u, v)) return false;
@@ -163,7 +180,12 @@ __device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_traverse, LBVH flavour: ordered traversal over 64-byte two-box nodes (see lbvh.cu for the layout).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock, 4) k_traverse_lbvh(const SceneView s, const QueueView q, const int depth) {
+template <bool SMEM>
+__global__ void __launch_bounds__(SMEM ? kBlockSmem : kBlock, SMEM ? 1 : 4) k_traverse_lbvh(const SceneView s, const QueueView q, const int depth) {
+  extern __shared__ float4 sm_scene[];
+  const float4* nodes = s.nodes;
+  const float4* tri_isect = s.tri_isect;
+  if (SMEM) stage_scene(s, 4, sm_scene, nodes, tri_isect);
   const int lane = threadIdx.x & 31;
   const int32_t n_closest = RTB_CNT_RAY(q, depth);
   const int32_t n_shadow = depth == 0 ? 0 : RTB_CNT_SHADOW(q, depth - 1);
@@ -207,8 +229,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_lbvh(const SceneView s, 
     // ---- inner nodes: descend until this lane holds a leaf (or runs out of work) ----
     while (cur >= 0) {
       n_nodes++;
-      const float4 n0 = __ldg(&s.nodes[4 * cur]), n1 = __ldg(&s.nodes[4 * cur + 1]);
-      const float4 n2 = __ldg(&s.nodes[4 * cur + 2]), n3 = __ldg(&s.nodes[4 * cur + 3]);
+      const float4 n0 = ld4<SMEM>(&nodes[4 * cur]), n1 = ld4<SMEM>(&nodes[4 * cur + 1]);
+      const float4 n2 = ld4<SMEM>(&nodes[4 * cur + 2]), n3 = ld4<SMEM>(&nodes[4 * cur + 3]);
       float dl, dr;
       const bool hl = slab_hit_fma(L.inv, ood, mk3(n0), mk3(n1), L.t, dl);
       const bool hr = slab_hit_fma(L.inv, ood, mk3(n2), mk3(n3), L.t, dr);
@@ -236,7 +258,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_lbvh(const SceneView s, 
       const int32_t first = code >> 3, count = (code & 7) + 1;
       bool occluded = false;
       n_tris += count;
-      for (int32_t i = 0; i < count && !occluded; i++) occluded = lane_test_triangle(L, s, first + i);
+      for (int32_t i = 0; i < count && !occluded; i++) occluded = lane_test_triangle<SMEM>(L, tri_isect, first + i);
       cur = RTB_REF_DONE;
       if (!occluded)
         while (sp > 0) {
@@ -264,7 +286,12 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_lbvh(const SceneView s, 
 // k_traverse, reference flavour: TraverseBVH compute:225-267 — LIFO stack, left child first, no distance ordering, node
 // culled when its own slab entry >= best t; leaves of any size.  Same results as the reference for every ray.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock, 4) k_traverse_ref(const SceneView s, const QueueView q, const int depth) {
+template <bool SMEM>
+__global__ void __launch_bounds__(SMEM ? kBlockSmem : kBlock, SMEM ? 1 : 4) k_traverse_ref(const SceneView s, const QueueView q, const int depth) {
+  extern __shared__ float4 sm_scene[];
+  const float4* nodes = s.nodes;
+  const float4* tri_isect = s.tri_isect;
+  if (SMEM) stage_scene(s, 2, sm_scene, nodes, tri_isect);
   const int lane = threadIdx.x & 31;
   const int32_t n_closest = RTB_CNT_RAY(q, depth);
   const int32_t n_shadow = depth == 0 ? 0 : RTB_CNT_SHADOW(q, depth - 1);
@@ -304,7 +331,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_ref(const SceneView s, c
     while (leaf_count == 0 && sp > 0) {
       const int32_t ni = stack[--sp];
       n_nodes++;
-      const float4 lo = __ldg(&s.nodes[2 * ni]), hi = __ldg(&s.nodes[2 * ni + 1]);
+      const float4 lo = ld4<SMEM>(&nodes[2 * ni]), hi = ld4<SMEM>(&nodes[2 * ni + 1]);
       Ray r; r.o = L.o; r.d = L.d; r.inv = L.inv;
       const float dst = slab_entry(r, mk3(lo), mk3(hi));
       if (dst >= L.t) continue;  // compute:246
@@ -316,7 +343,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_traverse_ref(const SceneView s, c
     if (leaf_count > 0) {
       bool occluded = false;
       n_tris += leaf_count;
-      for (int32_t i = 0; i < leaf_count && !occluded; i++) occluded = lane_test_triangle(L, s, leaf_first + i);
+      for (int32_t i = 0; i < leaf_count && !occluded; i++) occluded = lane_test_triangle<SMEM>(L, tri_isect, leaf_first + i);
       leaf_count = 0;
       if (occluded) sp = 0;
     }
@@ -688,7 +715,7 @@ int blocks_per_sm(K kernel) {
 }  // namespace
 
 int traverse_blocks_per_sm(int bvh) {
-  return bvh == RTB_BVH_REFERENCE ? blocks_per_sm(k_traverse_ref) : blocks_per_sm(k_traverse_lbvh);
+  return bvh == RTB_BVH_REFERENCE ? blocks_per_sm(k_traverse_ref<false>) : blocks_per_sm(k_traverse_lbvh<false>);
 }
 
 void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st) {
@@ -696,9 +723,23 @@ void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const Queu
   else k_raygen<RTB_BVH_LBVH><<<grid, kBlock, 0, st>>>(f, s, q, c);
 }
 
-void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int grid, cudaStream_t st) {
-  if (bvh == RTB_BVH_REFERENCE) k_traverse_ref<<<grid, kBlock, 0, st>>>(s, q, depth);
-  else k_traverse_lbvh<<<grid, kBlock, 0, st>>>(s, q, depth);
+size_t traverse_smem_bytes(int bvh, const SceneView& s) {
+  return ((size_t)s.n_nodes * (bvh == RTB_BVH_REFERENCE ? 2 : 4) + (size_t)s.n_tris * 3) * sizeof(float4);
+}
+
+cudaError_t traverse_enable_smem(int bvh, size_t bytes) {
+  if (bvh == RTB_BVH_REFERENCE) return cudaFuncSetAttribute(k_traverse_ref<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaFuncSetAttribute(k_traverse_lbvh<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int grid, size_t smem_bytes, cudaStream_t st) {
+  if (smem_bytes > 0) {  // small scene: one 1024-thread block per SM works out of its shared-memory copy
+    if (bvh == RTB_BVH_REFERENCE) k_traverse_ref<true><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
+    else k_traverse_lbvh<true><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
+  } else {
+    if (bvh == RTB_BVH_REFERENCE) k_traverse_ref<false><<<grid, kBlock, 0, st>>>(s, q, depth);
+    else k_traverse_lbvh<false><<<grid, kBlock, 0, st>>>(s, q, depth);
+  }
 }
 
 void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,

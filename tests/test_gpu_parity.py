@@ -406,3 +406,20 @@ def test_wavefront_and_tail_schedules_agree_with_oracle(samples, monkeypatch, ta
                 assert (s.rays_primary, s.rays_continuation, s.rays_shadow, s.paths_hit_primary) == (c.rays_primary, c.rays_continuation, c.rays_shadow, c.primary_hits)
             assert s.reserved[0] == 0
         rt.close()
+
+
+def test_shared_memory_staged_traversal_matches(samples, monkeypatch):
+    """RTB_SMEM=1: k_traverse works out of a per-block shared-memory copy of nodes + triangles (small scenes only)."""
+    monkeypatch.setenv("RTB_SMEM", "1")
+    monkeypatch.setenv("RTB_TAIL_MAX", "0")
+    for mode in (abi.RTB_BVH_REFERENCE, abi.RTB_BVH_LBVH):
+        rt = rt_mod.RayTracer(bvh_mode=mode)
+        for name in synth.SAMPLE_SCENES:
+            obj, osc, _ = samples[name]
+            p = params(400, 300, 6)
+            tex = rt.RenderAsync(obj, p)
+            ref = osc.render(p)
+            within, same, worst = assert_rgb_parity(tex.pixels, ref["rgba8"], f"smem {name} mode {mode}")
+            if mode == abi.RTB_BVH_REFERENCE:
+                assert same == 1.0
+        rt.close()
