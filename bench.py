@@ -167,7 +167,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -257,6 +257,7 @@ def main():
     ev0.record(stream)
     for _ in range(args.steps):
         step_device(sync=False)
+    rt.flush()  # the library alternates frames over two streams: make the timed stream wait for both
     ev1.record(stream)
     rt.synchronize(); torch.cuda.synchronize(); barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
@@ -307,10 +308,11 @@ def main():
     if world == 1:
         t0 = time.perf_counter()
         rt.InvalidateBVHCache()
+        t1 = time.perf_counter()
         rt.RenderInto(packed, st.to_params(), host_view)
-        cold_s = time.perf_counter() - t0
+        cold_s = time.perf_counter() - t1
         sc = rt.stats()
-        cold = {"ms": cold_s * 1e3, "ms_upload_total": sc.ms_upload, "ms_build_device": sc.ms_build,
+        cold = {"ms": cold_s * 1e3, "ms_invalidate": (t1 - t0) * 1e3, "ms_upload_total": sc.ms_upload, "ms_build_device": sc.ms_build,
                 "h2d_bytes": int(packed.desc.n_triangles) * 40, "note": "rtb_upload_scene + rtb_render, scene description in pageable host memory"}
 
     # ---- per-kernel-family times (profiling events per launch; separate, untimed pass) -------------------------------------
@@ -334,13 +336,18 @@ def main():
             ref, rows, c, build_s, sample = oracle_sample(args.workload)
             bpr, parts = algorithmic_bytes_per_closest_ray(c)
             closest_rays = float(s0.rays_primary + s0.rays_continuation)
-            achieved = closest_rays * bpr / (fam[0] * 1e-3) / 1e9
+            # k_traverse also serves the shadow rays: 32 n + 36 tau per shadow ray (no hit record is fetched)
+            bps = (32.0 * c.nodes_visited_shadow + 36.0 * c.tris_tested_shadow) / max(1, c.rays_shadow)
+            parts.update(shadow_nodes_per_ray=round(c.nodes_visited_shadow / max(1, c.rays_shadow), 3),
+                         shadow_tris_per_ray=round(c.tris_tested_shadow / max(1, c.rays_shadow), 3), bytes_per_shadow_ray=round(bps, 1))
+            achieved = (closest_rays * bpr + float(s0.rays_shadow) * bps) / (fam[0] * 1e-3) / 1e9
             traffic = None
             tp = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tp):
                 traffic = json.load(open(tp)).get(args.workload)
             roof.update(achieved=achieved, frac=achieved / peak, traffic=traffic, bytes_per_ray=round(bpr, 1), oracle_counts=parts,
-                        launches_per_frame=depth, ms_per_frame=float(fam[0]), rays_per_frame=closest_rays,
+                        launches_per_frame=depth + 1, ms_per_frame=float(fam[0]), rays_per_frame=closest_rays + float(s0.rays_shadow),
+                        gpu_nodes_fetched_per_ray=round(s0.reserved[1] / max(1.0, rays_rank), 3), gpu_tris_tested_per_ray=round(s0.reserved[2] / max(1.0, rays_rank), 3),
                         note="algorithmic bytes = rays x (32 n + 36 tau + 76 h), n/tau/h counted by the CPU oracle on the reference-shape BVH "
                              "(SURVEY.md 8d); the LBVH visits fewer nodes than that, so frac can exceed what DRAM counters show")
             cpu = {"value": c.rays / c.seconds / 1e6, "unit": "Mrays/s", "cores": int(c.threads), "kind": "port", "sample": sample,

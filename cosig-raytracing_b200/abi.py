@@ -123,6 +123,7 @@ SYMBOLS = {
     "rtb_set_cancel_flag": (C.c_int, [_VP, _VP]),
     "rtb_synchronize": (C.c_int, [_VP]),
     "rtb_get_stream": (_VP, [_VP, C.c_int32]),
+    "rtb_flush": (C.c_int, [_VP]),
     "rtb_last_error": (C.c_char_p, [_VP]),
     "rtb_alloc_pinned": (_VP, [C.c_size_t]),
     "rtb_free_pinned": (None, [_VP]),

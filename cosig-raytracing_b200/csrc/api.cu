@@ -35,14 +35,27 @@ struct Queues {
   int32_t capacity = 0, depth_cap = 0;
 };
 
+// A lane = a stream with its own wavefront queues.  Chunks (and, for asynchronous renders, whole frames) alternate between
+// the two lanes of a device, so the latency-bound tail of one chunk — a few very long rays — overlaps the bulk of the next.
+struct LaneState {
+  cudaStream_t stream = nullptr;
+  Queues q;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_done = nullptr;
+  uint64_t frame_id = 0;   // last frame that used this lane (its totals belong to that frame)
+  bool used = false;       // work was enqueued since the last join
+};
+
 struct DeviceState {
   int device = 0;
   int sm_count = 148;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_done = nullptr;
+  cudaStream_t stream = nullptr;  // == lane[0].stream: uploads, readback, and what rtb_get_stream hands out
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_done = nullptr;  // scene upload timing / cross-device completion
+  cudaEvent_t ev_resolve = nullptr;  // orders the resolve kernels of successive chunks / frames (they may share pixels)
+  bool resolve_pending = false;
+  LaneState lane[2];
+  int next_lane = 0;
   float* sphere_table = nullptr;
   DeviceScene scene;
-  Queues q;
   void* frame = nullptr;  // RGBA8 frame (device 0) — also the IPC-exported buffer
   size_t frame_bytes = 0;
   int32_t *aux_prim = nullptr, *aux_mat = nullptr;
@@ -66,6 +79,8 @@ struct rtb_context {
   const volatile int32_t* cancel = nullptr;
   bool profiling = false;
   int64_t chunk_slots = 1 << 23;
+  int n_lanes = 2;            // RTB_LANES: 2 = alternate chunks / async frames over two streams, 1 = single stream
+  uint64_t frame_id = 0;
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
   int32_t tail_max = 196608;  // queues smaller than this finish in k_tail (RTB_TAIL_MAX; 0 = pure wavefront)
   std::vector<void*> ipc_opened;
@@ -104,23 +119,45 @@ void free_scene(DeviceState& d) {
   s = DeviceScene();
 }
 
+void device_sync(DeviceState& d) {
+  cudaSetDevice(d.device);
+  for (auto& l : d.lane)
+    if (l.stream) cudaStreamSynchronize(l.stream);
+  for (auto& l : d.lane) l.used = false;
+  d.resolve_pending = false;
+}
+
+// lane 0's stream (the one the host sees) waits for everything enqueued on lane 1
+cudaError_t join_lanes(DeviceState& d) {
+  if (d.lane[1].used) {
+    cudaError_t e = cudaStreamWaitEvent(d.lane[0].stream, d.lane[1].ev_done, 0);
+    if (e != cudaSuccess) return e;
+    d.lane[1].used = false;
+  }
+  return cudaSuccess;
+}
+
 void free_targets(DeviceState& d) {
   cudaSetDevice(d.device);
-  dfree(d.q.base); dfree(d.q.counters); dfree(d.q.totals);
-  d.q = Queues();
+  for (auto& l : d.lane) {
+    dfree(l.q.base); dfree(l.q.counters); dfree(l.q.totals);
+    l.q = Queues();
+  }
   dfree(d.frame); d.frame_bytes = 0;
   dfree(d.aux_prim); dfree(d.aux_mat); dfree(d.aux_t); d.aux_px = 0;
 }
 
-int ensure_queues(rtb_context* ctx, DeviceState& d, int32_t capacity, int32_t depth_cap) {
-  if (d.q.capacity >= capacity && d.q.depth_cap >= depth_cap) return RTB_OK;
-  dfree(d.q.base); dfree(d.q.counters); dfree(d.q.totals);
-  d.q = Queues();
-  CK(ctx, cudaMalloc(&d.q.base, (size_t)capacity * 12 * sizeof(float4)));
-  CK(ctx, cudaMalloc(&d.q.counters, (size_t)depth_cap * 4 * sizeof(int32_t)));
-  CK(ctx, cudaMalloc(&d.q.totals, 8 * sizeof(unsigned long long)));
-  d.q.capacity = capacity;
-  d.q.depth_cap = depth_cap;
+int ensure_queues(rtb_context* ctx, LaneState& l, int32_t capacity, int32_t depth_cap) {
+  if (l.q.capacity >= capacity && l.q.depth_cap >= depth_cap) return RTB_OK;
+  CK(ctx, cudaStreamSynchronize(l.stream));
+  dfree(l.q.base); dfree(l.q.counters); dfree(l.q.totals);
+  l.q = Queues();
+  CK(ctx, cudaMalloc(&l.q.base, (size_t)capacity * 12 * sizeof(float4)));
+  CK(ctx, cudaMalloc(&l.q.counters, (size_t)depth_cap * 4 * sizeof(int32_t)));
+  CK(ctx, cudaMalloc(&l.q.totals, 8 * sizeof(unsigned long long)));
+  l.q.capacity = capacity;
+  l.q.depth_cap = depth_cap;
+  l.frame_id = 0;
   return RTB_OK;
 }
 
@@ -174,6 +211,7 @@ void prof_pair(DeviceState& d, int family, cudaEvent_t& a, cudaEvent_t& b) {
 int upload_on_device(rtb_context* ctx, DeviceState& d, const rtb_scene_desc& desc, const std::vector<FlattenObject>& objs, int32_t n_out,
                      const std::vector<float>& mats, int bvh_mode, float& ms_build) {
   CK(ctx, cudaSetDevice(d.device));
+  device_sync(d);
   free_scene(d);
   DeviceScene& s = d.scene;
   s.bvh_mode = bvh_mode;
@@ -265,10 +303,6 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
   const int32_t rows_per_chunk = (int32_t)std::min<int64_t>(tile_rows_per_chunk * 4, ((int64_t)local_rows + 3) / 4 * 4);
   const int32_t capacity = (int32_t)(((int64_t)rows_per_chunk / 4) * slots_per_tile_row);
   const int32_t depth_cap = f.max_depth + 2;
-  if (local_rows > 0) {
-    const int rc = ensure_queues(ctx, d, capacity, depth_cap);
-    if (rc != RTB_OK) return rc;
-  }
   if (!d.grid_traverse[bvh]) d.grid_traverse[bvh] = d.sm_count * traverse_blocks_per_sm(bvh);
   const int shade_grid = d.sm_count * 8;
   size_t smem_bytes = 0;  // small scenes: k_traverse works out of a shared-memory copy of nodes + triangles
@@ -279,19 +313,39 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
       smem_bytes = need;
     }
   }
-  const QueueView qv = queue_view(d.q);
-  CK(ctx, cudaEventRecord(d.ev_begin, d.stream));
-  if (local_rows > 0) CK(ctx, cudaMemsetAsync(d.q.totals, 0, 8 * sizeof(unsigned long long), d.stream));
   d.prof_used[0] = d.prof_used[1] = d.prof_used[2] = 0;
-  auto timed = [&](int family, auto&& launch) {
-    cudaEvent_t a = nullptr, b = nullptr;
-    if (ctx->profiling) { prof_pair(d, family, a, b); cudaEventRecord(a, d.stream); }
-    launch();
-    if (ctx->profiling) cudaEventRecord(b, d.stream);
-    launches++;
-  };
   for (int32_t row0 = 0; row0 < local_rows; row0 += rows_per_chunk) {
-    if (ctx->cancel && *ctx->cancel) { cudaStreamSynchronize(d.stream); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
+    LaneState& L = d.lane[d.next_lane];
+    if (ctx->n_lanes > 1) d.next_lane ^= 1;
+    cudaStream_t stream = L.stream;
+    if (ctx->cancel && *ctx->cancel) { device_sync(d); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
+    {
+      const int rc = ensure_queues(ctx, L, capacity, depth_cap);
+      if (rc != RTB_OK) return rc;
+    }
+    const QueueView qv = queue_view(L.q);
+    if (L.frame_id != ctx->frame_id) {  // first chunk of this frame on this lane
+      L.frame_id = ctx->frame_id;
+      CK(ctx, cudaEventRecord(L.ev_begin, stream));
+      CK(ctx, cudaMemsetAsync(L.q.totals, 0, 8 * sizeof(unsigned long long), stream));
+    }
+    L.used = true;
+    auto timed = [&](int family, auto&& launch) {
+      cudaEvent_t a = nullptr, b = nullptr;
+      if (ctx->profiling) { prof_pair(d, family, a, b); cudaEventRecord(a, stream); }
+      launch();
+      if (ctx->profiling) cudaEventRecord(b, stream);
+      launches++;
+    };
+    // successive resolves may write the same pixels (frames in flight on both lanes): keep them in issue order
+    auto ordered_resolve = [&](auto&& launch) -> cudaError_t {
+      cudaError_t e = cudaSuccess;
+      if (d.resolve_pending) e = cudaStreamWaitEvent(stream, d.ev_resolve, 0);
+      if (e != cudaSuccess) return e;
+      timed(2, launch);
+      d.resolve_pending = true;
+      return cudaEventRecord(d.ev_resolve, stream);
+    };
     ChunkView c;
     c.row0 = row0;
     c.rows = std::min(rows_per_chunk, local_rows - row0);
@@ -300,29 +354,31 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
     chunks++;
     const int resolve_grid = std::min(d.sm_count * 8, (c.rows * f.width + 255) / 256);
     if (f.debug != 0) {
-      timed(2, [&] { launch_debug(bvh, f, sv, c, dst, resolve_grid, d.stream); });
-      continue;
-    }
-    if (f.max_depth <= 0) {  // the depth loop never runs: sampleColor stays 0
-      CK(ctx, cudaMemsetAsync(qv.accum, 0, (size_t)c.n_slots * sizeof(float4), d.stream));
+      CK(ctx, ordered_resolve([&] { launch_debug(bvh, f, sv, c, dst, resolve_grid, stream); }));
     } else {
-      CK(ctx, cudaMemsetAsync(d.q.counters, 0, (size_t)d.q.depth_cap * 4 * sizeof(int32_t), d.stream));
-      // raygen fills the depth-0 queue; depth d: traverse (closest-hit rays of depth d + shadow rays emitted at depth d-1), then shade.  One more traverse
-      // at the end serves the last depth's shadow rays.
-      timed(1, [&] { launch_raygen(bvh, f, sv, qv, c, shade_grid, d.stream); });
-      for (int depth = 0; depth <= f.max_depth; depth++) {
-        if (depth > 0 && ctx->cancel && *ctx->cancel) { cudaStreamSynchronize(d.stream); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
-        if (depth < f.max_depth || f.en_diffuse == 1) timed(0, [&] { launch_traverse(bvh, sv, qv, depth, smem_bytes ? d.sm_count : d.grid_traverse[bvh], smem_bytes, d.stream); });
-        if (depth < f.max_depth) {
-          timed(1, [&] { launch_shade(f, sv, qv, c, depth, ctx->tail_max, shade_grid, d.stream); });
-          if (ctx->tail_max > 0) timed(0, [&] { launch_tail(bvh, f, sv, qv, c, depth, ctx->tail_max, d.sm_count * 4, d.stream); });
+      if (f.max_depth <= 0) {  // the depth loop never runs: sampleColor stays 0
+        CK(ctx, cudaMemsetAsync(qv.accum, 0, (size_t)c.n_slots * sizeof(float4), stream));
+      } else {
+        CK(ctx, cudaMemsetAsync(L.q.counters, 0, (size_t)L.q.depth_cap * 4 * sizeof(int32_t), stream));
+        // raygen fills the depth-0 queue; depth d: traverse (closest-hit rays of depth d + shadow rays emitted at depth d-1),
+        // then shade (or, for short queues, k_tail).  One more traverse at the end serves the last depth's shadow rays.
+        timed(1, [&] { launch_raygen(bvh, f, sv, qv, c, shade_grid, stream); });
+        for (int depth = 0; depth <= f.max_depth; depth++) {
+          if (depth > 0 && ctx->cancel && *ctx->cancel) { device_sync(d); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
+          if (depth < f.max_depth || f.en_diffuse == 1)
+            timed(0, [&] { launch_traverse(bvh, sv, qv, depth, smem_bytes ? d.sm_count : d.grid_traverse[bvh], smem_bytes, stream); });
+          if (depth < f.max_depth) {
+            timed(1, [&] { launch_shade(f, sv, qv, c, depth, ctx->tail_max, shade_grid, stream); });
+            if (ctx->tail_max > 0) timed(0, [&] { launch_tail(bvh, f, sv, qv, c, depth, ctx->tail_max, d.sm_count * 4, stream); });
+          }
         }
       }
+      CK(ctx, ordered_resolve([&] { launch_resolve(f, qv, c, dst, resolve_grid, stream); }));
     }
-    timed(2, [&] { launch_resolve(f, qv, c, dst, resolve_grid, d.stream); });
+    CK(ctx, cudaEventRecord(L.ev_end, stream));
+    CK(ctx, cudaEventRecord(L.ev_done, stream));
   }
   CK(ctx, cudaGetLastError());
-  CK(ctx, cudaEventRecord(d.ev_end, d.stream));
   return RTB_OK;
 }
 
@@ -357,6 +413,7 @@ int render_frame(rtb_context* ctx, const rtb_render_params* p, void* dst, size_t
   if (!dst || dst_bytes < rows_out * (size_t)f.width * 4) return fail(ctx, RTB_E_SIZE, "output buffer too small for the resolved resolution");
 
   int launches = 0, chunks = 0;
+  ctx->frame_id++;
   for (int k = 0; k < n_dev; k++) {
     FrameParams fk = f;
     if (n_dev > 1) { fk.band_world = n_dev; fk.band_rank = k; fk.out_compact = 0; }
@@ -365,10 +422,12 @@ int render_frame(rtb_context* ctx, const rtb_render_params* p, void* dst, size_t
   }
   // device 0 waits for the peers' stores (the NVLink gather is complete when their resolve kernels have finished)
   for (int k = 1; k < n_dev; k++) {
-    CK(ctx, cudaSetDevice(ctx->devs[(size_t)k].device));
-    CK(ctx, cudaEventRecord(ctx->devs[(size_t)k].ev_done, ctx->devs[(size_t)k].stream));
+    DeviceState& dk = ctx->devs[(size_t)k];
+    CK(ctx, cudaSetDevice(dk.device));
+    CK(ctx, join_lanes(dk));
+    CK(ctx, cudaEventRecord(dk.ev_done, dk.stream));
     CK(ctx, cudaSetDevice(ctx->devs[0].device));
-    CK(ctx, cudaStreamWaitEvent(ctx->devs[0].stream, ctx->devs[(size_t)k].ev_done, 0));
+    CK(ctx, cudaStreamWaitEvent(ctx->devs[0].stream, dk.ev_done, 0));
   }
   CK(ctx, cudaSetDevice(ctx->devs[0].device));
   rtb_stats& st = ctx->stats;
@@ -376,11 +435,9 @@ int render_frame(rtb_context* ctx, const rtb_render_params* p, void* dst, size_t
   st.h2d_bytes = (int64_t)sizeof(FrameParams) * launches;  // uniforms travel as kernel parameters
   st.d2h_bytes = 0;
   if (sync) {
-    for (int k = 0; k < n_dev; k++) {
-      CK(ctx, cudaSetDevice(ctx->devs[(size_t)k].device));
-      CK(ctx, cudaStreamSynchronize(ctx->devs[(size_t)k].stream));
-    }
+    for (int k = 0; k < n_dev; k++) device_sync(ctx->devs[(size_t)k]);
     CK(ctx, cudaSetDevice(ctx->devs[0].device));
+    CK(ctx, cudaGetLastError());
   }
   return RTB_OK;
 }
@@ -392,17 +449,18 @@ int collect_stats(rtb_context* ctx) {
   st.ms_traverse = st.ms_shade = st.ms_resolve = 0.0f;
   int64_t overflow = 0, nodes = 0, tris = 0;
   for (auto& d : ctx->devs) {
-    CK(ctx, cudaSetDevice(d.device));
-    CK(ctx, cudaStreamSynchronize(d.stream));
-    if (d.q.totals) {
+    device_sync(d);
+    CK(ctx, cudaGetLastError());
+    for (auto& l : d.lane) {
+      if (!l.q.totals || l.frame_id != ctx->frame_id || ctx->frame_id == 0) continue;
       unsigned long long t[8];
-      CK(ctx, cudaMemcpy(t, d.q.totals, sizeof t, cudaMemcpyDeviceToHost));
+      CK(ctx, cudaMemcpy(t, l.q.totals, sizeof t, cudaMemcpyDeviceToHost));
       st.rays_primary += (int64_t)t[0]; st.rays_continuation += (int64_t)t[1]; st.rays_shadow += (int64_t)t[2];
       st.paths_hit_primary += (int64_t)t[3]; overflow += (int64_t)t[4]; nodes += (int64_t)t[5]; tris += (int64_t)t[6];
+      float ms = 0.0f;
+      if (cudaEventElapsedTime(&ms, l.ev_begin, l.ev_end) == cudaSuccess) st.ms_render_device = std::max(st.ms_render_device, ms);
+      else cudaGetLastError();
     }
-    float ms = 0.0f;
-    if (cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end) == cudaSuccess) st.ms_render_device = std::max(st.ms_render_device, ms);
-    else cudaGetLastError();
     if (ctx->profiling && &d == &ctx->devs[0]) {
       st.ms_traverse = sum_pairs(d.prof_trace, d.prof_used[0]);
       st.ms_shade = sum_pairs(d.prof_shadow, d.prof_used[1]);
@@ -459,6 +517,7 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
     const long long v = std::atoll(env);
     if (v >= 1024) ctx->chunk_slots = v;
   }
+  if (const char* env = std::getenv("RTB_LANES")) ctx->n_lanes = std::atoi(env) >= 2 ? 2 : 1;
   if (const char* env = std::getenv("RTB_SMEM")) ctx->smem_mode = std::atoi(env);
   if (const char* env = std::getenv("RTB_TAIL_MAX")) ctx->tail_max = (int32_t)std::max(0LL, std::atoll(env));
   ctx->devs.resize(ids.size());
@@ -471,7 +530,14 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
     if (prop.major < 10) return fail(nullptr, RTB_E_CUDA, "librtb200 is built for sm_100a (B200) only");
     d.sm_count = prop.multiProcessorCount;
     d.smem_limit = prop.sharedMemPerBlockOptin;
-    CK(nullptr, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    for (auto& l : d.lane) {
+      CK(nullptr, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+      CK(nullptr, cudaEventCreate(&l.ev_begin));
+      CK(nullptr, cudaEventCreate(&l.ev_end));
+      CK(nullptr, cudaEventCreateWithFlags(&l.ev_done, cudaEventDisableTiming));
+    }
+    d.stream = d.lane[0].stream;
+    CK(nullptr, cudaEventCreateWithFlags(&d.ev_resolve, cudaEventDisableTiming));
     CK(nullptr, cudaEventCreate(&d.ev_begin));
     CK(nullptr, cudaEventCreate(&d.ev_end));
     CK(nullptr, cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming));
@@ -500,8 +566,7 @@ void rtb_destroy(rtb_context* ctx) {
     cudaIpcCloseMemHandle(p);
   }
   for (auto& d : ctx->devs) {
-    cudaSetDevice(d.device);
-    if (d.stream) cudaStreamSynchronize(d.stream);
+    device_sync(d);
     free_scene(d);
     free_targets(d);
     dfree(d.sphere_table);
@@ -510,7 +575,13 @@ void rtb_destroy(rtb_context* ctx) {
     if (d.ev_begin) cudaEventDestroy(d.ev_begin);
     if (d.ev_end) cudaEventDestroy(d.ev_end);
     if (d.ev_done) cudaEventDestroy(d.ev_done);
-    if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.ev_resolve) cudaEventDestroy(d.ev_resolve);
+    for (auto& l : d.lane) {
+      if (l.ev_begin) cudaEventDestroy(l.ev_begin);
+      if (l.ev_end) cudaEventDestroy(l.ev_end);
+      if (l.ev_done) cudaEventDestroy(l.ev_done);
+      if (l.stream) cudaStreamDestroy(l.stream);
+    }
   }
   delete ctx;
 }
@@ -554,7 +625,7 @@ int rtb_upload_scene(rtb_context* ctx, const rtb_scene_desc* scene, int32_t prim
 
 int rtb_invalidate(rtb_context* ctx) {
   if (!ctx) return RTB_E_ARG;
-  for (auto& d : ctx->devs) { cudaSetDevice(d.device); cudaStreamSynchronize(d.stream); free_scene(d); }
+  for (auto& d : ctx->devs) { device_sync(d); free_scene(d); }
   cudaSetDevice(ctx->devs[0].device);
   ctx->has_scene = false;
   return RTB_OK;
@@ -563,7 +634,7 @@ int rtb_invalidate(rtb_context* ctx) {
 int rtb_clear_target(rtb_context* ctx) {
   if (!ctx) return RTB_E_ARG;
   if (!ctx->ipc_opened.empty()) return fail(ctx, RTB_E_ARG, "frame buffers are shared over IPC; destroy the context instead");
-  for (auto& d : ctx->devs) { cudaSetDevice(d.device); cudaStreamSynchronize(d.stream); free_targets(d); }
+  for (auto& d : ctx->devs) { device_sync(d); free_targets(d); }
   cudaSetDevice(ctx->devs[0].device);
   return RTB_OK;
 }
@@ -584,10 +655,12 @@ int rtb_render(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, siz
   if (rc != RTB_OK) return rc;
   DeviceState& d0 = ctx->devs[0];
   const size_t need = (size_t)f.width * f.height * 4;
+  CK(ctx, cudaSetDevice(d0.device));
+  CK(ctx, join_lanes(d0));
   CK(ctx, cudaMemcpyAsync(rgba8, d0.frame, need, cudaMemcpyDeviceToHost, d0.stream));  // ReadPixels, RayTracer.cs:371-375
-  CK(ctx, cudaStreamSynchronize(d0.stream));
-  for (size_t k = 1; k < ctx->devs.size(); k++) { cudaSetDevice(ctx->devs[k].device); CK(ctx, cudaStreamSynchronize(ctx->devs[k].stream)); }
-  cudaSetDevice(d0.device);
+  for (auto& d : ctx->devs) device_sync(d);
+  CK(ctx, cudaSetDevice(d0.device));
+  CK(ctx, cudaGetLastError());
   ctx->stats.d2h_bytes = (int64_t)need;
   return RTB_OK;
 }
@@ -615,6 +688,7 @@ int rtb_render_aux(rtb_context* ctx, const rtb_render_params* p, int32_t* prim_i
     CK(ctx, cudaMalloc(&d.aux_t, n_px * 4));
     d.aux_px = n_px;
   }
+  device_sync(d);
   launch_aux(d.scene.bvh_mode, f, scene_view(d.scene), d.aux_prim, d.aux_t, d.aux_mat, d.sm_count * 8, d.stream);
   CK(ctx, cudaGetLastError());
   if (prim_id) CK(ctx, cudaMemcpyAsync(prim_id, d.aux_prim, n_px * 4, cudaMemcpyDeviceToHost, d.stream));
@@ -691,7 +765,15 @@ int rtb_set_cancel_flag(rtb_context* ctx, const volatile int32_t* flag) {
 
 int rtb_synchronize(rtb_context* ctx) {
   if (!ctx) return RTB_E_ARG;
-  for (auto& d : ctx->devs) { CK(ctx, cudaSetDevice(d.device)); CK(ctx, cudaStreamSynchronize(d.stream)); }
+  for (auto& d : ctx->devs) device_sync(d);
+  cudaSetDevice(ctx->devs[0].device);
+  CK(ctx, cudaGetLastError());
+  return RTB_OK;
+}
+
+int rtb_flush(rtb_context* ctx) {
+  if (!ctx) return RTB_E_ARG;
+  for (auto& d : ctx->devs) { CK(ctx, cudaSetDevice(d.device)); CK(ctx, join_lanes(d)); }
   cudaSetDevice(ctx->devs[0].device);
   return RTB_OK;
 }
@@ -741,8 +823,9 @@ int rtb_frame_read(rtb_context* ctx, uint8_t* rgba8, size_t bytes) {
   DeviceState& d = ctx->devs[0];
   if (!d.frame || d.frame_bytes < bytes) return fail(ctx, RTB_E_SIZE, "internal frame smaller than requested");
   CK(ctx, cudaSetDevice(d.device));
+  CK(ctx, join_lanes(d));
   CK(ctx, cudaMemcpyAsync(rgba8, d.frame, bytes, cudaMemcpyDeviceToHost, d.stream));
-  CK(ctx, cudaStreamSynchronize(d.stream));
+  device_sync(d);
   ctx->stats.d2h_bytes = (int64_t)bytes;
   return RTB_OK;
 }

@@ -247,6 +247,10 @@ class RayTracer:
         """cudaStream_t of device `index` (wrap with torch.cuda.ExternalStream to record events on it)."""
         return self._lib.rtb_get_stream(self._ctx, index)
 
+    def flush(self):
+        """Make stream(0) wait for every frame in flight on the context's second stream (see rtb_flush)."""
+        self._check(self._lib.rtb_flush(self._ctx))
+
     def synchronize(self):
         self._check(self._lib.rtb_synchronize(self._ctx))
 
