@@ -345,7 +345,14 @@ def main():
             tp = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tp):
                 traffic = json.load(open(tp)).get(args.workload)
-            roof.update(achieved=achieved, frac=achieved / peak, traffic=traffic, bytes_per_ray=round(bpr, 1), oracle_counts=parts,
+            # what the kernels actually requested: 64 B per LBVH node record (32 B per reference node), 48 B per triangle tested
+            node_bytes = 64.0 if args.bvh == "lbvh" else 32.0
+            requested = (float(s0.reserved[1]) * node_bytes + float(s0.reserved[2]) * 48.0) / (fam[0] * 1e-3) / 1e9
+            if parts["tris_per_ray"] > 1000.0:  # the reference builder degenerated (C3): its counts say nothing about this traversal
+                roof["note_degenerate_reference_bvh"] = ("the oracle's reference-shape BVH degenerates on this scene (leaves of ~10^5 triangles), so `achieved` "
+                                                         "is computed from the bytes this traversal requested instead of the oracle's counts")
+                achieved = requested
+            roof.update(achieved=achieved, frac=achieved / peak, traffic=traffic, requested_gbs=requested, bytes_per_ray=round(bpr, 1), oracle_counts=parts,
                         launches_per_frame=depth + 1, ms_per_frame=float(fam[0]), rays_per_frame=closest_rays + float(s0.rays_shadow),
                         gpu_nodes_fetched_per_ray=round(s0.reserved[1] / max(1.0, rays_rank), 3), gpu_tris_tested_per_ray=round(s0.reserved[2] / max(1.0, rays_rank), 3),
                         note="algorithmic bytes = rays x (32 n + 36 tau + 76 h), n/tau/h counted by the CPU oracle on the reference-shape BVH "
