@@ -21,7 +21,8 @@ namespace {
 thread_local std::string g_create_error;
 
 struct DeviceScene {
-  float4 *raw = nullptr, *nrm = nullptr, *isect = nullptr, *shade = nullptr, *nodes = nullptr, *materials = nullptr;
+  float4 *raw = nullptr, *nrm = nullptr, *isect = nullptr, *shade = nullptr, *nodes = nullptr, *materials = nullptr, *prims = nullptr;
+  int32_t n_prims = 0;
   int32_t* perm = nullptr;
   int32_t n_tris = 0, n_nodes = 0, n_mats = 0, root = 0;
   int bvh_mode = RTB_BVH_REFERENCE;
@@ -115,7 +116,7 @@ void dfree(T*& p) {
 void free_scene(DeviceState& d) {
   cudaSetDevice(d.device);
   DeviceScene& s = d.scene;
-  dfree(s.raw); dfree(s.nrm); dfree(s.isect); dfree(s.shade); dfree(s.nodes); dfree(s.materials); dfree(s.perm);
+  dfree(s.raw); dfree(s.nrm); dfree(s.isect); dfree(s.shade); dfree(s.nodes); dfree(s.materials); dfree(s.perm); dfree(s.prims);
   s = DeviceScene();
 }
 
@@ -179,6 +180,7 @@ SceneView scene_view(const DeviceScene& s) {
   SceneView v;
   v.tri_isect = s.isect; v.tri_shade = s.shade; v.nodes = s.nodes; v.materials = s.materials;
   v.n_tris = s.n_tris; v.n_nodes = s.n_nodes; v.n_mats = s.n_mats; v.root = s.root;
+  v.prims = s.prims; v.n_prims = s.n_prims;
   return v;
 }
 
@@ -209,7 +211,7 @@ void prof_pair(DeviceState& d, int family, cudaEvent_t& a, cudaEvent_t& b) {
 // Scene upload on one device
 // ---------------------------------------------------------------------------------------------------------------------
 int upload_on_device(rtb_context* ctx, DeviceState& d, const rtb_scene_desc& desc, const std::vector<FlattenObject>& objs, int32_t n_out,
-                     const std::vector<float>& mats, int bvh_mode, float& ms_build) {
+                     const std::vector<float>& mats, const std::vector<float>& prims, int bvh_mode, float& ms_build) {
   CK(ctx, cudaSetDevice(d.device));
   device_sync(d);
   free_scene(d);
@@ -220,6 +222,11 @@ int upload_on_device(rtb_context* ctx, DeviceState& d, const rtb_scene_desc& des
   CK(ctx, cudaMalloc(&s.materials, mats.size() * sizeof(float)));
   CK(ctx, cudaMemcpyAsync(s.materials, mats.data(), mats.size() * sizeof(float), cudaMemcpyHostToDevice, d.stream));
   if (n_out == 0) { CK(ctx, cudaStreamSynchronize(d.stream)); return RTB_OK; }
+  s.n_prims = (int32_t)(prims.size() / 24);
+  if (s.n_prims > 0) {
+    CK(ctx, cudaMalloc(&s.prims, prims.size() * sizeof(float)));
+    CK(ctx, cudaMemcpyAsync(s.prims, prims.data(), prims.size() * sizeof(float), cudaMemcpyHostToDevice, d.stream));
+  }
 
   float* tri_in = nullptr;
   FlattenObject* dobjs = nullptr;
@@ -306,7 +313,7 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
   if (!d.grid_traverse[bvh]) d.grid_traverse[bvh] = d.sm_count * traverse_blocks_per_sm(bvh);
   const int shade_grid = d.sm_count * 8;
   size_t smem_bytes = 0;  // small scenes: k_traverse works out of a shared-memory copy of nodes + triangles
-  if (ctx->smem_mode != 0 && d.scene.n_tris > 0) {
+  if (ctx->smem_mode != 0 && d.scene.n_tris > 0 && d.scene.n_prims == 0) {
     const size_t need = traverse_smem_bytes(bvh, sv);
     if (need + 1024 <= d.smem_limit) {
       CK(ctx, traverse_enable_smem(bvh, need));
@@ -590,14 +597,14 @@ const char* rtb_last_error(rtb_context* ctx) { return ctx ? ctx->err.c_str() : g
 
 int rtb_upload_scene(rtb_context* ctx, const rtb_scene_desc* scene, int32_t primitive_mode, int32_t bvh_mode) {
   if (!ctx || !scene) return fail(ctx, RTB_E_ARG, "null argument");
-  if (primitive_mode != RTB_PRIM_TESSELLATED)
-    return fail(ctx, RTB_E_ARG, "primitive_mode: only RTB_PRIM_TESSELLATED (the reference's behaviour) is implemented");
+  if (primitive_mode != RTB_PRIM_TESSELLATED && primitive_mode != RTB_PRIM_ANALYTIC) return fail(ctx, RTB_E_ARG, "unknown primitive_mode");
   if (bvh_mode != RTB_BVH_REFERENCE && bvh_mode != RTB_BVH_LBVH) return fail(ctx, RTB_E_ARG, "unknown bvh_mode");
   const std::string why = ctx->host.assign(*scene, /*copy_triangles=*/false);
   if (!why.empty()) return fail(ctx, RTB_E_ARG, why);
   ctx->has_scene = false;
   std::vector<FlattenObject> objs;
-  const int64_t n_out = build_object_table(*scene, objs);
+  std::vector<float> prims;
+  const int64_t n_out = build_object_table(*scene, primitive_mode == RTB_PRIM_ANALYTIC, objs, prims);
   if (n_out < 0) return fail(ctx, RTB_E_ARG, "scene has more than 2^31 triangles");
   if (bvh_mode == RTB_BVH_LBVH && n_out >= (1 << 28)) return fail(ctx, RTB_E_ARG, "LBVH mode supports fewer than 2^28 triangles");
   std::vector<float> mats;
@@ -607,7 +614,7 @@ int rtb_upload_scene(rtb_context* ctx, const rtb_scene_desc* scene, int32_t prim
   clock_gettime(CLOCK_MONOTONIC, &a);
   for (auto& d : ctx->devs) {
     float ms = 0.0f;
-    const int rc = upload_on_device(ctx, d, *scene, objs, (int32_t)n_out, mats, bvh_mode, ms);
+    const int rc = upload_on_device(ctx, d, *scene, objs, (int32_t)n_out, mats, prims, bvh_mode, ms);
     if (rc != RTB_OK) return rc;
     ms_build = std::max(ms_build, ms);
   }

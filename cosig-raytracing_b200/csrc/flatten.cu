@@ -55,6 +55,25 @@ __global__ void __launch_bounds__(kBlock) k_flatten(const float* __restrict__ tr
       }
       a = v[0]; b = v[1]; c = v[2];
       na = nb = nc = unity_normalized(cross3(b - a, c - a));
+    } else if (ob.kind == OBJ_BOX_ANALYTIC || ob.kind == OBJ_SPHERE_ANALYTIC) {
+      // Analytic primitive: its entry is the world-space bounding box of the 8 transformed corners of the unit cube
+      // (+-0.5) or of the unit sphere's cube (+-1), SphereInstance / BoxInstance constructors, HittableObjects.cs:22-39, 129-145.
+      // Rows (bmin, bmax, bmin) let every builder treat it like a triangle whose three "vertices" span that box.
+      const float h = ob.kind == OBJ_BOX_ANALYTIC ? 0.5f : 1.0f;
+      f3 bmin = mk3(INFINITY, INFINITY, INFINITY), bmax = mk3(-INFINITY, -INFINITY, -INFINITY);
+      for (int ci = 0; ci < 8; ci++) {
+        const f3 p = mul_point(ob.m, mk3((ci & 1) ? h : -h, (ci & 2) ? h : -h, (ci & 4) ? h : -h));
+        bmin = mk3(fminf(bmin.x, p.x), fminf(bmin.y, p.y), fminf(bmin.z, p.z));
+        bmax = mk3(fmaxf(bmax.x, p.x), fmaxf(bmax.y, p.y), fmaxf(bmax.z, p.z));
+      }
+      const f3 ctr = (bmin + bmax) * 0.5f;
+      raw[3 * (size_t)i] = make_float4(bmin.x, bmin.y, bmin.z, ctr.x);
+      raw[3 * (size_t)i + 1] = make_float4(bmax.x, bmax.y, bmax.z, ctr.y);
+      raw[3 * (size_t)i + 2] = make_float4(bmin.x, bmin.y, bmin.z, ctr.z);
+      nrm[3 * (size_t)i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(material));
+      nrm[3 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(ob.kind == OBJ_SPHERE_ANALYTIC ? 1 : 2));
+      nrm[3 * (size_t)i + 2] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(ob.src_first));
+      continue;
     } else {  // AddSphere :192-229 + AddSmoothTri :245-264
       int ia, ib, ic;
       const int last = kSphereVerts - 1;
@@ -88,13 +107,20 @@ __global__ void __launch_bounds__(kBlock) k_pack(const float4* __restrict__ raw,
     const int32_t src = perm[j];
     const float4 a = raw[3 * (size_t)src], b = raw[3 * (size_t)src + 1], c = raw[3 * (size_t)src + 2];
     const float4 n0 = nrm[3 * (size_t)src], n1 = nrm[3 * (size_t)src + 1], n2 = nrm[3 * (size_t)src + 2];
+    if (__float_as_int(n1.w) != 0) {  // analytic primitive: (table index, -, -, prim_id) (-, -, -, material) (-, -, -, kind)
+      isect[3 * (size_t)j] = make_float4(n2.w, 0.0f, 0.0f, __int_as_float(src));
+      isect[3 * (size_t)j + 1] = make_float4(0.0f, 0.0f, 0.0f, n0.w);
+      isect[3 * (size_t)j + 2] = make_float4(0.0f, 0.0f, 0.0f, n1.w);
+      shade[3 * (size_t)j] = shade[3 * (size_t)j + 1] = shade[3 * (size_t)j + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      continue;
+    }
     // edges exactly as IntersectTriangle forms them (BVHRayTracing.compute:155-156): v1 - v0, v2 - v0
     isect[3 * (size_t)j] = make_float4(a.x, a.y, a.z, __int_as_float(src));
     isect[3 * (size_t)j + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, n0.w);
     isect[3 * (size_t)j + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.0f);
     shade[3 * (size_t)j] = make_float4(n0.x, n0.y, n0.z, 0.0f);
-    shade[3 * (size_t)j + 1] = n1;
-    shade[3 * (size_t)j + 2] = n2;
+    shade[3 * (size_t)j + 1] = make_float4(n1.x, n1.y, n1.z, 0.0f);
+    shade[3 * (size_t)j + 2] = make_float4(n2.x, n2.y, n2.z, 0.0f);
   }
 }
 

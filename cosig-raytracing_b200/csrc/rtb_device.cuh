@@ -97,11 +97,14 @@ struct ChunkView {
 
 // Geometry as laid out in HBM.
 struct SceneView {
-  const float4* __restrict__ tri_isect;  // 3 per triangle, leaf order: (v0, prim_id) (e1, material) (e2, 0)
+  const float4* __restrict__ tri_isect;  // 3 per triangle, leaf order: (v0, prim_id) (e1, material) (e2, 0); analytic primitive:
+                                         //   (table index bits, -, -, prim_id) (-, -, -, material) (-, -, -, kind: 1 sphere, 2 box)
   const float4* __restrict__ tri_shade;  // 3 per triangle, leaf order: n0 n1 n2
   const float4* __restrict__ nodes;      // reference: 2 per node (min,leftOrFirst)(max,count); LBVH: 4 per node (see lbvh.cu)
                                          //   LBVH boxes are padded outward (lbvh.cu: k_emit) so the FMA slab test stays conservative
   const float4* __restrict__ materials;  // 2 per material: (r,g,b,ka) (kd,ks,kr,ior)
+  const float4* __restrict__ prims;      // analytic mode: 6 per primitive: objectToWorld rows 0..2, worldToObject rows 0..2
+  int32_t n_prims;
   int32_t n_tris, n_nodes, n_mats;
   int32_t root;                          // LBVH: root reference (>= 0 internal node, < 0 leaf, see lbvh_leaf_ref)
 };

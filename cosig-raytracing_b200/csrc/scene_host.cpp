@@ -102,9 +102,26 @@ static void fill_object(FlattenObject& o, const Mat4& M, bool with_normal_matrix
   }
 }
 
-int64_t build_object_table(const rtb_scene_desc& s, std::vector<FlattenObject>& out) {
+int64_t build_object_table(const rtb_scene_desc& s, bool analytic, std::vector<FlattenObject>& out, std::vector<float>& prims) {
   out.clear();
+  prims.clear();
   int64_t at = 0;
+  auto push_analytic = [&](int kind, int xform, int material) {
+    const Mat4 M = composite_matrix(s, xform);
+    const Mat4 W = inverse(M);
+    FlattenObject o;
+    std::memset(&o, 0, sizeof o);
+    fill_object(o, M, false);
+    o.kind = kind;
+    o.material = material;
+    o.out_first = (int32_t)at;
+    o.src_first = (int32_t)(prims.size() / 24);
+    o.count = 1;
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) prims.push_back(M.at(r, c));
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) prims.push_back(W.at(r, c));
+    at += 1;
+    out.push_back(o);
+  };
   auto push = [&](int kind, int xform, int material, int64_t src_first, int64_t count) {
     FlattenObject o;
     std::memset(&o, 0, sizeof o);
@@ -118,8 +135,14 @@ int64_t build_object_table(const rtb_scene_desc& s, std::vector<FlattenObject>& 
     if (count > 0) out.push_back(o);
   };
   for (int i = 0; i < s.n_meshes && at <= INT32_MAX; i++) push(OBJ_MESH, s.meshes[i].xform, 0, s.meshes[i].first_tri, s.meshes[i].n_tris);
-  for (int i = 0; i < s.n_boxes && at <= INT32_MAX; i++) push(OBJ_BOX, s.boxes[i].xform, s.boxes[i].material, 0, kBoxTris);
-  for (int i = 0; i < s.n_spheres && at <= INT32_MAX; i++) push(OBJ_SPHERE, s.spheres[i].xform, s.spheres[i].material, 0, kSphereTris);
+  for (int i = 0; i < s.n_boxes && at <= INT32_MAX; i++) {
+    if (analytic) push_analytic(OBJ_BOX_ANALYTIC, s.boxes[i].xform, s.boxes[i].material);
+    else push(OBJ_BOX, s.boxes[i].xform, s.boxes[i].material, 0, kBoxTris);
+  }
+  for (int i = 0; i < s.n_spheres && at <= INT32_MAX; i++) {
+    if (analytic) push_analytic(OBJ_SPHERE_ANALYTIC, s.spheres[i].xform, s.spheres[i].material);
+    else push(OBJ_SPHERE, s.spheres[i].xform, s.spheres[i].material, 0, kSphereTris);
+  }
   if (at > INT32_MAX - 64 || s.n_triangles > INT32_MAX - 64) return -1;
   return at;
 }

@@ -38,21 +38,24 @@ struct HostScene {
 Mat4 composite_matrix(const rtb_scene_desc& s, int index);
 
 // One entry per scene object, in emission order (meshes, boxes, spheres: SceneGeometryConverter.cs:23-48).
-enum : int32_t { OBJ_MESH = 0, OBJ_BOX = 1, OBJ_SPHERE = 2 };
+enum : int32_t { OBJ_MESH = 0, OBJ_BOX = 1, OBJ_SPHERE = 2,
+                 OBJ_BOX_ANALYTIC = 3, OBJ_SPHERE_ANALYTIC = 4 };  // analytic mode: one bounding-box entry per primitive
 struct FlattenObject {
   float m[12];        // rows 0..2 of the object's composite matrix (x' = m0*x + m1*y + m2*z + m3)
   float nm[9];        // rows 0..2 of (M^-1)^T, 3x3 part: sphere normals (SceneGeometryConverter.cs:258)
   int32_t kind;
   int32_t material;   // boxes / spheres
   int32_t out_first;  // index of the object's first emitted triangle
-  int32_t src_first;  // meshes: index of its first input triangle
+  int32_t src_first;  // meshes: index of its first input triangle; analytic primitives: index into the analytic table
   int32_t count;      // emitted triangles
   int32_t pad[2];
 };
 static_assert(sizeof(FlattenObject) == 112, "FlattenObject layout");
 
-// Builds the object table; returns the total emitted triangle count (or -1 if it exceeds int32).
-int64_t build_object_table(const rtb_scene_desc& s, std::vector<FlattenObject>& out);
+// Builds the object table; returns the total emitted entry count (or -1 if it exceeds int32).  With `analytic`, boxes and
+// spheres are not tessellated: each becomes one entry plus a row of `prims` — 24 floats: objectToWorld rows 0..2, then
+// worldToObject rows 0..2 (SphereInstance / BoxInstance, Assets/Services/BVH/HittableObjects.cs:16-20, 124-127).
+int64_t build_object_table(const rtb_scene_desc& s, bool analytic, std::vector<FlattenObject>& out, std::vector<float>& prims);
 
 // The 402 unit-sphere vertices of AddSphere (SceneGeometryConverter.cs:161-190), xyz per vertex.
 const float* unit_sphere_table();  // 402 * 3 floats

@@ -165,12 +165,16 @@ __device__ __forceinline__ void stage_scene(const SceneView& s, int node_f4, flo
 }
 
 // Triangle test shared by both flavours.  Returns true when a shadow ray found its occluder.
-template <bool SMEM>
-__device__ __forceinline__ bool lane_test_triangle(Lane& L, const float4* tri_isect, int32_t tri) {
+template <bool SMEM, bool ANALYTIC>
+__device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, const float4* tri_isect, int32_t tri) {
   const float4 a = ld4<SMEM>(&tri_isect[3 * tri]), b = ld4<SMEM>(&tri_isect[3 * tri + 1]), c = ld4<SMEM>(&tri_isect[3 * tri + 2]);
   Ray r; r.o = L.o; r.d = L.d;
   float t, u, v;
-  if (!moller_trumbore(r, mk3(a), mk3(b), mk3(c), t, u, v)) return false;
+  if (ANALYTIC && __float_as_int(c.w) != 0) {  // analytic primitive: hit record = (t_world, t_object, face code)
+    int face;
+    if (!intersect_analytic(&s.prims[6 * __float_as_int(a.x)], __float_as_int(c.w), L.o, L.d, t, u, face)) return false;
+    v = (float)face;
+  } else if (!moller_trumbore(r, mk3(a), mk3(b), mk3(c), t, u, v)) return false;
   if (!(t < L.t)) return false;
   if (L.shadow) { L.tri = 0; return true; }
   L.t = t; L.u = u; L.v = v; L.tri = tri;
@@ -180,7 +184,7 @@ __device__ __forceinline__ bool lane_test_triangle(Lane& L, const float4* tri_is
 // ---------------------------------------------------------------------------------------------------------------------
 // k_traverse, LBVH flavour: ordered traversal over 64-byte two-box nodes (see lbvh.cu for the layout).
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool SMEM>
+template <bool SMEM, bool ANALYTIC>
 __global__ void __launch_bounds__(SMEM ? kBlockSmem : kBlock, SMEM ? 1 : 4) k_traverse_lbvh(const SceneView s, const QueueView q, const int depth) {
   extern __shared__ float4 sm_scene[];
   const float4* nodes = s.nodes;
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kBlock, SMEM ? 1 : 4) k_tr
       const int32_t first = code >> 3, count = (code & 7) + 1;
       bool occluded = false;
       n_tris += count;
-      for (int32_t i = 0; i < count && !occluded; i++) occluded = lane_test_triangle<SMEM>(L, tri_isect, first + i);
+      for (int32_t i = 0; i < count && !occluded; i++) occluded = lane_test_triangle<SMEM, ANALYTIC>(L, s, tri_isect, first + i);
       cur = RTB_REF_DONE;
       if (!occluded)
         while (sp > 0) {
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kBlock, SMEM ? 1 : 4) k_tr
 // k_traverse, reference flavour: TraverseBVH compute:225-267 — LIFO stack, left child first, no distance ordering, node
 // culled when its own slab entry >= best t; leaves of any size.  Same results as the reference for every ray.
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool SMEM>
+template <bool SMEM, bool ANALYTIC>
 __global__ void __launch_bounds__(SMEM ? kBlockSmem : kBlock, SMEM ? 1 : 4) k_traverse_ref(const SceneView s, const QueueView q, const int depth) {
   extern __shared__ float4 sm_scene[];
   const float4* nodes = s.nodes;
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kBlock, SMEM ? 1 : 4) k_tr
     if (leaf_count > 0) {
       bool occluded = false;
       n_tris += leaf_count;
-      for (int32_t i = 0; i < leaf_count && !occluded; i++) occluded = lane_test_triangle<SMEM>(L, tri_isect, leaf_first + i);
+      for (int32_t i = 0; i < leaf_count && !occluded; i++) occluded = lane_test_triangle<SMEM, ANALYTIC>(L, s, tri_isect, leaf_first + i);
       leaf_count = 0;
       if (occluded) sp = 0;
     }
@@ -434,10 +438,11 @@ struct Shaded {
   f3 start, dir, att;          // :472 and the attenuation after :440/446/453
 };
 
+template <bool ANALYTIC>
 __device__ __forceinline__ void shade_hit(const FrameParams& f, const SceneView& s, const Ray& ray, f3 att, const Hit& hit, int px, int py, int sample,
                                           int depth, Shaded& o) {
-  const f3 pos = ray.o + hit.t * ray.d;  // :183
-  const f3 nrm = hit_normal(s, hit);
+  f3 pos, nrm;
+  hit_surface<ANALYTIC>(s, ray, hit, pos, nrm);  // :183-187
   const Material m = fetch_material(s, __float_as_int(__ldg(&s.tri_isect[3 * hit.tri + 1]).w));
   f3 local = mk3(0.0f, 0.0f, 0.0f);
   if (f.en_ambient == 1) local = local + m.color * m.ka;  // :379
@@ -506,6 +511,7 @@ __device__ __forceinline__ void shade_hit(const FrameParams& f, const SceneView&
 // ---------------------------------------------------------------------------------------------------------------------
 // k_shade: everything the reference does with a closest-hit result at one depth, for queues of at least `tail_max` rays.
 // ---------------------------------------------------------------------------------------------------------------------
+template <bool ANALYTIC>
 __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth,
                                                   const int32_t tail_max) {
   const int lane = threadIdx.x & 31;
@@ -549,7 +555,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const Sce
     }
     if (found) {
       if (depth == 0) n_hits++;
-      shade_hit(f, s, ray, att, hit, px, py, sample, depth, o);
+      shade_hit<ANALYTIC>(f, s, ray, att, hit, px, py, sample, depth, o);
       if (!o.emit_shadow) {  // otherwise k_traverse adds the lit or unlit increment once the shadow query is decided
         const f3 sum = prev + o.unlit;
         q.accum[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f);
@@ -590,7 +596,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const Sce
 // end in one thread — shade, shadow query, next closest hit, shade, ... — so slow rays of different depths overlap.  Same
 // per-slot operation order as the wavefront (and as the reference's depth loop), hence the same bits.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int BVH>
+template <int BVH, bool ANALYTIC>
 __global__ void __launch_bounds__(kBlock) k_tail(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth0,
                                                  const int32_t tail_max) {
   const int32_t n = RTB_CNT_RAY(q, depth0);
@@ -615,12 +621,12 @@ __global__ void __launch_bounds__(kBlock) k_tail(const FrameParams f, const Scen
       if (hit.tri < 0) { acc = acc + att * mk3(f.bg[0], f.bg[1], f.bg[2]); break; }  // :364-368
       if (depth == 0) n_hits++;
       Shaded o;
-      shade_hit(f, s, ray, att, hit, px, py, sample, depth, o);
+      shade_hit<ANALYTIC>(f, s, ray, att, hit, px, py, sample, depth, o);
       if (o.emit_shadow) {
         n_shadow++;
         Ray sr; sr.o = o.sh_origin; sr.d = o.sh_dir; sr.inv = mk3(1.0f / o.sh_dir.x, 1.0f / o.sh_dir.y, 1.0f / o.sh_dir.z);  // :395-398
         Hit sh;
-        const bool occluded = traverse<BVH, true>(s, sr, o.sh_dist, sh, overflow);
+        const bool occluded = traverse<BVH, true, ANALYTIC>(s, sr, o.sh_dist, sh, overflow);
         acc = acc + (occluded ? o.unlit : o.lit);  // :406-418
       } else {
         acc = acc + o.unlit;
@@ -629,7 +635,7 @@ __global__ void __launch_bounds__(kBlock) k_tail(const FrameParams f, const Scen
       n_cont++;
       ray = make_ray(o.start, o.dir);
       att = o.att;
-      traverse<BVH, false>(s, ray, 0.0f, hit, overflow);
+      traverse<BVH, false, ANALYTIC>(s, ray, 0.0f, hit, overflow);
     }
     q.accum[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
   }
@@ -666,7 +672,7 @@ __global__ void __launch_bounds__(kBlock) k_resolve(const FrameParams f, const Q
   }
 }
 
-template <int BVH>
+template <int BVH, bool ANALYTIC>
 __global__ void __launch_bounds__(kBlock) k_debug(const FrameParams f, const SceneView s, const ChunkView c, uchar4* __restrict__ dst) {
   const int n_px = c.rows * f.width;
   unsigned overflow = 0;
@@ -675,17 +681,20 @@ __global__ void __launch_bounds__(kBlock) k_debug(const FrameParams f, const Sce
     const int py = band_global_row(c.row0 + r, f.band_rank, f.band_world, f.band_rows);
     const Ray ray = generate_ray(f, px, py, -2);  // :486-489
     Hit h;
-    const bool found = traverse<BVH, false>(s, ray, 0.0f, h, overflow);
+    const bool found = traverse<BVH, false, ANALYTIC>(s, ray, 0.0f, h, overflow);
     f3 fin;
     if (f.debug == 1) { const float g = h.t / 100.0f; fin = found ? mk3(g, g, g) : mk3(1.0f, 0.0f, 0.0f); }
-    else if (f.debug == 2) fin = found ? hit_normal(s, h) * 0.5f + mk3(0.5f, 0.5f, 0.5f) : mk3(0.0f, 0.0f, 1.0f);
+    else if (f.debug == 2) {
+      fin = mk3(0.0f, 0.0f, 1.0f);
+      if (found) { f3 pos, nrm; hit_surface<ANALYTIC>(s, ray, h, pos, nrm); fin = nrm * 0.5f + mk3(0.5f, 0.5f, 0.5f); }
+    }
     else fin = found ? mk3(0.0f, 1.0f, 0.0f) : mk3(0.2f, 0.2f, 0.2f);
     dst[out_index(f, c.row0 + r, px)] = make_uchar4((unsigned char)quantize_unorm8(fin.x, f.srgb), (unsigned char)quantize_unorm8(fin.y, f.srgb),
                                                      (unsigned char)quantize_unorm8(fin.z, f.srgb), 255);
   }
 }
 
-template <int BVH>
+template <int BVH, bool ANALYTIC>
 __global__ void __launch_bounds__(kBlock) k_aux(const FrameParams f, const SceneView s, int32_t* __restrict__ prim, float* __restrict__ t_out, int32_t* __restrict__ mat) {
   // 8x4 tiles keep a warp's rays coherent; i enumerates tile-major
   const int tiles_x = (f.width + 7) >> 3;
@@ -697,7 +706,7 @@ __global__ void __launch_bounds__(kBlock) k_aux(const FrameParams f, const Scene
     if (px >= f.width || py >= f.height) continue;
     const Ray ray = generate_ray(f, px, py, -1);
     Hit h;
-    const bool found = traverse<BVH, false>(s, ray, 0.0f, h, overflow);
+    const bool found = traverse<BVH, false, ANALYTIC>(s, ray, 0.0f, h, overflow);
     const size_t at = (size_t)py * (size_t)f.width + (size_t)px;
     if (prim) prim[at] = found ? __float_as_int(__ldg(&s.tri_isect[3 * h.tri]).w) : -1;
     if (t_out) t_out[at] = h.t;
@@ -715,7 +724,7 @@ int blocks_per_sm(K kernel) {
 }  // namespace
 
 int traverse_blocks_per_sm(int bvh) {
-  return bvh == RTB_BVH_REFERENCE ? blocks_per_sm(k_traverse_ref<false>) : blocks_per_sm(k_traverse_lbvh<false>);
+  return bvh == RTB_BVH_REFERENCE ? blocks_per_sm(k_traverse_ref<false, false>) : blocks_per_sm(k_traverse_lbvh<false, false>);
 }
 
 void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st) {
@@ -728,29 +737,42 @@ size_t traverse_smem_bytes(int bvh, const SceneView& s) {
 }
 
 cudaError_t traverse_enable_smem(int bvh, size_t bytes) {
-  if (bvh == RTB_BVH_REFERENCE) return cudaFuncSetAttribute(k_traverse_ref<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  return cudaFuncSetAttribute(k_traverse_lbvh<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (bvh == RTB_BVH_REFERENCE) return cudaFuncSetAttribute(k_traverse_ref<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaFuncSetAttribute(k_traverse_lbvh<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// Scenes with analytic primitives (s.n_prims > 0) run the ANALYTIC instantiations; everything else keeps the leaner
+// triangle-only code.  The shared-memory variant exists for triangle-only scenes.
 void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int grid, size_t smem_bytes, cudaStream_t st) {
-  if (smem_bytes > 0) {  // small scene: one 1024-thread block per SM works out of its shared-memory copy
-    if (bvh == RTB_BVH_REFERENCE) k_traverse_ref<true><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
-    else k_traverse_lbvh<true><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
+  const bool ref = bvh == RTB_BVH_REFERENCE;
+  if (s.n_prims > 0) {
+    if (ref) k_traverse_ref<false, true><<<grid, kBlock, 0, st>>>(s, q, depth);
+    else k_traverse_lbvh<false, true><<<grid, kBlock, 0, st>>>(s, q, depth);
+  } else if (smem_bytes > 0) {  // small scene: one 1024-thread block per SM works out of its shared-memory copy
+    if (ref) k_traverse_ref<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
+    else k_traverse_lbvh<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
   } else {
-    if (bvh == RTB_BVH_REFERENCE) k_traverse_ref<false><<<grid, kBlock, 0, st>>>(s, q, depth);
-    else k_traverse_lbvh<false><<<grid, kBlock, 0, st>>>(s, q, depth);
+    if (ref) k_traverse_ref<false, false><<<grid, kBlock, 0, st>>>(s, q, depth);
+    else k_traverse_lbvh<false, false><<<grid, kBlock, 0, st>>>(s, q, depth);
   }
 }
 
 void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,
                   cudaStream_t st) {
-  k_shade<<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+  if (s.n_prims > 0) k_shade<true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+  else k_shade<false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
 }
 
 void launch_tail(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,
                  cudaStream_t st) {
-  if (bvh == RTB_BVH_REFERENCE) k_tail<RTB_BVH_REFERENCE><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
-  else k_tail<RTB_BVH_LBVH><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+  const bool ref = bvh == RTB_BVH_REFERENCE;
+  if (s.n_prims > 0) {
+    if (ref) k_tail<RTB_BVH_REFERENCE, true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+    else k_tail<RTB_BVH_LBVH, true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+  } else {
+    if (ref) k_tail<RTB_BVH_REFERENCE, false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+    else k_tail<RTB_BVH_LBVH, false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+  }
 }
 
 void launch_resolve(const FrameParams& f, const QueueView& q, const ChunkView& c, void* dst, int grid, cudaStream_t st) {
@@ -758,13 +780,25 @@ void launch_resolve(const FrameParams& f, const QueueView& q, const ChunkView& c
 }
 
 void launch_debug(int bvh, const FrameParams& f, const SceneView& s, const ChunkView& c, void* dst, int grid, cudaStream_t st) {
-  if (bvh == RTB_BVH_REFERENCE) k_debug<RTB_BVH_REFERENCE><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
-  else k_debug<RTB_BVH_LBVH><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
+  const bool ref = bvh == RTB_BVH_REFERENCE;
+  if (s.n_prims > 0) {
+    if (ref) k_debug<RTB_BVH_REFERENCE, true><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
+    else k_debug<RTB_BVH_LBVH, true><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
+  } else {
+    if (ref) k_debug<RTB_BVH_REFERENCE, false><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
+    else k_debug<RTB_BVH_LBVH, false><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
+  }
 }
 
 void launch_aux(int bvh, const FrameParams& f, const SceneView& s, int32_t* prim, float* t, int32_t* mat, int grid, cudaStream_t st) {
-  if (bvh == RTB_BVH_REFERENCE) k_aux<RTB_BVH_REFERENCE><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
-  else k_aux<RTB_BVH_LBVH><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
+  const bool ref = bvh == RTB_BVH_REFERENCE;
+  if (s.n_prims > 0) {
+    if (ref) k_aux<RTB_BVH_REFERENCE, true><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
+    else k_aux<RTB_BVH_LBVH, true><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
+  } else {
+    if (ref) k_aux<RTB_BVH_REFERENCE, false><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
+    else k_aux<RTB_BVH_LBVH, false><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
+  }
 }
 
 }  // namespace rtb

@@ -141,6 +141,78 @@ __device__ __forceinline__ bool slab_hit_fma(f3 inv, f3 ood, f3 mn, f3 mx, float
 __device__ __forceinline__ float safe_rcp(float d) { return fabsf(d) > 1e-18f ? 1.0f / d : copysignf(1e18f, d); }
 __device__ __forceinline__ f3 safe_inverse(f3 d) { return mk3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)); }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Analytic primitives (RTB_PRIM_ANALYTIC): the reference's SphereInstance / BoxInstance, Assets/Services/BVH/HittableObjects.cs
+// (never instantiated there; semantics taken from it): the ray goes to object space with its direction re-normalised
+// (:49-54, :153-155), meets the unit sphere (quadratic, :82-107) or the unit cube (slabs with face tracking, :180-223),
+// the hit point returns to world space and t = |pWS - origin| (:60-62).  P = 6 float4: objectToWorld rows, worldToObject rows.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ f3 mul_point_rows(const float4 r0, const float4 r1, const float4 r2, f3 v) {  // MultiplyPoint3x4
+  return mk3(((r0.x * v.x + r0.y * v.y) + r0.z * v.z) + r0.w, ((r1.x * v.x + r1.y * v.y) + r1.z * v.z) + r1.w,
+             ((r2.x * v.x + r2.y * v.y) + r2.z * v.z) + r2.w);
+}
+__device__ __forceinline__ f3 mul_vector_rows(const float4 r0, const float4 r1, const float4 r2, f3 v) {  // MultiplyVector
+  return mk3((r0.x * v.x + r0.y * v.y) + r0.z * v.z, (r1.x * v.x + r1.y * v.y) + r1.z * v.z, (r2.x * v.x + r2.y * v.y) + r2.z * v.z);
+}
+__device__ __forceinline__ bool intersect_unit_sphere(f3 o, f3 d, float& t) {
+  const float a = dot3(d, d);
+  const float b = 2.0f * dot3(o, d);
+  const float c = dot3(o, o) - 1.0f;
+  const float disc = b * b - (4.0f * a) * c;
+  if (disc < 0.0f) return false;
+  const float s = sqrtf(disc);
+  const float t0 = (-b - s) / (2.0f * a), t1 = (-b + s) / (2.0f * a);
+  t = (t0 > 1e-3f) ? t0 : t1;
+  return t > 1e-3f;
+}
+// face: 0 none, 1 -x, 2 +x, 3 -y, 4 +y, 5 -z, 6 +z
+__device__ __forceinline__ bool intersect_unit_box(f3 o, f3 d, float& t, int& face) {
+  float tmin = -1e20f, tmax = 1e20f;
+  int nmin = 0, nmax = 0;
+  const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+  for (int axis = 0; axis < 3; axis++) {
+    const float inv_d = fabsf(dd[axis]) > 1e-8f ? 1.0f / dd[axis] : INFINITY;
+    float t1 = (-0.5f - oo[axis]) * inv_d, t2 = (0.5f - oo[axis]) * inv_d;
+    int n1 = 1 + 2 * axis, n2 = 2 + 2 * axis;
+    if (t1 > t2) { const float tt = t1; t1 = t2; t2 = tt; const int nn = n1; n1 = n2; n2 = nn; }
+    if (t1 > tmin) { tmin = t1; nmin = n1; }
+    if (t2 < tmax) { tmax = t2; nmax = n2; }
+    if (tmin > tmax) return false;
+    if (tmax < 1e-3f) return false;
+  }
+  t = tmin >= 1e-3f ? tmin : tmax;
+  face = (t == tmin) ? nmin : nmax;
+  return t >= 1e-3f;
+}
+// Hit test of one analytic primitive.  Returns true with world t, object-space t and the box face when it is hit with
+// t_world > Epsilon; the caller applies its upper bound.
+__device__ __forceinline__ bool intersect_analytic(const float4* __restrict__ P, int kind, f3 ro, f3 rd, float& t_world, float& t_os, int& face) {
+  const float4 w0 = __ldg(&P[3]), w1 = __ldg(&P[4]), w2 = __ldg(&P[5]);
+  const f3 o = mul_point_rows(w0, w1, w2, ro);
+  const f3 d = unity_normalized(mul_vector_rows(w0, w1, w2, rd));
+  face = 0;
+  if (kind == 1 ? !intersect_unit_sphere(o, d, t_os) : !intersect_unit_box(o, d, t_os, face)) return false;
+  const f3 p_os = o + t_os * d;
+  const f3 p_ws = mul_point_rows(__ldg(&P[0]), __ldg(&P[1]), __ldg(&P[2]), p_os);
+  const f3 dv = p_ws - ro;
+  t_world = sqrtf((dv.x * dv.x + dv.y * dv.y) + dv.z * dv.z);
+  return t_world > RTB_EPSILON;
+}
+// World position and normal of an analytic hit: rec.positionWS = pWS, rec.normalWS = (worldToObject^T nOS).normalized (:65-71, :166-170)
+__device__ __forceinline__ void analytic_surface(const float4* __restrict__ P, int kind, f3 ro, f3 rd, float t_os, int face, f3& pos, f3& nrm) {
+  const float4 w0 = __ldg(&P[3]), w1 = __ldg(&P[4]), w2 = __ldg(&P[5]);
+  const f3 o = mul_point_rows(w0, w1, w2, ro);
+  const f3 d = unity_normalized(mul_vector_rows(w0, w1, w2, rd));
+  const f3 p_os = o + t_os * d;
+  pos = mul_point_rows(__ldg(&P[0]), __ldg(&P[1]), __ldg(&P[2]), p_os);
+  f3 n_os;
+  if (kind == 1) n_os = unity_normalized(p_os);
+  else n_os = mk3(face == 1 ? -1.0f : (face == 2 ? 1.0f : 0.0f), face == 3 ? -1.0f : (face == 4 ? 1.0f : 0.0f), face == 5 ? -1.0f : (face == 6 ? 1.0f : 0.0f));
+  nrm = unity_normalized(mk3((w0.x * n_os.x + w1.x * n_os.y) + w2.x * n_os.z, (w0.y * n_os.x + w1.y * n_os.y) + w2.y * n_os.z,
+                             (w0.z * n_os.x + w1.z * n_os.y) + w2.z * n_os.z));
+}
+
 // IntersectTriangle, compute:153-190, on the stored (v0, e1 = v1-v0, e2 = v2-v0).  Returns true and t,u,v when the
 // triangle is hit with t > Epsilon; the caller applies its own upper bound (closest: t < best.t; shadow: t <= dist).
 __device__ __forceinline__ bool moller_trumbore(const Ray& r, f3 v0, f3 e1, f3 e2, float& t, float& u, float& v) {
@@ -158,14 +230,28 @@ __device__ __forceinline__ bool moller_trumbore(const Ray& r, f3 v0, f3 e1, f3 e
   return t > RTB_EPSILON;
 }
 
+// For an analytic primitive the hit record holds (t_world, t_object, face code) in (t, u, v).
+template <bool ANALYTIC>
 __device__ __forceinline__ void test_triangle_closest(const SceneView& s, const Ray& r, int32_t tri, Hit& best) {
   const float4 a = __ldg(&s.tri_isect[3 * tri]), b = __ldg(&s.tri_isect[3 * tri + 1]), c = __ldg(&s.tri_isect[3 * tri + 2]);
   float t, u, v;
+  if (ANALYTIC && __float_as_int(c.w) != 0) {
+    int face;
+    if (intersect_analytic(&s.prims[6 * __float_as_int(a.x)], __float_as_int(c.w), r.o, r.d, t, u, face) && t < best.t) {
+      best.t = t; best.u = u; best.v = (float)face; best.tri = tri;
+    }
+    return;
+  }
   if (moller_trumbore(r, mk3(a), mk3(b), mk3(c), t, u, v) && t < best.t) { best.t = t; best.u = u; best.v = v; best.tri = tri; }
 }
+template <bool ANALYTIC>
 __device__ __forceinline__ bool test_triangle_any(const SceneView& s, const Ray& r, int32_t tri, float t_limit) {
   const float4 a = __ldg(&s.tri_isect[3 * tri]), b = __ldg(&s.tri_isect[3 * tri + 1]), c = __ldg(&s.tri_isect[3 * tri + 2]);
   float t, u, v;
+  if (ANALYTIC && __float_as_int(c.w) != 0) {
+    int face;
+    return intersect_analytic(&s.prims[6 * __float_as_int(a.x)], __float_as_int(c.w), r.o, r.d, t, u, face) && t <= t_limit;
+  }
   return moller_trumbore(r, mk3(a), mk3(b), mk3(c), t, u, v) && t <= t_limit;
 }
 
@@ -174,7 +260,7 @@ __device__ __forceinline__ bool test_triangle_any(const SceneView& s, const Ray&
 // when its slab entry distance >= the best t so far.  ANY = shadow query: stops at the first triangle with
 // Epsilon < t <= t_limit, which decides "lit" exactly like the reference's closest-hit test (:403-406): lit <=> no such hit.
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool ANY>
+template <bool ANY, bool ANALYTIC>
 __device__ __forceinline__ bool traverse_reference(const SceneView& s, const Ray& r, float t_limit, Hit& best, unsigned& overflow) {
   best.t = RTB_INFINITY; best.u = 0.0f; best.v = 0.0f; best.tri = -1;
   if (s.n_nodes == 0) return false;
@@ -189,8 +275,8 @@ __device__ __forceinline__ bool traverse_reference(const SceneView& s, const Ray
     const int32_t count = __float_as_int(hi.w), left_or_first = __float_as_int(lo.w);
     if (count > 0) {
       for (int32_t i = 0; i < count; i++) {
-        if (ANY) { if (test_triangle_any(s, r, left_or_first + i, t_limit)) return true; }
-        else test_triangle_closest(s, r, left_or_first + i, best);
+        if (ANY) { if (test_triangle_any<ANALYTIC>(s, r, left_or_first + i, t_limit)) return true; }
+        else test_triangle_closest<ANALYTIC>(s, r, left_or_first + i, best);
       }
     } else if (sp + 2 <= RTB_STACK_REF) {
       stack[sp++] = left_or_first + 1;
@@ -209,7 +295,7 @@ __device__ __forceinline__ bool traverse_reference(const SceneView& s, const Ray
 // boxes.  (This per-thread form serves the aux / debug kernels; the wavefront uses the persistent form in trace.cu.)
 // Node layout (4 x float4): (lmin, left_ref) (lmax, right_ref) (rmin, -) (rmax, -).
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool ANY>
+template <bool ANY, bool ANALYTIC>
 __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, float t_limit, Hit& best, unsigned& overflow) {
   best.t = RTB_INFINITY; best.u = 0.0f; best.v = 0.0f; best.tri = -1;
   if (s.n_tris == 0) return false;
@@ -244,8 +330,8 @@ __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, 
       const int32_t code = ~cur;
       const int32_t first = code >> 3, count = (code & 7) + 1;
       for (int32_t i = 0; i < count; i++) {
-        if (ANY) { if (test_triangle_any(s, r, first + i, t_limit)) return true; }
-        else test_triangle_closest(s, r, first + i, best);
+        if (ANY) { if (test_triangle_any<ANALYTIC>(s, r, first + i, t_limit)) return true; }
+        else test_triangle_closest<ANALYTIC>(s, r, first + i, best);
       }
     }
     // pop the next deferred child that can still matter
@@ -258,17 +344,35 @@ __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, 
   }
 }
 
-template <int BVH, bool ANY>
+template <int BVH, bool ANY, bool ANALYTIC>
 __device__ __forceinline__ bool traverse(const SceneView& s, const Ray& r, float t_limit, Hit& best, unsigned& overflow) {
-  if (BVH == RTB_BVH_REFERENCE) return traverse_reference<ANY>(s, r, t_limit, best, overflow);
-  return traverse_lbvh<ANY>(s, r, t_limit, best, overflow);
+  if (BVH == RTB_BVH_REFERENCE) return traverse_reference<ANY, ANALYTIC>(s, r, t_limit, best, overflow);
+  return traverse_lbvh<ANY, ANALYTIC>(s, r, t_limit, best, overflow);
 }
+
+// Position and shading normal of a closest hit: triangle (compute:183-187) or analytic primitive.
+template <bool ANALYTIC>
+__device__ __forceinline__ void hit_surface(const SceneView& s, const Ray& ray, const Hit& h, f3& pos, f3& nrm);
 
 // Interpolated normal of a hit, compute:186-187
 __device__ __forceinline__ f3 hit_normal(const SceneView& s, const Hit& h) {
   const float4 n0 = __ldg(&s.tri_shade[3 * h.tri]), n1 = __ldg(&s.tri_shade[3 * h.tri + 1]), n2 = __ldg(&s.tri_shade[3 * h.tri + 2]);
   const float w = 1.0f - h.u - h.v;
   return hlsl_normalize((w * mk3(n0) + h.u * mk3(n1)) + h.v * mk3(n2));
+}
+
+template <bool ANALYTIC>
+__device__ __forceinline__ void hit_surface(const SceneView& s, const Ray& ray, const Hit& h, f3& pos, f3& nrm) {
+  if (ANALYTIC) {
+    const int kind = __float_as_int(__ldg(&s.tri_isect[3 * h.tri + 2]).w);
+    if (kind != 0) {
+      const int idx = __float_as_int(__ldg(&s.tri_isect[3 * h.tri]).x);
+      analytic_surface(&s.prims[6 * idx], kind, ray.o, ray.d, h.u, (int)h.v, pos, nrm);
+      return;
+    }
+  }
+  pos = ray.o + h.t * ray.d;
+  nrm = hit_normal(s, h);
 }
 
 struct Material { f3 color; float ka, kd, ks, kr, ior; };

@@ -154,7 +154,8 @@ struct RenderTexture { void* device_ptr = nullptr; int width = 0, height = 0; };
 
 class RayTracer {
  public:
-  explicit RayTracer(const std::vector<int32_t>& devices = {}, int bvh_mode = RTB_BVH_REFERENCE) : bvh_mode_(bvh_mode) {
+  explicit RayTracer(const std::vector<int32_t>& devices = {}, int bvh_mode = RTB_BVH_REFERENCE, int primitive_mode = RTB_PRIM_TESSELLATED)
+      : bvh_mode_(bvh_mode), primitive_mode_(primitive_mode) {
     const int rc = rtb_create(&ctx_, devices.empty() ? nullptr : devices.data(), (int32_t)devices.size());
     if (rc != RTB_OK) throw Error(rc, rtb_last_error(nullptr));
   }
@@ -205,7 +206,7 @@ class RayTracer {
     if (!scene) return false;
     if (needs_rebuild_ || cached_ != scene) {  // RayTracer.cs:118-123: the cache key is the scene object's identity
       packed_ = std::make_unique<PackedScene>(*scene);
-      check(rtb_upload_scene(ctx_, packed_->desc(), RTB_PRIM_TESSELLATED, bvh_mode_));
+      check(rtb_upload_scene(ctx_, packed_->desc(), primitive_mode_, bvh_mode_));
       cached_ = scene;
       needs_rebuild_ = false;
     }
@@ -215,7 +216,7 @@ class RayTracer {
   void check_create(int rc) { if (rc != RTB_OK) throw Error(rc, rtb_last_error(nullptr)); }
 
   rtb_context* ctx_ = nullptr;
-  int bvh_mode_;
+  int bvh_mode_, primitive_mode_;
   const ObjectData* cached_ = nullptr;
   bool needs_rebuild_ = true;
   std::unique_ptr<PackedScene> packed_;

@@ -451,7 +451,7 @@ static void add_sphere(std::vector<Tri>& out, const M4& m, int mat) {
     add_smooth_tri(out, m, normalMat, sv[last], sv[last - (nbLong + 1) + lon], sv[last - (nbLong + 1) + lon + 1], mat);
 }
 // ExtractTriangles :18-51 — meshes, then boxes, then spheres
-static std::vector<Tri> extract_triangles(const rtb_scene_desc& s) {
+static std::vector<Tri> extract_triangles(const rtb_scene_desc& s, bool meshes_only = false) {
   std::vector<Tri> out;
   out.reserve((size_t)s.n_triangles + 12 * (size_t)s.n_boxes + 768 * (size_t)s.n_spheres);
   for (int mi = 0; mi < s.n_meshes; mi++) {
@@ -464,6 +464,7 @@ static std::vector<Tri> extract_triangles(const rtb_scene_desc& s) {
       out.push_back(make_tri(a, b, c, t.material));
     }
   }
+  if (meshes_only) return out;  // analytic mode: boxes and spheres stay primitives (struct Analytic below)
   for (int i = 0; i < s.n_boxes; i++) add_cube(out, build_matrix(s, s.boxes[i].xform), s.boxes[i].material);
   for (int i = 0; i < s.n_spheres; i++) add_sphere(out, build_matrix(s, s.spheres[i].xform), s.spheres[i].material);
   return out;
@@ -519,8 +520,16 @@ struct Builder {
   }
 };
 
+// Analytic primitive mode (RTB_PRIM_ANALYTIC): spheres and boxes keep the semantics of the reference's (never instantiated)
+// SphereInstance / BoxInstance, Assets/Services/BVH/HittableObjects.cs:6-224 — unit sphere / unit cube in object space, ray
+// taken to object space with the direction re-normalised, world t = |pWS - origin|, normal = normalize((M^-1)^T n).
+struct Analytic { int kind; /* 1 sphere, 2 box */ M4 M, W; int material; };
+struct AnalyticHit { float tOS; int face; };  // what shading needs besides t: object-space t; box face 1..6 = -x +x -y +y -z +z
+
 struct Scene {
   OwnedScene owned;
+  bool analytic = false;
+  std::vector<Analytic> prims;      // analytic mode: boxes then spheres (emission order continues after the mesh triangles)
   std::vector<Tri> tris_emit;       // emission order (prim_id = index here)
   std::vector<Tri> tris;            // BVH leaf order (what the reference uploads)
   std::vector<int> orig;            // tris[i] == tris_emit[orig[i]]
@@ -531,8 +540,13 @@ struct Scene {
 
 static void build_scene(Scene& sc) {
   const rtb_scene_desc& d = sc.owned.d;
-  sc.tris_emit = extract_triangles(d);
-  sc.nodes.clear(); sc.tris.clear(); sc.orig.clear();
+  sc.tris_emit = extract_triangles(d, sc.analytic);
+  sc.prims.clear();
+  if (sc.analytic) {
+    for (int i = 0; i < d.n_boxes; i++) { M4 M = build_matrix(d, d.boxes[i].xform); sc.prims.push_back(Analytic{2, M, m4_inverse(M), d.boxes[i].material}); }
+    for (int i = 0; i < d.n_spheres; i++) { M4 M = build_matrix(d, d.spheres[i].xform); sc.prims.push_back(Analytic{1, M, m4_inverse(M), d.spheres[i].material}); }
+  }
+  sc.nodes.clear(); sc.tris.clear(); sc.orig.clear(); sc.max_leaf = 0;
   if (!sc.tris_emit.empty()) {
     Builder b(sc.tris_emit);
     int root = b.build(0, (int)sc.tris_emit.size());
@@ -569,7 +583,9 @@ static void build_scene(Scene& sc) {
 // ---------------------------------------------------------------------------------------------------------------------
 struct Ray { V3 o, d, inv; };
 static inline Ray CreateRay(V3 o, V3 d) { return Ray{o, d, v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z)}; }  // :137-144
-struct Hit { bool hit; float t; int tri; float u, v; };  // HitRecord :22-29 (position/normal derived from t,u,v on demand)
+// HitRecord :22-29 (position/normal derived on demand).  tri >= 0: triangle (leaf order), u,v barycentrics.
+// prim >= 0: analytic primitive, u = object-space t, v = box face code.
+struct Hit { bool hit; float t; int tri; float u, v; int prim = -1; };
 
 struct Counters {
   int64_t rays_primary = 0, rays_continuation = 0, rays_shadow = 0, nodes_visited = 0, tris_tested = 0, closest_hits = 0, primary_hits = 0;
@@ -627,6 +643,75 @@ static Hit TraverseBVH(const Scene& sc, const Ray& r, Counters& c) {
   }
   return hit;
 }
+// SphereInstance.IntersectUnitSphere, HittableObjects.cs:82-107
+static inline bool IntersectUnitSphere(V3 o, V3 d, float* t) {
+  float a = dot(d, d);
+  float b = 2.0f * dot(o, d);
+  float c = dot(o, o) - 1.0f;
+  float disc = b * b - (4.0f * a) * c;
+  if (disc < 0.0f) return false;
+  float s = sqrtf(disc);
+  float t0 = (-b - s) / (2.0f * a), t1 = (-b + s) / (2.0f * a);
+  *t = (t0 > 1e-3f) ? t0 : t1;
+  return *t > 1e-3f;
+}
+// BoxInstance.IntersectUnitBox, HittableObjects.cs:180-223; face: 0 none, 1 -x, 2 +x, 3 -y, 4 +y, 5 -z, 6 +z
+static inline bool IntersectUnitBox(V3 o, V3 d, float* t, int* face) {
+  float tmin = -1e20f, tmax = 1e20f;
+  int nmin = 0, nmax = 0;
+  const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+  for (int axis = 0; axis < 3; axis++) {
+    float invD = fabsf(dd[axis]) > 1e-8f ? 1.0f / dd[axis] : INFINITY;
+    float t1 = (-0.5f - oo[axis]) * invD, t2 = (0.5f - oo[axis]) * invD;
+    int n1 = 1 + 2 * axis, n2 = 2 + 2 * axis;
+    if (t1 > t2) { std::swap(t1, t2); std::swap(n1, n2); }
+    if (t1 > tmin) { tmin = t1; nmin = n1; }
+    if (t2 < tmax) { tmax = t2; nmax = n2; }
+    if (tmin > tmax) return false;
+    if (tmax < 1e-3f) return false;
+  }
+  *t = tmin >= 1e-3f ? tmin : tmax;
+  *face = (*t == tmin) ? nmin : nmax;
+  return *t >= 1e-3f;
+}
+static inline V3 face_normal(int face) {
+  switch (face) {
+    case 1: return v3(-1, 0, 0); case 2: return v3(1, 0, 0); case 3: return v3(0, -1, 0);
+    case 4: return v3(0, 1, 0); case 5: return v3(0, 0, -1); case 6: return v3(0, 0, 1);
+    default: return v3(0, 0, 0);
+  }
+}
+static inline V3 analytic_point_os(const Analytic& p, const Ray& r, float tOS) {  // pOS = rOS.origin + tOS * rOS.direction
+  V3 o = mul_point3x4(p.W, r.o), d = unity_normalized(mul_vector(p.W, r.d));
+  return o + tOS * d;
+}
+// SphereInstance.Hit :45-77 / BoxInstance.Hit :149-174 with tMin = Epsilon, tMax = best.t of the live kernel's loop
+static inline void IntersectAnalytic(const Ray& r, const Analytic& p, int index, Hit& best) {
+  V3 o = mul_point3x4(p.W, r.o), d = unity_normalized(mul_vector(p.W, r.d));
+  float tOS; int face = 0;
+  if (p.kind == 1 ? !IntersectUnitSphere(o, d, &tOS) : !IntersectUnitBox(o, d, &tOS, &face)) return;
+  V3 pOS = o + tOS * d;
+  V3 pWS = mul_point3x4(p.M, pOS);
+  V3 dv = pWS - r.o;
+  float tWS = sqrtf((dv.x * dv.x + dv.y * dv.y) + dv.z * dv.z);  // .magnitude
+  if (tWS < best.t && tWS > kEpsilon) { best.hit = true; best.t = tWS; best.tri = -1; best.prim = index; best.u = tOS; best.v = (float)face; }
+}
+// worldToObject.transpose.MultiplyVector(nOS).normalized
+static inline V3 analytic_normal(const Analytic& p, const Ray& r, const Hit& h) {
+  V3 nOS = p.kind == 1 ? unity_normalized(analytic_point_os(p, r, h.u)) : face_normal((int)h.v);
+  const M4& W = p.W;
+  return unity_normalized(v3((W.m[0][0] * nOS.x + W.m[1][0] * nOS.y) + W.m[2][0] * nOS.z, (W.m[0][1] * nOS.x + W.m[1][1] * nOS.y) + W.m[2][1] * nOS.z,
+                             (W.m[0][2] * nOS.x + W.m[1][2] * nOS.y) + W.m[2][2] * nOS.z));
+}
+static Hit TraverseBVH(const Scene& sc, const Ray& r, Counters& c);
+// The scene query of analytic mode: triangles through the BVH, then every analytic primitive in emission order; the
+// strict "<" keeps the first of equal t, as everywhere else.
+static Hit TraverseScene(const Scene& sc, const Ray& r, Counters& c) {
+  Hit hit = TraverseBVH(sc, r, c);
+  for (size_t i = 0; i < sc.prims.size(); i++) IntersectAnalytic(r, sc.prims[i], (int)i, hit);
+  return hit;
+}
+
 static inline V3 hit_normal(const Tri& t, float u, float v) {  // :186-187
   float w = 1.0f - u - v;
   return hlsl_normalize((w * t.n0 + u * t.n1) + v * t.n2);
@@ -734,16 +819,26 @@ static V3 trace_sample(const Scene& sc, const Frame& f, int px, int py, int i, C
   Ray ray = gen_ray(f, px, py, i);
   for (int depth = 0; depth < f.maxDepth; depth++) {
     if (depth == 0) c.rays_primary++; else c.rays_continuation++;
-    Hit hit = TraverseBVH(sc, ray, c);
+    Hit hit = TraverseScene(sc, ray, c);
     if (depth == 0 && primary_out) *primary_out = hit;
     if (!hit.hit) { sampleColor = sampleColor + attenuation * f.bg; break; }
     c.closest_hits++;
     if (depth == 0) c.primary_hits++;
-    const Tri& tri = sc.tris[hit.tri];
-    V3 pos = ray.o + hit.t * ray.d;
-    V3 n = hit_normal(tri, hit.u, hit.v);
+    V3 pos, n;
+    int material_index;
+    if (hit.prim >= 0) {  // analytic primitive: rec.positionWS = pWS, rec.normalWS (HittableObjects.cs:65-71)
+      const Analytic& ap = sc.prims[hit.prim];
+      pos = mul_point3x4(ap.M, analytic_point_os(ap, ray, hit.u));
+      n = analytic_normal(ap, ray, hit);
+      material_index = ap.material;
+    } else {
+      const Tri& tri = sc.tris[hit.tri];
+      pos = ray.o + hit.t * ray.d;
+      n = hit_normal(tri, hit.u, hit.v);
+      material_index = tri.material;
+    }
     V3 col; float ka, kd, ks, kr, ior;
-    material_of(sc, tri.material, col, ka, kd, ks, kr, ior);
+    material_of(sc, material_index, col, ka, kd, ks, kr, ior);
     V3 local = v3(0, 0, 0);
     if (f.amb == 1) local = local + col * ka;
     V3 lightPos = f.lightPos;
@@ -759,7 +854,7 @@ static V3 trace_sample(const Scene& sc, const Frame& f, int px, int py, int i, C
       float dist = hlsl_length(toL);
       c.rays_shadow++;
       const int64_t n0 = c.nodes_visited, t0 = c.tris_tested;
-      Hit sh = TraverseBVH(sc, sr, c);
+      Hit sh = TraverseScene(sc, sr, c);
       c.nodes_visited_shadow += c.nodes_visited - n0;
       c.tris_tested_shadow += c.tris_tested - t0;
       if (!sh.hit || sh.t > dist) {
@@ -856,6 +951,15 @@ int orc_load(const char* path, orc_scene** out, char* err, size_t cap) {
   return orc_parse(text.data(), text.size(), out, err, cap);
 }
 
+// RTB_PRIM_TESSELLATED (0, the reference's behaviour) or RTB_PRIM_ANALYTIC (1): rebuilds the scene.
+int orc_set_primitive_mode(orc_scene* s, int32_t mode) {
+  if (!s || (mode != RTB_PRIM_TESSELLATED && mode != RTB_PRIM_ANALYTIC)) return RTB_E_ARG;
+  s->s.analytic = mode == RTB_PRIM_ANALYTIC;
+  build_scene(s->s);
+  return RTB_OK;
+}
+int64_t orc_n_primitives(const orc_scene* s) { return (int64_t)(s->s.tris_emit.size() + s->s.prims.size()); }
+
 void orc_free(orc_scene* s) { delete s; }
 const rtb_scene_desc* orc_desc(const orc_scene* s) { return &s->s.owned.d; }
 int64_t orc_n_triangles(const orc_scene* s) { return (int64_t)s->s.tris_emit.size(); }
@@ -930,21 +1034,21 @@ int orc_render(const orc_scene* s, const rtb_render_params* p, int32_t row_begin
       }
       float ns = (float)f.n_samples;
       V3 fin = v3(accum.x / ns, accum.y / ns, accum.z / ns);  // :478
-      if (want_aux) { Counters scratch; ph = TraverseBVH(sc, gen_ray(f, x, y, -1), scratch); }
+      if (want_aux) { Counters scratch; ph = TraverseScene(sc, gen_ray(f, x, y, -1), scratch); }
       if (f.debug != 0) {
         Counters scratch;
         Ray cr = gen_ray(f, x, y, -2);  // centre ray, always perspective, :486-489
-        Hit ph = TraverseBVH(sc, cr, scratch);
+        Hit ph = TraverseScene(sc, cr, scratch);
         if (f.debug == 1) { float g = ph.t / 100.0f; fin = ph.hit ? v3(g, g, g) : v3(1, 0, 0); }
-        else if (f.debug == 2) { if (ph.hit) { V3 n = hit_normal(sc.tris[ph.tri], ph.u, ph.v); fin = n * 0.5f + v3(0.5f, 0.5f, 0.5f); } else fin = v3(0, 0, 1); }
+        else if (f.debug == 2) { if (ph.hit) { V3 n = ph.prim >= 0 ? analytic_normal(sc.prims[ph.prim], cr, ph) : hit_normal(sc.tris[ph.tri], ph.u, ph.v); fin = n * 0.5f + v3(0.5f, 0.5f, 0.5f); } else fin = v3(0, 0, 1); }
         else if (f.debug == 3) fin = ph.hit ? v3(0, 1, 0) : v3(0.2f, 0.2f, 0.2f);
       }
       size_t at = (size_t)y * (size_t)f.w + (size_t)x;
       if (rgba8) { rgba8[at * 4] = quantize(fin.x); rgba8[at * 4 + 1] = quantize(fin.y); rgba8[at * 4 + 2] = quantize(fin.z); rgba8[at * 4 + 3] = 255; }
       if (rgbf) { rgbf[at * 3] = fin.x; rgbf[at * 3 + 1] = fin.y; rgbf[at * 3 + 2] = fin.z; }
-      if (prim) prim[at] = ph.hit ? sc.orig[ph.tri] : -1;
+      if (prim) prim[at] = !ph.hit ? -1 : (ph.prim >= 0 ? (int)sc.tris_emit.size() + ph.prim : sc.orig[ph.tri]);
       if (tout) tout[at] = ph.t;
-      if (mat) mat[at] = ph.hit ? sc.tris[ph.tri].material : -1;
+      if (mat) mat[at] = !ph.hit ? -1 : (ph.prim >= 0 ? sc.prims[ph.prim].material : sc.tris[ph.tri].material);
     }
   }
 #ifdef _OPENMP

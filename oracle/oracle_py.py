@@ -56,6 +56,9 @@ def lib():
             getattr(L, n).argtypes = [VP]
             getattr(L, n).restype = C.c_int64
         L.orc_max_leaf.argtypes = [VP]
+        L.orc_set_primitive_mode.argtypes = [VP, C.c_int32]
+        L.orc_n_primitives.argtypes = [VP]
+        L.orc_n_primitives.restype = C.c_int64
         L.orc_get_triangles.argtypes = [VP, VP, VP, VP]
         L.orc_get_bvh.argtypes = [VP, VP, VP]
         L.orc_resolve.argtypes = [VP, C.POINTER(_abi.RenderParams), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -98,6 +101,16 @@ class OracleScene:
         if getattr(self, "h", None):
             lib().orc_free(self.h)
             self.h = None
+
+    def set_primitive_mode(self, mode: int):
+        """0 = tessellated (reference behaviour), 1 = analytic spheres / boxes (HittableObjects.cs semantics)."""
+        if lib().orc_set_primitive_mode(self.h, mode) != 0:
+            raise ValueError("bad primitive mode")
+        return self
+
+    @property
+    def n_primitives(self) -> int:
+        return lib().orc_n_primitives(self.h)
 
     @property
     def desc(self):

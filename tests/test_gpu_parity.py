@@ -247,7 +247,7 @@ def test_errors(tracers, samples, abi):
     lib.rtb_set_cancel_flag(ctx, C.addressof(flag))
     assert lib.rtb_render(ctx, C.byref(p), buf.ctypes.data, buf.nbytes, None, None) == abi.RTB_E_CANCELLED
     lib.rtb_set_cancel_flag(ctx, None)
-    assert lib.rtb_upload_scene(ctx, packed.ptr(), abi.RTB_PRIM_ANALYTIC, abi.RTB_BVH_REFERENCE) == abi.RTB_E_ARG
+    assert lib.rtb_upload_scene(ctx, packed.ptr(), 7, abi.RTB_BVH_REFERENCE) == abi.RTB_E_ARG  # unknown primitive mode
     lib.rtb_destroy(ctx)
 
 
@@ -423,3 +423,37 @@ def test_shared_memory_staged_traversal_matches(samples, monkeypatch):
             if mode == abi.RTB_BVH_REFERENCE:
                 assert same == 1.0
         rt.close()
+
+
+# ---- analytic primitive mode: spheres / boxes with the semantics of the reference's HittableObjects.cs ----------------
+@pytest.mark.parametrize("mode", [abi.RTB_BVH_REFERENCE, abi.RTB_BVH_LBVH])
+@pytest.mark.parametrize("scene_name", ["test_scene_1", "eval_scene", "grid4", "grid_rot"])
+def test_analytic_primitive_mode_matches_oracle(oracle, samples, mode, scene_name):
+    if scene_name == "grid4":
+        obj = synth.sphere_grid_scene(4)
+    elif scene_name == "grid_rot":  # rotated, non-uniformly scaled spheres and boxes: exercises the inverse-transpose normals
+        obj = synth.sphere_grid_scene(3)
+        T = scene_mod.TransformElement
+        for k, tr in enumerate(obj.Transformations[3:12]):
+            tr.Elements += [T.RotationX(20.0 * k), T.RotationZ(35.0), T.Scale((1.0 + 0.2 * k, 0.7, 1.3))]
+        obj.Transformations.append(scene_mod.CompositeTransformation([T.Translation((0.0, 0.0, 6.0)), T.RotationY(30.0), T.Scale((4.0, 2.0, 1.0))]))
+        obj.Boxes.append(scene_mod.BoxDescription(len(obj.Transformations) - 1, 1))
+    else:
+        obj = samples[scene_name][0]
+    osc, holder = oracle_scene(oracle, obj)
+    osc.set_primitive_mode(abi.RTB_PRIM_ANALYTIC)
+    rt = rt_mod.RayTracer(bvh_mode=mode, primitive_mode=abi.RTB_PRIM_ANALYTIC)
+    for kw in (dict(), dict(is_orthographic=1), dict(debug_mode=2)):
+        p = params(400, 300, 8, **kw)
+        tex = rt.RenderAsync(obj, p)
+        ref = osc.render(p, want_aux=True)
+        within, same, worst = assert_rgb_parity(tex.pixels, ref["rgba8"], f"analytic {scene_name} mode {mode} {kw}")
+        if not kw:
+            s, c = rt.stats(), ref["counters"]
+            assert s.n_triangles == osc.n_primitives
+            assert abs((s.rays_primary + s.rays_continuation + s.rays_shadow) - c.rays) <= 0.001 * c.rays
+            prim, t, mat = rt.primary_hits(obj, p)
+            assert (t.view(np.uint32) == ref["t"].view(np.uint32)).mean() >= 0.9999
+            assert (prim == ref["prim"]).mean() >= 0.999 and (mat == ref["mat"]).mean() >= 0.999
+            assert s.reserved[0] == 0
+    rt.close()
