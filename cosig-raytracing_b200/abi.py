@@ -115,6 +115,8 @@ SYMBOLS = {
     "rtb_invalidate": (C.c_int, [_VP]),
     "rtb_clear_target": (C.c_int, [_VP]),
     "rtb_render": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "rtb_render_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, C.c_size_t, C.POINTER(C.c_int32)]),
+    "rtb_render_end": (C.c_int, [_VP, C.c_int32]),
     "rtb_render_device": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, C.c_size_t, C.c_int32]),
     "rtb_render_aux": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, _VP, _VP]),
     "rtb_get_triangles": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.POINTER(C.c_int64)]),

@@ -55,6 +55,9 @@ struct DeviceState {
   bool resolve_pending = false;
   LaneState lane[2];
   int next_lane = 0;
+  int last_lane = 0;              // lane of the last chunk enqueued (where a frame's readback is ordered)
+  void* frame_async[2] = {nullptr, nullptr};  // frames of rtb_render_begin, alternating, so a readback never races the next frame
+  size_t frame_async_bytes[2] = {0, 0};
   float* sphere_table = nullptr;
   DeviceScene scene;
   void* frame = nullptr;  // RGBA8 frame (device 0) — also the IPC-exported buffer
@@ -85,6 +88,9 @@ struct rtb_context {
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
   int32_t tail_max = 196608;  // queues smaller than this finish in k_tail (RTB_TAIL_MAX; 0 = pure wavefront)
   std::vector<void*> ipc_opened;
+  static constexpr int kTickets = 8;  // frames in flight through rtb_render_begin
+  cudaEvent_t ticket_event[kTickets] = {};
+  uint64_t tickets_issued = 0;
 };
 
 struct rtb_scene {
@@ -145,6 +151,7 @@ void free_targets(DeviceState& d) {
     l.q = Queues();
   }
   dfree(d.frame); d.frame_bytes = 0;
+  for (int k = 0; k < 2; k++) { dfree(d.frame_async[k]); d.frame_async_bytes[k] = 0; }
   dfree(d.aux_prim); dfree(d.aux_mat); dfree(d.aux_t); d.aux_px = 0;
 }
 
@@ -323,6 +330,7 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
   d.prof_used[0] = d.prof_used[1] = d.prof_used[2] = 0;
   for (int32_t row0 = 0; row0 < local_rows; row0 += rows_per_chunk) {
     LaneState& L = d.lane[d.next_lane];
+    d.last_lane = d.next_lane;
     if (ctx->n_lanes > 1) d.next_lane ^= 1;
     cudaStream_t stream = L.stream;
     if (ctx->cancel && *ctx->cancel) { device_sync(d); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
@@ -568,6 +576,8 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
 
 void rtb_destroy(rtb_context* ctx) {
   if (!ctx) return;
+  for (auto& e : ctx->ticket_event)
+    if (e) { cudaSetDevice(ctx->devs[0].device); cudaEventDestroy(e); }
   for (void* p : ctx->ipc_opened) {
     cudaSetDevice(ctx->devs[0].device);
     cudaIpcCloseMemHandle(p);
@@ -669,6 +679,64 @@ int rtb_render(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, siz
   CK(ctx, cudaSetDevice(d0.device));
   CK(ctx, cudaGetLastError());
   ctx->stats.d2h_bytes = (int64_t)need;
+  return RTB_OK;
+}
+
+// Pipelined form of rtb_render: enqueues the frame and its readback and returns; up to 8 frames may be in flight.  Successive
+// frames alternate between the two lanes (their tails overlap the next frame's bulk) and between two device frame buffers.
+int rtb_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* ticket) {
+  if (!ctx || !p || !rgba8 || !ticket) return fail(ctx, RTB_E_ARG, "null argument");
+  if (p->band_world > 1) return fail(ctx, RTB_E_ARG, "rtb_render_begin renders whole frames");
+  if (ctx->devs.size() > 1) return fail(ctx, RTB_E_ARG, "rtb_render_begin needs a single-device context (use rtb_render)");
+  if (!ctx->has_scene) return fail(ctx, RTB_E_NOSCENE, "no scene uploaded (rtb_upload_scene)");
+  FrameParams f;
+  std::string why;
+  if (!resolve_frame(ctx->host.d, *p, f, why)) return fail(ctx, RTB_E_ARG, why);
+  const size_t need = (size_t)f.width * f.height * 4;
+  if (bytes < need) return fail(ctx, RTB_E_SIZE, "rgba8 buffer too small for the resolved resolution");
+  DeviceState& d = ctx->devs[0];
+  CK(ctx, cudaSetDevice(d.device));
+  const uint64_t n = ctx->tickets_issued;
+  const int slot = (int)(n % rtb_context::kTickets), buf = (int)(n & 1);
+  if (!ctx->ticket_event[slot]) CK(ctx, cudaEventCreateWithFlags(&ctx->ticket_event[slot], cudaEventDisableTiming));
+  else CK(ctx, cudaEventSynchronize(ctx->ticket_event[slot]));  // the ring is full: wait for the frame issued 8 calls ago
+  if (d.frame_async_bytes[buf] < need) {
+    device_sync(d);
+    dfree(d.frame_async[buf]);
+    d.frame_async_bytes[buf] = 0;
+    CK(ctx, cudaMalloc(&d.frame_async[buf], need));
+    d.frame_async_bytes[buf] = need;
+  }
+  // this frame reuses the device buffer of the frame before the previous one: its readback must have finished
+  if (n >= 2) {
+    cudaEvent_t prev = ctx->ticket_event[(n - 2) % rtb_context::kTickets];
+    for (auto& l : d.lane) CK(ctx, cudaStreamWaitEvent(l.stream, prev, 0));
+  }
+  const int rc = render_frame(ctx, p, d.frame_async[buf], d.frame_async_bytes[buf], /*to_internal_frame=*/false, /*sync=*/false, f);
+  if (rc != RTB_OK) return rc;
+  LaneState& last = d.lane[d.last_lane];
+  LaneState& other = d.lane[d.last_lane ^ 1];
+  if (other.frame_id == ctx->frame_id) CK(ctx, cudaStreamWaitEvent(last.stream, other.ev_done, 0));  // multi-chunk frame: both lanes
+  CK(ctx, cudaMemcpyAsync(rgba8, d.frame_async[buf], need, cudaMemcpyDeviceToHost, last.stream));
+  CK(ctx, cudaEventRecord(ctx->ticket_event[slot], last.stream));
+  CK(ctx, cudaEventRecord(last.ev_done, last.stream));
+  last.used = true;
+  ctx->stats.d2h_bytes = (int64_t)need;
+  *ticket = (int32_t)(n & 0x7fffffff);
+  ctx->tickets_issued++;
+  return RTB_OK;
+}
+
+// Waits until the frame of `ticket` is complete in its host buffer.
+int rtb_render_end(rtb_context* ctx, int32_t ticket) {
+  if (!ctx) return RTB_E_ARG;
+  const uint64_t issued = ctx->tickets_issued;
+  if (ticket < 0 || (uint64_t)ticket >= issued) return fail(ctx, RTB_E_ARG, "unknown ticket");
+  const uint64_t t = (uint64_t)ticket;
+  if (issued - t > (uint64_t)rtb_context::kTickets) return RTB_OK;  // its ring slot was recycled, which waited for it
+  CK(ctx, cudaSetDevice(ctx->devs[0].device));
+  CK(ctx, cudaEventSynchronize(ctx->ticket_event[t % rtb_context::kTickets]));
+  CK(ctx, cudaGetLastError());
   return RTB_OK;
 }
 

@@ -146,6 +146,13 @@ int rtb_clear_target(rtb_context* ctx);
  * a staging copy).  `bytes` is the capacity of rgba8.  out_w/out_h (optional) receive the resolved resolution. */
 int rtb_render(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* out_w, int32_t* out_h);
 
+/* Pipelined RenderAsync for hosts that render a stream of frames (the reference's realtime mode calls its renderer once per
+ * Unity frame, SceneBuilder.cs:521-537): rtb_render_begin enqueues the frame and its readback into `rgba8` (page-locked memory,
+ * see rtb_alloc_pinned, for a truly asynchronous copy) and returns a ticket; rtb_render_end blocks until that frame is in
+ * `rgba8`.  Up to 8 frames may be in flight; `rgba8` must stay valid until its rtb_render_end.  Single-device contexts. */
+int rtb_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* ticket);
+int rtb_render_end(rtb_context* ctx, int32_t ticket);
+
 /* RenderToTexture, RayTracer.cs:82-202 (no readback): renders into device memory `dst_device` (on device_ids[0], or a
  * peer-mapped pointer into another GPU's frame for the fused NVLink gather).  Asynchronous on the context's stream unless
  * `sync` != 0.  Honors band_rank/band_world/out_layout. */

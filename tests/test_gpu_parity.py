@@ -457,3 +457,23 @@ def test_analytic_primitive_mode_matches_oracle(oracle, samples, mode, scene_nam
             assert (prim == ref["prim"]).mean() >= 0.999 and (mat == ref["mat"]).mean() >= 0.999
             assert s.reserved[0] == 0
     rt.close()
+
+
+# ---- pipelined host API ------------------------------------------------------------------------------------------------------------
+def test_render_begin_end_pipeline_matches_blocking(samples, monkeypatch):
+    """Frames in flight (two lanes, two device frame buffers) must land in their own host buffers, bit-identical to rtb_render."""
+    monkeypatch.setenv("RTB_CHUNK_SLOTS", "60000")  # several chunks per frame, alternating lanes
+    obj = samples["test_scene_2"][0]
+    rt = rt_mod.RayTracer()
+    settings = [params(320, 200, 4, has_fov=1, fov_deg=20.0 + 3.0 * k) for k in range(12)]
+    want = [rt.RenderAsync(obj, p).pixels for p in settings]
+    outs = [np.zeros((200, 320, 4), np.uint8) for _ in settings]
+    tickets = [rt.RenderBegin(obj, p, o) for p, o in zip(settings, outs)]  # 12 > 8: the ticket ring recycles
+    for t in tickets:
+        rt.RenderEnd(t)
+    for k in range(len(settings)):
+        assert (outs[k] == want[k]).all(), k
+    assert len({w.tobytes() for w in want}) > 6  # the frames really differ
+    with pytest.raises(rt_mod.RtbError):
+        rt.RenderEnd(10 ** 6)
+    rt.close()
