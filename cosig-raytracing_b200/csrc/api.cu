@@ -273,27 +273,36 @@ int upload_on_device(rtb_context* ctx, DeviceState& d, const rtb_scene_desc& des
     CK(ctx, cudaEventRecord(d.ev_end, d.stream));
     CK(ctx, cudaStreamSynchronize(d.stream));  // bvh vectors go out of scope
   } else {
-    s.n_nodes = n_out > 1 ? n_out - 1 : 1;
-    s.node_floats = 16;
-    CK(ctx, cudaMalloc(&s.nodes, (size_t)s.n_nodes * 4 * sizeof(float4)));
-    CK(ctx, cudaMemsetAsync(s.nodes, 0, (size_t)s.n_nodes * 4 * sizeof(float4), d.stream));
+    const int32_t max_nodes = n_out > 1 ? n_out - 1 : 1;
+    s.node_floats = 4 * lbvh_node_f4;
+    float4* big = nullptr;  // worst-case sized; the records actually written are copied into an exact allocation below
+    CK(ctx, cudaMalloc(&big, (size_t)max_nodes * lbvh_node_f4 * sizeof(float4)));
     LbvhBuffers b;
-    b.nodes = s.nodes;
+    b.nodes = big;
     b.perm = s.perm;
     b.workspace_bytes = lbvh_workspace_bytes(n_out);
     void* ws = nullptr;
     int32_t* root_dev = nullptr;
-    CK(ctx, cudaMalloc(&ws, b.workspace_bytes));
-    if (cudaMalloc(&root_dev, sizeof(int32_t)) != cudaSuccess) { cudaFree(ws); return fail(ctx, RTB_E_CUDA, "cudaMalloc(root) failed"); }
+    int32_t root_host[2] = {0, 0};
+    if (cudaMalloc(&ws, b.workspace_bytes) != cudaSuccess) { cudaFree(big); return fail(ctx, RTB_E_CUDA, "cudaMalloc(LBVH workspace) failed"); }
+    if (cudaMalloc(&root_dev, 2 * sizeof(int32_t)) != cudaSuccess) { cudaFree(ws); cudaFree(big); return fail(ctx, RTB_E_CUDA, "cudaMalloc(root) failed"); }
     b.workspace = ws;
     b.root_out = root_dev;
     cudaError_t e = lbvh_build(s.raw, n_out, b, d.stream);
     if (e == cudaSuccess) { launch_pack(s.raw, s.nrm, s.perm, n_out, s.isect, s.shade, d.stream); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(root_host, root_dev, sizeof root_host, cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    if (e == cudaSuccess) {
+      s.root = root_host[0];
+      s.n_nodes = std::max(1, std::min(root_host[1], max_nodes));
+      e = cudaMalloc(&s.nodes, (size_t)s.n_nodes * lbvh_node_f4 * sizeof(float4));
+      if (e == cudaSuccess) e = cudaMemcpyAsync(s.nodes, big, (size_t)s.n_nodes * lbvh_node_f4 * sizeof(float4), cudaMemcpyDeviceToDevice, d.stream);
+    }
     if (e == cudaSuccess) e = cudaEventRecord(d.ev_end, d.stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&s.root, root_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
     cudaFree(ws);
     cudaFree(root_dev);
+    cudaFree(big);
     if (e != cudaSuccess) return fail(ctx, RTB_E_CUDA, std::string("LBVH build failed: ") + cudaGetErrorString(e));
   }
   CK(ctx, cudaEventElapsedTime(&ms_build, d.ev_begin, d.ev_end));
@@ -500,7 +509,8 @@ int rtb_api_version(void) { return RTB_API_VERSION; }
 
 void rtb_abi_sizes(int32_t* out, int32_t n) {
   const int32_t v[] = {(int32_t)sizeof(rtb_xform_elem), (int32_t)sizeof(rtb_material), (int32_t)sizeof(rtb_triangle), (int32_t)sizeof(rtb_mesh),
-                       (int32_t)sizeof(rtb_prim), (int32_t)sizeof(rtb_scene_desc), (int32_t)sizeof(rtb_render_params), (int32_t)sizeof(rtb_stats)};
+                       (int32_t)sizeof(rtb_prim), (int32_t)sizeof(rtb_scene_desc), (int32_t)sizeof(rtb_render_params), (int32_t)sizeof(rtb_stats),
+                       (int32_t)(4 * lbvh_node_f4)};  // [8]: 32-bit words per LBVH node record (rtb_get_bvh)
   for (int32_t i = 0; i < n && i < (int32_t)(sizeof v / sizeof v[0]); i++) out[i] = v[i];
 }
 

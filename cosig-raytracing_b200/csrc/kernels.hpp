@@ -19,13 +19,14 @@ void launch_pack(const float4* raw, const float4* nrm, const int32_t* perm, int3
 
 // ---- lbvh.cu (K2: Morton-code LBVH built on the GPU) -------------------------------------------------------------------
 struct LbvhBuffers {            // all device memory, sized by lbvh_workspace_bytes / allocated by the caller
-  float4* nodes;                // 4 * max(1, n-1)
+  float4* nodes;                // (4 or 8, see lbvh_node_f4) * max(1, n-1): worst case; root_out[1] tells how many records were written
   int32_t* perm;                // n
   void* workspace;              // lbvh_workspace_bytes(n)
   size_t workspace_bytes;
-  int32_t* root_out;            // 1 int on the device: root reference
+  int32_t* root_out;            // 2 ints on the device: root reference, number of node records
 };
 size_t lbvh_workspace_bytes(int32_t n);
+constexpr int lbvh_node_f4 = RTB_LBVH_WIDTH == 4 ? 8 : 4;  // float4 per node record
 // Returns cudaSuccess or the failing call's error.  Asynchronous on `st`.
 cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaStream_t st);
 

@@ -8,11 +8,13 @@
 //   cub radix sort      keys + values
 //   k_hierarchy         Karras 2012 binary radix tree over the sorted keys (ties broken by index), parent links, ranges
 //   k_refit             bottom-up AABBs: each leaf thread climbs, the second arrival at a node merges its children
-//   k_emit              traversal nodes: every tree node whose range holds <= RTB_LEAF_MAX triangles collapses into a
-//                       leaf (its triangles are contiguous in sorted order), every larger node becomes a 64-byte record
-//                       carrying BOTH children's boxes, so one fetch decides both descents
+//   k_emit / k_emit4    traversal records: every tree node whose range holds <= RTB_LEAF_MAX triangles collapses into a leaf
+//                       (its triangles are contiguous in sorted order).  RTB_LBVH_WIDTH 2: every larger node becomes a
+//                       64-byte record carrying BOTH children's boxes (default); RTB_LBVH_WIDTH 4: every larger node of
+//                       even depth becomes a 128-byte record carrying its (up to) four grandchildren's boxes, compacted
 // The sorted value array is the leaf order (perm) used by launch_pack.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "kernels.hpp"
 
@@ -35,6 +37,7 @@ struct Workspace {
   int32_t* parent;           // 2n-1: parents of internal nodes [0,n-1) then of leaves [n-1, 2n-1)
   int32_t* flag;             // n-1
   float4* box;               // 2*(2n-1): min,max of internal nodes then leaves
+  int32_t* idx4;             // n-1: compact index of each emitted 4-wide node (exclusive scan of the emit flags)
   void* cub_temp;
   size_t cub_bytes;
 };
@@ -42,10 +45,11 @@ struct Workspace {
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t cub_temp_bytes(int32_t n) {
-  size_t bytes = 0;
+  size_t bytes = 0, scan = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const int32_t*)nullptr,
                                   (int32_t*)nullptr, n, 0, 63);
-  return bytes;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan, (const int32_t*)nullptr, (int32_t*)nullptr, n);
+  return bytes > scan ? bytes : scan;
 }
 
 Workspace carve(void* base, int32_t n) {
@@ -62,6 +66,7 @@ Workspace carve(void* base, int32_t n) {
   w.parent = (int32_t*)take(na * 4);
   w.flag = (int32_t*)take(ni * 4);
   w.box = (float4*)take(na * 2 * sizeof(float4));
+  w.idx4 = (int32_t*)take(ni * 4);
   w.cub_bytes = cub_temp_bytes(n);
   w.cub_temp = take(w.cub_bytes);
   return w;
@@ -202,13 +207,14 @@ __global__ void __launch_bounds__(kBlock) k_refit(const float4* __restrict__ raw
 __device__ __forceinline__ float pad_lo(float v, float radius) { return v - 1e-6f * (fabsf(v) + radius); }
 __device__ __forceinline__ float pad_hi(float v, float radius) { return v + 1e-6f * (fabsf(v) + radius); }
 
+#if RTB_LBVH_WIDTH != 4
 __global__ void __launch_bounds__(kBlock) k_emit(int32_t n, const int2* __restrict__ child, const int2* __restrict__ range,
                                                  const float4* __restrict__ box, const unsigned* __restrict__ bounds, float4* __restrict__ nodes,
                                                  int32_t* __restrict__ root_out) {
   const int32_t n_int = n - 1;
   float radius = 0.0f;
   for (int a = 0; a < 6; a++) radius = fmaxf(radius, fabsf(o2f(bounds[a])));
-  if (blockIdx.x == 0 && threadIdx.x == 0) *root_out = (n <= RTB_LEAF_MAX) ? lbvh_leaf_ref(0, n) : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { root_out[0] = (n <= RTB_LEAF_MAX) ? lbvh_leaf_ref(0, n) : 0; root_out[1] = n_int > 0 ? n_int : 1; }
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_int; i += gridDim.x * blockDim.x) {
     const int2 rg = range[i];
     if (rg.y - rg.x + 1 <= RTB_LEAF_MAX) continue;  // inside a collapsed leaf: never referenced
@@ -233,6 +239,71 @@ __global__ void __launch_bounds__(kBlock) k_emit(int32_t n, const int2* __restri
   }
 }
 
+#else
+// ---- 4-wide records (RTB_LBVH_WIDTH == 4): the binary tree collapsed by two levels -----------------------------------------
+// A record is emitted for every internal node of even depth whose range holds > RTB_LEAF_MAX triangles; its slots are its
+// grandchildren (or a child, where that child is already a leaf).  Records are compacted with an exclusive scan of the flags.
+// Layout (8 x float4 = 128 B = one cache line): min.x[4] min.y[4] min.z[4] max.x[4] max.y[4] max.z[4] ref[4] (unused);
+// unused slots carry ref = RTB_REF_DONE and a copy of slot 0's box.
+__device__ __forceinline__ bool is_big(const int2* __restrict__ range, int32_t i) { const int2 r = range[i]; return r.y - r.x + 1 > RTB_LEAF_MAX; }
+
+__global__ void __launch_bounds__(kBlock) k_mark4(int32_t n, const int2* __restrict__ range, const int32_t* __restrict__ parent, int32_t* __restrict__ flag4) {
+  const int32_t n_int = n - 1;
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_int; i += gridDim.x * blockDim.x) {
+    int depth = 0;
+    for (int32_t p = parent[i]; p >= 0; p = parent[p]) depth++;
+    flag4[i] = (is_big(range, i) && (depth & 1) == 0) ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_emit4(int32_t n, const int2* __restrict__ child, const int2* __restrict__ range, const float4* __restrict__ box,
+                                                  const unsigned* __restrict__ bounds, const int32_t* __restrict__ flag4, const int32_t* __restrict__ idx4,
+                                                  float4* __restrict__ nodes, int32_t* __restrict__ root_out) {
+  const int32_t n_int = n - 1;
+  float radius = 0.0f;
+  for (int a = 0; a < 6; a++) radius = fmaxf(radius, fabsf(o2f(bounds[a])));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    root_out[0] = (n <= RTB_LEAF_MAX) ? lbvh_leaf_ref(0, n) : 0;
+    root_out[1] = n_int > 0 ? idx4[n_int - 1] + flag4[n_int - 1] : 0;
+  }
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_int; i += gridDim.x * blockDim.x) {
+    if (!flag4[i]) continue;
+    int ns = 0;
+    int32_t sref[4];
+    size_t sbox[4];
+    auto add = [&](int32_t c) {  // c: Karras child reference (>= 0 internal, < 0 leaf)
+      if (c < 0) { sref[ns] = lbvh_leaf_ref(~c, 1); sbox[ns] = (size_t)(n_int + ~c); }
+      else if (!is_big(range, c)) { const int2 cr = range[c]; sref[ns] = lbvh_leaf_ref(cr.x, cr.y - cr.x + 1); sbox[ns] = (size_t)c; }
+      else { sref[ns] = idx4[c]; sbox[ns] = (size_t)c; }  // even depth, big: a record of its own
+      ns++;
+    };
+    const int2 ch = child[i];
+    const int32_t cc[2] = {ch.x, ch.y};
+    for (int k = 0; k < 2; k++) {
+      if (cc[k] >= 0 && is_big(range, cc[k])) { const int2 g = child[cc[k]]; add(g.x); add(g.y); }
+      else add(cc[k]);
+    }
+    float mn[3][4], mx[3][4];
+    int32_t refs[4];
+    for (int k = 0; k < 4; k++) {
+      const int src = k < ns ? k : 0;
+      const float4 bmn = box[2 * sbox[src]], bmx = box[2 * sbox[src] + 1];
+      mn[0][k] = pad_lo(bmn.x, radius); mn[1][k] = pad_lo(bmn.y, radius); mn[2][k] = pad_lo(bmn.z, radius);
+      mx[0][k] = pad_hi(bmx.x, radius); mx[1][k] = pad_hi(bmx.y, radius); mx[2][k] = pad_hi(bmx.z, radius);
+      refs[k] = k < ns ? sref[k] : RTB_REF_DONE;
+    }
+    float4* out = nodes + 8 * (size_t)idx4[i];
+    for (int a = 0; a < 3; a++) {
+      out[a] = make_float4(mn[a][0], mn[a][1], mn[a][2], mn[a][3]);
+      out[3 + a] = make_float4(mx[a][0], mx[a][1], mx[a][2], mx[a][3]);
+    }
+    out[6] = make_float4(__int_as_float(refs[0]), __int_as_float(refs[1]), __int_as_float(refs[2]), __int_as_float(refs[3]));
+    out[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+}
+
+#endif
+
 inline int grid_for(int64_t n) {
   const int64_t g = (n + kBlock - 1) / kBlock;
   return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -244,7 +315,7 @@ size_t lbvh_workspace_bytes(int32_t n) {
   if (n <= 0) return 256;
   const size_t ni = (size_t)(n > 1 ? n - 1 : 1), nt = (size_t)n, na = 2 * nt;
   return align_up(24) + 2 * align_up(nt * 8) + align_up(nt * 4) + 2 * align_up(ni * 8) + align_up(na * 4) + align_up(ni * 4) +
-         align_up(na * 2 * sizeof(float4)) + align_up(cub_temp_bytes(n)) + 256;
+         align_up(na * 2 * sizeof(float4)) + align_up(ni * 4) + align_up(cub_temp_bytes(n)) + 256;
 }
 
 cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaStream_t st) {
@@ -263,7 +334,17 @@ cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaS
     k_hierarchy<<<grid_for(n - 1), kBlock, 0, st>>>(w.keys_sorted, n, w.child, w.range, w.parent);
   }
   k_refit<<<grid_for(n), kBlock, 0, st>>>(raw, b.perm, n, w.child, w.parent, w.flag, w.box);
+#if RTB_LBVH_WIDTH == 4
+  if (n > 1) {
+    k_mark4<<<grid_for(n - 1), kBlock, 0, st>>>(n, w.range, w.parent, w.flag);
+    temp = w.cub_bytes;
+    e = cub::DeviceScan::ExclusiveSum(w.cub_temp, temp, (const int32_t*)w.flag, w.idx4, n - 1, st);
+    if (e != cudaSuccess) return e;
+  }
+  k_emit4<<<grid_for(n > 1 ? n - 1 : 1), kBlock, 0, st>>>(n, w.child, w.range, w.box, w.bounds, w.flag, w.idx4, b.nodes, b.root_out);
+#else
   k_emit<<<grid_for(n > 1 ? n - 1 : 1), kBlock, 0, st>>>(n, w.child, w.range, w.box, w.bounds, b.nodes, b.root_out);
+#endif
   return cudaGetLastError();
 }
 

@@ -21,7 +21,10 @@ namespace rtb {
 #define RTB_LEAF_MAX 4     /* LBVH leaf size (<= 8) */
 #endif
 #define RTB_REF_DONE ((int32_t)0x80000000) /* LBVH traversal: "no more work" reference (never a valid leaf: n < 2^28) */
-#define RTB_REF_LEAF ((int32_t)0x80000001) /* LBVH traversal: the lane is inside a leaf (triangle cursor in registers) */
+#define RTB_REF_MISS ((int32_t)0x80000001) /* lbvh_visit: no child of the node was hit (the caller pops its stack) */
+#ifndef RTB_LBVH_WIDTH
+#define RTB_LBVH_WIDTH 2   /* children per LBVH node record: 2 (64-byte records) or 4 (128-byte records, binary tree collapsed by two levels) */
+#endif
 
 struct f3 { float x, y, z; };
 __host__ __device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -100,7 +103,7 @@ struct SceneView {
   const float4* __restrict__ tri_isect;  // 3 per triangle, leaf order: (v0, prim_id) (e1, material) (e2, 0); analytic primitive:
                                          //   (table index bits, -, -, prim_id) (-, -, -, material) (-, -, -, kind: 1 sphere, 2 box)
   const float4* __restrict__ tri_shade;  // 3 per triangle, leaf order: n0 n1 n2
-  const float4* __restrict__ nodes;      // reference: 2 per node (min,leftOrFirst)(max,count); LBVH: 4 per node (see lbvh.cu)
+  const float4* __restrict__ nodes;      // reference: 2 per node (min,leftOrFirst)(max,count); LBVH: 4 or 8 per node (see lbvh.cu)
                                          //   LBVH boxes are padded outward (lbvh.cu: k_emit) so the FMA slab test stays conservative
   const float4* __restrict__ materials;  // 2 per material: (r,g,b,ka) (kd,ks,kr,ior)
   const float4* __restrict__ prims;      // analytic mode: 6 per primitive: objectToWorld rows 0..2, worldToObject rows 0..2

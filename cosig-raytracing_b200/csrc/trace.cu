@@ -149,11 +149,6 @@ __device__ __forceinline__ void lane_finish(Lane& L, const QueueView& q, int32_t
   L.done = false;
 }
 
-// Scene data of k_traverse comes either from global memory through the read-only path, or — small scenes — from the
-// copy the block staged in shared memory (SMEM).
-template <bool SMEM>
-__device__ __forceinline__ float4 ld4(const float4* p) { return SMEM ? *p : __ldg(p); }
-
 // Stages the traversal arrays (nodes, then tri_isect) into dynamic shared memory; returns the two base pointers.
 __device__ __forceinline__ void stage_scene(const SceneView& s, int node_f4, float4* sm, const float4*& nodes, const float4*& tris) {
   const int n_node = s.n_nodes * node_f4, n_tri = s.n_tris * 3;
@@ -189,7 +184,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kBlock, SMEM ? 1 : 4) k_tr
   extern __shared__ float4 sm_scene[];
   const float4* nodes = s.nodes;
   const float4* tri_isect = s.tri_isect;
-  if (SMEM) stage_scene(s, 4, sm_scene, nodes, tri_isect);
+  if (SMEM) stage_scene(s, lbvh_node_f4, sm_scene, nodes, tri_isect);
   const int lane = threadIdx.x & 31;
   const int32_t n_closest = RTB_CNT_RAY(q, depth);
   const int32_t n_shadow = depth == 0 ? 0 : RTB_CNT_SHADOW(q, depth - 1);
@@ -233,19 +228,9 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kBlock, SMEM ? 1 : 4) k_tr
     // ---- inner nodes: descend until this lane holds a leaf (or runs out of work) ----
     while (cur >= 0) {
       n_nodes++;
-      const float4 n0 = ld4<SMEM>(&nodes[4 * cur]), n1 = ld4<SMEM>(&nodes[4 * cur + 1]);
-      const float4 n2 = ld4<SMEM>(&nodes[4 * cur + 2]), n3 = ld4<SMEM>(&nodes[4 * cur + 3]);
-      float dl, dr;
-      const bool hl = slab_hit_fma(L.inv, ood, mk3(n0), mk3(n1), L.t, dl);
-      const bool hr = slab_hit_fma(L.inv, ood, mk3(n2), mk3(n3), L.t, dr);
-      const int32_t lref = __float_as_int(n0.w), rref = __float_as_int(n1.w);
-      if (hl && hr) {
-        const bool left_first = !(dr < dl);
-        if (sp < RTB_STACK_LBVH) { stack_ref[sp] = left_first ? rref : lref; stack_dst[sp] = left_first ? dr : dl; sp++; }
-        else overflow++;
-        cur = left_first ? lref : rref;
-      } else if (hl) cur = lref;
-      else if (hr) cur = rref;
+      // closest: a box is skipped when entry >= best t (compute:246); shadow rays carry nextafter(distToLight) as bound
+      const int32_t next = lbvh_visit<SMEM>(nodes, cur, L.inv, ood, L.t, stack_ref, stack_dst, sp, overflow);
+      if (next != RTB_REF_MISS) cur = next;
       else {
         cur = RTB_REF_DONE;
         while (sp > 0) {
@@ -383,10 +368,17 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const FrameParams f, const Sc
   if (BVH == RTB_BVH_REFERENCE) {
     if (s.n_nodes > 0) { rmn = mk3(__ldg(&s.nodes[0])); rmx = mk3(__ldg(&s.nodes[1])); have_box = true; }
   } else if (s.n_tris > 0 && s.root >= 0) {
+#if RTB_LBVH_WIDTH == 4
+    const float4* rec = s.nodes + 8 * (size_t)s.root;  // unused slots repeat slot 0's box, so the union may include them
+    const float4 a0 = __ldg(rec), a1 = __ldg(rec + 1), a2 = __ldg(rec + 2), b0 = __ldg(rec + 3), b1 = __ldg(rec + 4), b2 = __ldg(rec + 5);
+    rmn = mk3(fminf(fminf(a0.x, a0.y), fminf(a0.z, a0.w)), fminf(fminf(a1.x, a1.y), fminf(a1.z, a1.w)), fminf(fminf(a2.x, a2.y), fminf(a2.z, a2.w)));
+    rmx = mk3(fmaxf(fmaxf(b0.x, b0.y), fmaxf(b0.z, b0.w)), fmaxf(fmaxf(b1.x, b1.y), fmaxf(b1.z, b1.w)), fmaxf(fmaxf(b2.x, b2.y), fmaxf(b2.z, b2.w)));
+#else
     const float4 n0 = __ldg(&s.nodes[4 * s.root]), n1 = __ldg(&s.nodes[4 * s.root + 1]);
     const float4 n2 = __ldg(&s.nodes[4 * s.root + 2]), n3 = __ldg(&s.nodes[4 * s.root + 3]);
     rmn = mk3(fminf(n0.x, n2.x), fminf(n0.y, n2.y), fminf(n0.z, n2.z));
     rmx = mk3(fmaxf(n1.x, n3.x), fmaxf(n1.y, n3.y), fmaxf(n1.z, n3.z));
+#endif
     have_box = true;
   }
   const bool empty = (BVH == RTB_BVH_REFERENCE) ? s.n_nodes == 0 : s.n_tris == 0;
@@ -733,7 +725,7 @@ void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const Queu
 }
 
 size_t traverse_smem_bytes(int bvh, const SceneView& s) {
-  return ((size_t)s.n_nodes * (bvh == RTB_BVH_REFERENCE ? 2 : 4) + (size_t)s.n_tris * 3) * sizeof(float4);
+  return ((size_t)s.n_nodes * (bvh == RTB_BVH_REFERENCE ? 2 : lbvh_node_f4) + (size_t)s.n_tris * 3) * sizeof(float4);
 }
 
 cudaError_t traverse_enable_smem(int bvh, size_t bytes) {

@@ -288,6 +288,68 @@ __device__ __forceinline__ bool traverse_reference(const SceneView& s, const Ray
   return best.tri >= 0;
 }
 
+// Scene data of the traversal kernels comes either from global memory through the read-only path, or — small scenes —
+// from the copy the block staged in shared memory (SMEM).
+template <bool SMEM>
+__device__ __forceinline__ float4 ld4(const float4* p) { return SMEM ? *p : __ldg(p); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One LBVH node visit, shared by the persistent kernel and the per-thread traversals (so both order children the same
+// way and pick the same winner among equal t): tests the record's children against the ray, returns the nearest child
+// that can still matter and pushes the others, farthest first, with their entry distances.  RTB_REF_MISS: none was hit.
+// ---------------------------------------------------------------------------------------------------------------------
+#if RTB_LBVH_WIDTH == 4
+template <bool SMEM>
+__device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, f3 inv, f3 ood, float bound, int32_t* stack_ref, float* stack_dst,
+                                              int& sp, unsigned& overflow) {
+  const float4* rec = nodes + 8 * (size_t)cur;
+  const float4 mnx = ld4<SMEM>(rec), mny = ld4<SMEM>(rec + 1), mnz = ld4<SMEM>(rec + 2);
+  const float4 mxx = ld4<SMEM>(rec + 3), mxy = ld4<SMEM>(rec + 4), mxz = ld4<SMEM>(rec + 5);
+  const float4 rf = ld4<SMEM>(rec + 6);
+  float e0, e1, e2, e3;
+  const bool h0 = slab_hit_fma(inv, ood, mk3(mnx.x, mny.x, mnz.x), mk3(mxx.x, mxy.x, mxz.x), bound, e0);
+  const bool h1 = slab_hit_fma(inv, ood, mk3(mnx.y, mny.y, mnz.y), mk3(mxx.y, mxy.y, mxz.y), bound, e1);
+  const bool h2 = slab_hit_fma(inv, ood, mk3(mnx.z, mny.z, mnz.z), mk3(mxx.z, mxy.z, mxz.z), bound, e2);
+  const bool h3 = slab_hit_fma(inv, ood, mk3(mnx.w, mny.w, mnz.w), mk3(mxx.w, mxy.w, mxz.w), bound, e3);
+  int32_t r0 = __float_as_int(rf.x), r1 = __float_as_int(rf.y), r2 = __float_as_int(rf.z), r3 = __float_as_int(rf.w);
+  // misses (and unused slots) sort to the end
+  if (!h0) e0 = INFINITY;
+  if (!h1 || r1 == RTB_REF_DONE) e1 = INFINITY;
+  if (!h2 || r2 == RTB_REF_DONE) e2 = INFINITY;
+  if (!h3 || r3 == RTB_REF_DONE) e3 = INFINITY;
+  const int n_hit = (e0 < INFINITY) + (e1 < INFINITY) + (e2 < INFINITY) + (e3 < INFINITY);
+  if (n_hit == 0) return RTB_REF_MISS;
+#define RTB_CE(ea, ra, eb, rb) { if (eb < ea) { const float te = ea; ea = eb; eb = te; const int32_t tr = ra; ra = rb; rb = tr; } }
+  RTB_CE(e0, r0, e1, r1) RTB_CE(e2, r2, e3, r3) RTB_CE(e0, r0, e2, r2) RTB_CE(e1, r1, e3, r3) RTB_CE(e1, r1, e2, r2)
+#undef RTB_CE
+  if (sp + n_hit - 1 > RTB_STACK_LBVH) { overflow++; return r0; }
+  if (n_hit > 3) { stack_ref[sp] = r3; stack_dst[sp] = e3; sp++; }
+  if (n_hit > 2) { stack_ref[sp] = r2; stack_dst[sp] = e2; sp++; }
+  if (n_hit > 1) { stack_ref[sp] = r1; stack_dst[sp] = e1; sp++; }
+  return r0;
+}
+#else
+template <bool SMEM>
+__device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, f3 inv, f3 ood, float bound, int32_t* stack_ref, float* stack_dst,
+                                              int& sp, unsigned& overflow) {
+  const float4 n0 = ld4<SMEM>(&nodes[4 * cur]), n1 = ld4<SMEM>(&nodes[4 * cur + 1]);
+  const float4 n2 = ld4<SMEM>(&nodes[4 * cur + 2]), n3 = ld4<SMEM>(&nodes[4 * cur + 3]);
+  float dl, dr;
+  const bool hl = slab_hit_fma(inv, ood, mk3(n0), mk3(n1), bound, dl);
+  const bool hr = slab_hit_fma(inv, ood, mk3(n2), mk3(n3), bound, dr);
+  const int32_t lref = __float_as_int(n0.w), rref = __float_as_int(n1.w);
+  if (hl && hr) {
+    const bool left_first = !(dr < dl);
+    if (sp < RTB_STACK_LBVH) { stack_ref[sp] = left_first ? rref : lref; stack_dst[sp] = left_first ? dr : dl; sp++; }
+    else overflow++;
+    return left_first ? lref : rref;
+  }
+  if (hl) return lref;
+  if (hr) return rref;
+  return RTB_REF_MISS;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------------
 // LBVH traversal: 64-byte nodes holding both children's boxes, near child first, deferred child kept with its entry
 // distance so it can be dropped without a fetch once a closer hit is known.  Triangle arithmetic is the same as above,
@@ -307,25 +369,10 @@ __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, 
   const f3 ood = r.o * inv;
   for (;;) {
     if (cur >= 0) {
-      const float4 n0 = __ldg(&s.nodes[4 * cur]), n1 = __ldg(&s.nodes[4 * cur + 1]);
-      const float4 n2 = __ldg(&s.nodes[4 * cur + 2]), n3 = __ldg(&s.nodes[4 * cur + 3]);
-      // same box test, bound and child order as k_traverse_lbvh, so both forms pick the same winner among equal t
+      // same box test, bound and child order as k_traverse_lbvh
       const float bound = ANY ? nextafterf(t_limit, INFINITY) : best.t;
-      float dl, dr;
-      const bool hl = slab_hit_fma(inv, ood, mk3(n0), mk3(n1), bound, dl);
-      const bool hr = slab_hit_fma(inv, ood, mk3(n2), mk3(n3), bound, dr);
-      const int32_t lref = __float_as_int(n0.w), rref = __float_as_int(n1.w);
-      if (hl && hr) {
-        const bool left_first = !(dr < dl);
-        const int32_t far_ref = left_first ? rref : lref;
-        const float far_dst = left_first ? dr : dl;
-        cur = left_first ? lref : rref;
-        if (sp < RTB_STACK_LBVH) { stack_ref[sp] = far_ref; stack_dst[sp] = far_dst; sp++; }
-        else overflow++;
-        continue;
-      }
-      if (hl) { cur = lref; continue; }
-      if (hr) { cur = rref; continue; }
+      const int32_t next = lbvh_visit<false>(s.nodes, cur, inv, ood, bound, stack_ref, stack_dst, sp, overflow);
+      if (next != RTB_REF_MISS) { cur = next; continue; }
     } else {
       const int32_t code = ~cur;
       const int32_t first = code >> 3, count = (code & 7) + 1;

@@ -206,7 +206,8 @@ int rtb_get_bvh(rtb_context* ctx, void* nodes, int64_t nodes_capacity_bytes, int
  *   _CameraDistance, tan(fov/2), _OrthoSize, _LightPosition xyz, _BackgroundColor rgb; wh = width, height.
  * rtb_build_reference_bvh: BVHBuilder.Build (BVHBuilder.cs:76-95) on caller-provided triangles, 12 floats each
  *   (v0.xyz, c.x, v1.xyz, c.y, v2.xyz, c.z); nodes8 = 8 words per node, perm = leaf order -> input index.
- * rtb_abi_sizes: sizeof of the 8 public structs in declaration order, for binding self-checks. */
+ * rtb_abi_sizes: sizeof of the 8 public structs in declaration order, for binding self-checks; entry [8] = 32-bit words per
+ *   LBVH node record as returned by rtb_get_bvh. */
 int rtb_resolve_frame(const rtb_scene_desc* scene, const rtb_render_params* p, float* out25, int32_t* wh);
 int rtb_build_reference_bvh(const float* raw12, int32_t n, float* nodes8, int64_t nodes_capacity, int64_t* n_nodes, int32_t* perm);
 void rtb_abi_sizes(int32_t* out, int32_t n);
