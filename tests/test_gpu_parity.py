@@ -477,3 +477,19 @@ def test_render_begin_end_pipeline_matches_blocking(samples, monkeypatch):
     with pytest.raises(rt_mod.RtbError):
         rt.RenderEnd(10 ** 6)
     rt.close()
+
+
+def test_rotation_sweep_matches_frame_by_frame_renders(samples, oracle):
+    """GifGenerator.GenerateRotationFrames (GifGenerator.cs:40-72): 36 frames, CameraRotationOverride.z = 0, 10, ..., 350."""
+    gif_mod = importlib.import_module("cosig-raytracing_b200.gif_generator")
+    obj, osc, _ = samples["test_scene_1"]
+    rt = rt_mod.RayTracer()
+    base = scene_mod.RenderSettings(ResolutionOverride=(160, 120), MaxDepth=3, CameraPositionOverride=(0.0, 0.0, 0.0), CameraRotationOverride=(-60.0, 0.0, 0.0))
+    seen = []
+    frames = gif_mod.GifGenerator(rt, obj).GenerateRotationFrames(base, progress=lambda v, msg: seen.append(msg))
+    assert len(frames) == 36 and len(seen) == 36 and seen[-1].startswith("Rendering frame 36/36")
+    for k in (0, 7, 35):
+        st = scene_mod.RenderSettings(ResolutionOverride=(160, 120), MaxDepth=3, CameraPositionOverride=(0.0, 0.0, 0.0), CameraRotationOverride=(-60.0, 0.0, 10.0 * k))
+        assert (frames[k].pixels == osc.render(st.to_params())["rgba8"]).all(), k
+    assert len({f.pixels.tobytes() for f in frames}) >= 30
+    rt.close()

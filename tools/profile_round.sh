@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: scratch/profile_round.sh <tag>   — bench lines + ncu launch list + ncu full capture of k_traverse for C4 (1 GPU)
+# usage: tools/profile_round.sh <tag>   — bench lines + ncu launch list + ncu full capture of k_traverse for C4 (1 GPU)
 TAG=$1
 python bench.py --steps 100 --warmup 3 > gpurun_out/bench_c4_$TAG.json 2> gpurun_out/bench_c4_$TAG.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_c4_$TAG.json 2>/dev/null
