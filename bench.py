@@ -355,7 +355,7 @@ def main():
         roof = {"bound": "hbm", "kernel": "k_traverse (every BVH query of the frame: closest-hit and shadow rays), all depths", "achieved": None,
                 "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src}
         cpu = None
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline:
             ref, rows, c, build_s, sample = oracle_sample(args.workload, analytic=args.prim == "analytic")
             bpr, parts = algorithmic_bytes_per_closest_ray(c)
             closest_rays = float(s0.rays_primary + s0.rays_continuation)
@@ -380,11 +380,15 @@ def main():
                         gpu_nodes_fetched_per_ray=round(s0.reserved[1] / max(1.0, rays_rank), 3), gpu_tris_tested_per_ray=round(s0.reserved[2] / max(1.0, rays_rank), 3),
                         note="algorithmic bytes = rays x (32 n + 36 tau + 76 h), n/tau/h counted by the CPU oracle on the reference-shape BVH "
                              "(SURVEY.md 8d); the LBVH visits fewer nodes than that, so frac can exceed what DRAM counters show")
+            # per-GPU figures at N > 1: rank 0's rays over rank 0's kernel time; the CPU baseline itself is an N = 1 item
             cpu = {"value": c.rays / c.seconds / 1e6, "unit": "Mrays/s", "cores": int(c.threads), "kind": "port", "sample": sample,
-                   "seconds": c.seconds}
+                   "seconds": c.seconds} if world == 1 else None
             # the sampled rows must agree with the GPU frame (same scene, same settings): parity spot-check inside the bench
             d = np.abs(host[rows][..., :3].astype(np.int32) - ref["rgba8"][rows][..., :3].astype(np.int32)).max(axis=-1)
-            cpu["parity_rows_within_1_255"] = float((d <= 1).mean())
+            parity = float((d <= 1).mean())
+            if cpu is not None:
+                cpu["parity_rows_within_1_255"] = parity
+            roof["parity_rows_within_1_255"] = parity
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -1,0 +1,35 @@
+"""Small renders through every kernel variant, for compute-sanitizer (memcheck) — keep it tiny: the tool slows kernels ~50x."""
+import importlib, os, sys
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import numpy as np
+from util import abi, params, scene_mod, synth, tiny_scene
+rt_mod = importlib.import_module("cosig-raytracing_b200.raytracer")
+
+def run(tag, env, mode, prim, obj, p):
+    for k in ("RTB_TAIL_MAX", "RTB_SMEM", "RTB_CHUNK_SLOTS", "RTB_LANES"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    rt = rt_mod.RayTracer(bvh_mode=mode, primitive_mode=prim)
+    a = rt.RenderAsync(obj, p).pixels
+    out = [np.zeros_like(a) for _ in range(3)]
+    ts = [rt.RenderBegin(obj, p, o) for o in out]
+    for t in ts:
+        rt.RenderEnd(t)
+    assert all((o == a).all() for o in out), tag
+    rt.primary_hits(obj, p)
+    st = rt.stats()
+    rt.close()
+    print(tag, "ok", st.rays_primary, st.rays_continuation, st.rays_shadow, flush=True)
+
+s1 = synth.sample_scene("test_scene_1")
+hf = synth.heightfield_scene(40, 20)
+for mode in (abi.RTB_BVH_REFERENCE, abi.RTB_BVH_LBVH):
+    run(f"wavefront mode{mode}", {"RTB_TAIL_MAX": "0", "RTB_SMEM": "0"}, mode, 0, s1, params(96, 64, 4, 2))
+    run(f"tail+smem mode{mode}", {"RTB_TAIL_MAX": "1000000", "RTB_SMEM": "1"}, mode, 0, s1, params(96, 64, 4))
+    run(f"smem wavefront chunks mode{mode}", {"RTB_TAIL_MAX": "0", "RTB_SMEM": "1", "RTB_CHUNK_SLOTS": "2048"}, mode, 0, s1, params(96, 64, 3))
+    run(f"analytic mode{mode}", {"RTB_TAIL_MAX": "2000"}, mode, 1, s1, params(96, 64, 4, soft_shadows=1, light_size=2.0, glossy=1, roughness=0.1))
+    run(f"heightfield mode{mode}", {}, mode, 0, hf, params(128, 72, 6))
+    run(f"tiny mode{mode}", {}, mode, 0, tiny_scene(1), params(33, 17, 2, debug_mode=2))
+empty = scene_mod.ObjectData(); synth._sample_camera_and_light(empty)
+run("empty", {}, abi.RTB_BVH_LBVH, 0, empty, params(40, 24, 3))
+print("sanitize run complete")
