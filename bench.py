@@ -107,7 +107,16 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would otherwise throttle the oracle)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def oracle_sample(workload, threads=0, analytic=False):
+    threads = threads or host_threads()
     """The CPU oracle on every k-th row of the workload's frame.  Returns (counters, seconds, description)."""
     from oracle import oracle_py as O
     scene_mod = importlib.import_module("cosig-raytracing_b200.scene")
@@ -154,7 +163,7 @@ def run_reference(args, rank, world):
     rays = secs = 0.0
     threads = 0
     for i in range(args.warmup + args.steps):
-        c = osc.render(p, rows=(b0 + (i % step if e0 < 0 else 0), e0, step))["counters"]
+        c = osc.render(p, rows=(b0 + (i % step if e0 < 0 else 0), e0, step), threads=host_threads())["counters"]
         if i >= args.warmup:
             rays += c.rays; secs += c.seconds
         threads = c.threads
