@@ -286,20 +286,21 @@ def main():
     host = np.zeros((h, w, 4), np.uint8)
     lib = abi.load()
     import ctypes as C
-    pinned = [lib.rtb_alloc_pinned(frame_bytes) for _ in range(2)]
+    n_flight = max(2, min(4, int(os.environ.get("RTB_LANES", "3"))))  # frames in flight of the pipelined host API = the library's lanes
+    pinned = [lib.rtb_alloc_pinned(frame_bytes) for _ in range(n_flight)]
     host_views = [np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_uint8)), shape=(h, w, 4)) for pp in pinned]
     host_view = host_views[0]
-    e2e_mode = "rtb_render_begin/end, 2 frames in flight, pinned host buffers" if world == 1 else "blocking per frame (barrier across ranks)"
+    e2e_mode = f"rtb_render_begin/end, {n_flight} frames in flight, pinned host buffers" if world == 1 else "blocking per frame (barrier across ranks)"
 
     def run_e2e(n_steps):
         """N = 1: the pipelined host API — every step still copies its uniforms in and its RGBA8 frame out.  N > 1: blocking."""
         if world == 1:
             tickets = []
             for k in range(n_steps):
-                if k >= 2:
-                    rt.RenderEnd(tickets[k - 2])
-                tickets.append(rt.RenderBegin(packed, st.to_params(), host_views[k & 1]))
-            for t in tickets[-2:]:
+                if k >= n_flight:
+                    rt.RenderEnd(tickets[k - n_flight])
+                tickets.append(rt.RenderBegin(packed, st.to_params(), host_views[k % n_flight]))
+            for t in tickets[-n_flight:]:
                 rt.RenderEnd(t)
             return
         for _ in range(n_steps):
@@ -313,7 +314,7 @@ def main():
                 if rank == 0:
                     rt.frame_read(host_view)
 
-    run_e2e(2)
+    run_e2e(n_flight)
     torch.cuda.synchronize(); rt.synchronize(); barrier()
     t0 = time.perf_counter()
     run_e2e(args.steps)

@@ -53,11 +53,12 @@ struct DeviceState {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_done = nullptr;  // scene upload timing / cross-device completion
   cudaEvent_t ev_resolve = nullptr;  // orders the resolve kernels of successive chunks / frames (they may share pixels)
   bool resolve_pending = false;
-  LaneState lane[2];
+  static constexpr int kMaxLanes = 4;
+  LaneState lane[kMaxLanes];
   int next_lane = 0;
   int last_lane = 0;              // lane of the last chunk enqueued (where a frame's readback is ordered)
-  void* frame_async[2] = {nullptr, nullptr};  // frames of rtb_render_begin, alternating, so a readback never races the next frame
-  size_t frame_async_bytes[2] = {0, 0};
+  void* frame_async[kMaxLanes] = {};  // frames of rtb_render_begin, rotating, so a readback never races the following frames
+  size_t frame_async_bytes[kMaxLanes] = {};
   float* sphere_table = nullptr;
   DeviceScene scene;
   void* frame = nullptr;  // RGBA8 frame (device 0) — also the IPC-exported buffer
@@ -83,7 +84,7 @@ struct rtb_context {
   const volatile int32_t* cancel = nullptr;
   bool profiling = false;
   int64_t chunk_slots = 1 << 23;
-  int n_lanes = 2;            // RTB_LANES: 2 = alternate chunks / async frames over two streams, 1 = single stream
+  int n_lanes = 3;            // RTB_LANES (1..4): chunks / async frames rotate over this many streams, each with its own queues
   uint64_t frame_id = 0;
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
   int32_t tail_max = 196608;  // queues smaller than this finish in k_tail (RTB_TAIL_MAX; 0 = pure wavefront)
@@ -136,11 +137,12 @@ void device_sync(DeviceState& d) {
 
 // lane 0's stream (the one the host sees) waits for everything enqueued on lane 1
 cudaError_t join_lanes(DeviceState& d) {
-  if (d.lane[1].used) {
-    cudaError_t e = cudaStreamWaitEvent(d.lane[0].stream, d.lane[1].ev_done, 0);
-    if (e != cudaSuccess) return e;
-    d.lane[1].used = false;
-  }
+  for (int k = 1; k < DeviceState::kMaxLanes; k++)
+    if (d.lane[k].used) {
+      cudaError_t e = cudaStreamWaitEvent(d.lane[0].stream, d.lane[k].ev_done, 0);
+      if (e != cudaSuccess) return e;
+      d.lane[k].used = false;
+    }
   return cudaSuccess;
 }
 
@@ -151,7 +153,7 @@ void free_targets(DeviceState& d) {
     l.q = Queues();
   }
   dfree(d.frame); d.frame_bytes = 0;
-  for (int k = 0; k < 2; k++) { dfree(d.frame_async[k]); d.frame_async_bytes[k] = 0; }
+  for (int k = 0; k < DeviceState::kMaxLanes; k++) { dfree(d.frame_async[k]); d.frame_async_bytes[k] = 0; }
   dfree(d.aux_prim); dfree(d.aux_mat); dfree(d.aux_t); d.aux_px = 0;
 }
 
@@ -340,7 +342,7 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
   for (int32_t row0 = 0; row0 < local_rows; row0 += rows_per_chunk) {
     LaneState& L = d.lane[d.next_lane];
     d.last_lane = d.next_lane;
-    if (ctx->n_lanes > 1) d.next_lane ^= 1;
+    d.next_lane = (d.next_lane + 1) % ctx->n_lanes;
     cudaStream_t stream = L.stream;
     if (ctx->cancel && *ctx->cancel) { device_sync(d); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
     {
@@ -542,7 +544,7 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
     const long long v = std::atoll(env);
     if (v >= 1024) ctx->chunk_slots = v;
   }
-  if (const char* env = std::getenv("RTB_LANES")) ctx->n_lanes = std::atoi(env) >= 2 ? 2 : 1;
+  if (const char* env = std::getenv("RTB_LANES")) ctx->n_lanes = std::min((int)DeviceState::kMaxLanes, std::max(1, std::atoi(env)));
   if (const char* env = std::getenv("RTB_SMEM")) ctx->smem_mode = std::atoi(env);
   if (const char* env = std::getenv("RTB_TAIL_MAX")) ctx->tail_max = (int32_t)std::max(0LL, std::atoll(env));
   ctx->devs.resize(ids.size());
@@ -707,7 +709,8 @@ int rtb_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba
   DeviceState& d = ctx->devs[0];
   CK(ctx, cudaSetDevice(d.device));
   const uint64_t n = ctx->tickets_issued;
-  const int slot = (int)(n % rtb_context::kTickets), buf = (int)(n & 1);
+  const int n_buf = std::max(2, ctx->n_lanes);
+  const int slot = (int)(n % rtb_context::kTickets), buf = (int)(n % (uint64_t)n_buf);
   if (!ctx->ticket_event[slot]) CK(ctx, cudaEventCreateWithFlags(&ctx->ticket_event[slot], cudaEventDisableTiming));
   else CK(ctx, cudaEventSynchronize(ctx->ticket_event[slot]));  // the ring is full: wait for the frame issued 8 calls ago
   if (d.frame_async_bytes[buf] < need) {
@@ -717,16 +720,16 @@ int rtb_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba
     CK(ctx, cudaMalloc(&d.frame_async[buf], need));
     d.frame_async_bytes[buf] = need;
   }
-  // this frame reuses the device buffer of the frame before the previous one: its readback must have finished
-  if (n >= 2) {
-    cudaEvent_t prev = ctx->ticket_event[(n - 2) % rtb_context::kTickets];
+  // this frame reuses the device buffer of the frame issued n_buf calls ago: its readback must have finished
+  if (n >= (uint64_t)n_buf) {
+    cudaEvent_t prev = ctx->ticket_event[(n - (uint64_t)n_buf) % rtb_context::kTickets];
     for (auto& l : d.lane) CK(ctx, cudaStreamWaitEvent(l.stream, prev, 0));
   }
   const int rc = render_frame(ctx, p, d.frame_async[buf], d.frame_async_bytes[buf], /*to_internal_frame=*/false, /*sync=*/false, f);
   if (rc != RTB_OK) return rc;
   LaneState& last = d.lane[d.last_lane];
-  LaneState& other = d.lane[d.last_lane ^ 1];
-  if (other.frame_id == ctx->frame_id) CK(ctx, cudaStreamWaitEvent(last.stream, other.ev_done, 0));  // multi-chunk frame: both lanes
+  for (int k = 0; k < DeviceState::kMaxLanes; k++)  // multi-chunk frame: every lane that carried one of its chunks
+    if (k != d.last_lane && d.lane[k].stream && d.lane[k].frame_id == ctx->frame_id) CK(ctx, cudaStreamWaitEvent(last.stream, d.lane[k].ev_done, 0));
   CK(ctx, cudaMemcpyAsync(rgba8, d.frame_async[buf], need, cudaMemcpyDeviceToHost, last.stream));
   CK(ctx, cudaEventRecord(ctx->ticket_event[slot], last.stream));
   CK(ctx, cudaEventRecord(last.ev_done, last.stream));
