@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--prim", default="tessellated", choices=["tessellated", "analytic"],
                     help="analytic: spheres / boxes are intersected analytically (SURVEY A13) instead of tessellated like the reference")
+    ap.add_argument("--band-rows", type=int, default=32, help="N > 1: rows per band (multiple of 4); band b is rendered by rank b % N")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--out-png", default=None, help="rank 0 writes the last frame here")
     args = ap.parse_args()
@@ -227,9 +228,10 @@ def main():
 
     # ---- where this rank's pixels go -----------------------------------------------------------------------------------
     p = st.to_params()
+    BR = args.band_rows
     local = None
     if world > 1:
-        p.band_rank, p.band_world, p.band_rows = rank, world, 32
+        p.band_rank, p.band_world, p.band_rows = rank, world, BR
     if world > 1 and args.gather == "peer":
         handle = [None]
         if rank == 0:
@@ -240,7 +242,7 @@ def main():
         dst_bytes = frame_bytes
     elif world > 1:
         p.out_layout = abi.RTB_OUT_COMPACT
-        local = torch.empty((max(1, bands.local_row_count(h, rank, world, 32)), w, 4), dtype=torch.uint8, device="cuda")
+        local = torch.empty((max(1, bands.local_row_count(h, rank, world, BR)), w, 4), dtype=torch.uint8, device="cuda")
         dst_ptr, dst_bytes = local.data_ptr(), local.numel()
     else:
         dst_ptr, _ = rt.frame_export(frame_bytes)
@@ -250,7 +252,7 @@ def main():
         rt.RenderToTexture(packed, p, dst_ptr, dst_bytes, sync=sync)
         if world > 1 and args.gather == "nccl":
             rt.synchronize()
-            return bands.gather_bands(local[:bands.local_row_count(h, rank, world, 32)], h, w, rank, world, 32, dst=0)
+            return bands.gather_bands(local[:bands.local_row_count(h, rank, world, BR)], h, w, rank, world, BR, dst=0)
         return None
 
     # ---- scene upload (first frame) --------------------------------------------------------------------------------------
@@ -277,7 +279,11 @@ def main():
     ev1.record(stream)
     rt.synchronize(); torch.cuda.synchronize(); barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    rank_ms = [float(ms[0]) / args.steps]
     if world > 1:
+        every = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(every, ms)
+        rank_ms = [float(t[0]) / args.steps for t in every]  # per-rank device time: the spread is the load imbalance of the bands
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms[0]) / args.steps
     value = rays_frame / (ms_per_step * 1e-3) / 1e6
@@ -303,16 +309,37 @@ def main():
             for t in tickets[-n_flight:]:
                 rt.RenderEnd(t)
             return
-        for _ in range(n_steps):
-            if args.gather == "nccl":
+        if args.gather == "nccl":
+            for _ in range(n_steps):
                 fr = step_device(sync=True)
                 if rank == 0:
                     host_view[:] = fr.cpu().numpy()
-            else:
-                step_device(sync=True)
+            return
+        # peer-store gather, software-pipelined over two contexts per rank: while every rank renders frame k into frame buffer
+        # k % 2 of rank 0, rank 0 reads frame k-1 back (its ranks finished it: context sync + barrier).
+        for k in range(n_steps + 1):
+            if k < n_steps:
+                if k >= 2:
+                    barrier()  # frame k reuses the buffer of frame k-2: rank 0 must have finished reading it
+                twin[k & 1].RenderToTexture(packed, p, twin_dst[k & 1], frame_bytes, sync=False)
+            if k >= 1:
+                twin[(k - 1) & 1].synchronize()
                 barrier()
                 if rank == 0:
-                    rt.frame_read(host_view)
+                    twin[(k - 1) & 1].frame_read(host_views[(k - 1) & 1])
+        host_view[:] = host_views[(n_steps - 1) & 1]
+
+    twin, twin_dst = [rt, None], [dst_ptr, None]
+    if world > 1 and args.gather == "peer":
+        e2e_mode = "two contexts per rank: frame k renders on all ranks while rank 0 reads frame k-1 back (barrier per frame)"
+        twin[1] = rt_mod.RayTracer(devices=[local_rank], bvh_mode=rt.bvh_mode, primitive_mode=rt.primitive_mode)
+        handle2 = [None]
+        if rank == 0:
+            ptr1, hb = twin[1].frame_export(frame_bytes)
+            handle2[0] = hb
+        dist.broadcast_object_list(handle2, src=0)
+        twin_dst[1] = ptr1 if rank == 0 else twin[1].frame_import(handle2[0])
+        twin[1].RenderToTexture(packed, p, twin_dst[1], frame_bytes, sync=True)  # uploads the scene to the second context
 
     run_e2e(n_flight)
     torch.cuda.synchronize(); rt.synchronize(); barrier()
@@ -403,7 +430,8 @@ def main():
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "bvh": args.bvh, "primitives": args.prim, "rays_per_frame": rays_frame, "frame_ms": ms_per_step,
-                       "sharding": f"{world} rank(s), 32-row bands round-robin, gather={args.gather if world > 1 else 'none'}",
+                       "sharding": f"{world} rank(s), {BR}-row bands round-robin, gather={args.gather if world > 1 else 'none'}",
+                       "rank_ms_per_step": [round(x, 4) for x in rank_ms],
                        "l2": "no explicit flush: scene arrays (160 MB) plus ~1.4 GB of wavefront queues streamed per frame exceed the 126 MB L2",
                        "n_triangles": int(sl.n_triangles), "first_frame_s": first_frame_s},
             "clocks": clocks,
@@ -424,6 +452,8 @@ def main():
     for pp in pinned:
         lib.rtb_free_pinned(pp)
     barrier()
+    if twin[1] is not None:
+        twin[1].close()
     rt.close()
     if world > 1:
         dist.destroy_process_group()

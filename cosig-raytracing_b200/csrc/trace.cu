@@ -30,6 +30,17 @@ namespace rtb {
 namespace {
 
 constexpr int kBlock = 256;
+// Persistent traversal kernels (global-memory variant): block size and resident blocks per SM the register allocation is
+// bounded for.  Measured on the B200 (profiles/r1e_sweep_occupancy.log): 128 x 10 = 40 warps per SM at 48
+// registers (152 B of spills outside the node loop) beats 256 x 4 = 32 warps at 64 registers by 3-4 % on C3 / C4; 48 warps
+// (40 registers) loses again.  Build-time knobs so the sweep can be repeated (tools/build_variants.sh).
+#ifndef RTB_TRAVERSE_BLOCK
+#define RTB_TRAVERSE_BLOCK 128
+#endif
+#ifndef RTB_TRAVERSE_MIN_BLOCKS
+#define RTB_TRAVERSE_MIN_BLOCKS 10
+#endif
+constexpr int kTravBlock = RTB_TRAVERSE_BLOCK;
 constexpr int kBlockSmem = 1024;  // shared-memory staged k_traverse: one block per SM
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -180,7 +191,7 @@ __device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, 
 // k_traverse, LBVH flavour: ordered traversal over 64-byte two-box nodes (see lbvh.cu for the layout).
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool SMEM, bool ANALYTIC>
-__global__ void __launch_bounds__(SMEM ? kBlockSmem : kBlock, SMEM ? 1 : 4) k_traverse_lbvh(const SceneView s, const QueueView q, const int depth) {
+__global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB_TRAVERSE_MIN_BLOCKS) k_traverse_lbvh(const SceneView s, const QueueView q, const int depth) {
   extern __shared__ float4 sm_scene[];
   const float4* nodes = s.nodes;
   const float4* tri_isect = s.tri_isect;
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kBlock, SMEM ? 1 : 4) k_tr
 // culled when its own slab entry >= best t; leaves of any size.  Same results as the reference for every ray.
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool SMEM, bool ANALYTIC>
-__global__ void __launch_bounds__(SMEM ? kBlockSmem : kBlock, SMEM ? 1 : 4) k_traverse_ref(const SceneView s, const QueueView q, const int depth) {
+__global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB_TRAVERSE_MIN_BLOCKS) k_traverse_ref(const SceneView s, const QueueView q, const int depth) {
   extern __shared__ float4 sm_scene[];
   const float4* nodes = s.nodes;
   const float4* tri_isect = s.tri_isect;
@@ -709,7 +720,7 @@ __global__ void __launch_bounds__(kBlock) k_aux(const FrameParams f, const Scene
 template <typename K>
 int blocks_per_sm(K kernel) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kBlock, 0) != cudaSuccess || n < 1) n = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kTravBlock, 0) != cudaSuccess || n < 1) n = 1;
   return n;
 }
 
@@ -738,14 +749,14 @@ cudaError_t traverse_enable_smem(int bvh, size_t bytes) {
 void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int grid, size_t smem_bytes, cudaStream_t st) {
   const bool ref = bvh == RTB_BVH_REFERENCE;
   if (s.n_prims > 0) {
-    if (ref) k_traverse_ref<false, true><<<grid, kBlock, 0, st>>>(s, q, depth);
-    else k_traverse_lbvh<false, true><<<grid, kBlock, 0, st>>>(s, q, depth);
+    if (ref) k_traverse_ref<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth);
+    else k_traverse_lbvh<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth);
   } else if (smem_bytes > 0) {  // small scene: one 1024-thread block per SM works out of its shared-memory copy
     if (ref) k_traverse_ref<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
     else k_traverse_lbvh<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
   } else {
-    if (ref) k_traverse_ref<false, false><<<grid, kBlock, 0, st>>>(s, q, depth);
-    else k_traverse_lbvh<false, false><<<grid, kBlock, 0, st>>>(s, q, depth);
+    if (ref) k_traverse_ref<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth);
+    else k_traverse_lbvh<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth);
   }
 }
 
