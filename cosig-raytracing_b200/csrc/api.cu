@@ -249,7 +249,7 @@ int upload_on_device(rtb_context* ctx, DeviceState& d, const rtb_scene_desc& des
   const size_t tri_bytes = (size_t)n_out * 3 * sizeof(float4);
   CK(ctx, cudaMalloc(&s.raw, tri_bytes));
   CK(ctx, cudaMalloc(&s.nrm, tri_bytes));
-  CK(ctx, cudaMalloc(&s.isect, tri_bytes));
+  CK(ctx, cudaMalloc(&s.isect, (size_t)n_out * RTB_TRI_F4 * sizeof(float4)));
   CK(ctx, cudaMalloc(&s.shade, tri_bytes));
   CK(ctx, cudaMalloc(&s.perm, (size_t)n_out * sizeof(int32_t)));
 

@@ -107,17 +107,18 @@ __global__ void __launch_bounds__(kBlock) k_pack(const float4* __restrict__ raw,
     const int32_t src = perm[j];
     const float4 a = raw[3 * (size_t)src], b = raw[3 * (size_t)src + 1], c = raw[3 * (size_t)src + 2];
     const float4 n0 = nrm[3 * (size_t)src], n1 = nrm[3 * (size_t)src + 1], n2 = nrm[3 * (size_t)src + 2];
+    if (RTB_TRI_F4 > 3) isect[RTB_TRI_F4 * (size_t)j + 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (__float_as_int(n1.w) != 0) {  // analytic primitive: (table index, -, -, prim_id) (-, -, -, material) (-, -, -, kind)
-      isect[3 * (size_t)j] = make_float4(n2.w, 0.0f, 0.0f, __int_as_float(src));
-      isect[3 * (size_t)j + 1] = make_float4(0.0f, 0.0f, 0.0f, n0.w);
-      isect[3 * (size_t)j + 2] = make_float4(0.0f, 0.0f, 0.0f, n1.w);
+      isect[RTB_TRI_F4 * (size_t)j] = make_float4(n2.w, 0.0f, 0.0f, __int_as_float(src));
+      isect[RTB_TRI_F4 * (size_t)j + 1] = make_float4(0.0f, 0.0f, 0.0f, n0.w);
+      isect[RTB_TRI_F4 * (size_t)j + 2] = make_float4(0.0f, 0.0f, 0.0f, n1.w);
       shade[3 * (size_t)j] = shade[3 * (size_t)j + 1] = shade[3 * (size_t)j + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       continue;
     }
     // edges exactly as IntersectTriangle forms them (BVHRayTracing.compute:155-156): v1 - v0, v2 - v0
-    isect[3 * (size_t)j] = make_float4(a.x, a.y, a.z, __int_as_float(src));
-    isect[3 * (size_t)j + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, n0.w);
-    isect[3 * (size_t)j + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.0f);
+    isect[RTB_TRI_F4 * (size_t)j] = make_float4(a.x, a.y, a.z, __int_as_float(src));
+    isect[RTB_TRI_F4 * (size_t)j + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, n0.w);
+    isect[RTB_TRI_F4 * (size_t)j + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.0f);
     shade[3 * (size_t)j] = make_float4(n0.x, n0.y, n0.z, 0.0f);
     shade[3 * (size_t)j + 1] = make_float4(n1.x, n1.y, n1.z, 0.0f);
     shade[3 * (size_t)j + 2] = make_float4(n2.x, n2.y, n2.z, 0.0f);

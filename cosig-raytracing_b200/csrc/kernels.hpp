@@ -14,7 +14,7 @@ namespace rtb {
 // nrm[3i..] = (n0,material)(n1,0)(n2,0).
 void launch_flatten(const float* tri_in, const FlattenObject* objs, int n_objs, const float* sphere_table, int32_t n_out, float4* raw,
                     float4* nrm, cudaStream_t st);
-// Gathers into leaf order: isect[3j..] = (v0,prim_id)(v1-v0,material)(v2-v0,0), shade[3j..] = n0 n1 n2, prim_id = perm[j].
+// Gathers into leaf order: isect[RTB_TRI_F4 j..] = (v0,prim_id)(v1-v0,material)(v2-v0,0), shade[3j..] = n0 n1 n2, prim_id = perm[j].
 void launch_pack(const float4* raw, const float4* nrm, const int32_t* perm, int32_t n, float4* isect, float4* shade, cudaStream_t st);
 
 // ---- lbvh.cu (K2: Morton-code LBVH built on the GPU) -------------------------------------------------------------------

@@ -16,6 +16,12 @@ namespace rtb {
 #define RTB_OFFSET (1e-4f * 100.0f)   /* "Epsilon * 100.0", BVHRayTracing.compute:396,442,447,454 */
 
 #define RTB_STACK_REF 64   /* reference traversal: int stack (the reference has 32 unchecked, compute:235) */
+/* float4 per tri_isect record: 3 = packed 48-byte records (three 128-bit loads per test).  4 = 64-byte records, 32-byte
+   aligned, fetched with one 256-bit + one 128-bit load: measured 1 % SLOWER on C2-C4 (more bytes, same sectors), kept as a
+   build option. */
+#ifndef RTB_TRI_F4
+#define RTB_TRI_F4 3
+#endif
 #define RTB_STACK_LBVH 96  /* LBVH ordered traversal: one deferred sibling per level */
 #ifndef RTB_LEAF_MAX
 #define RTB_LEAF_MAX 4     /* LBVH leaf size (<= 8) */
@@ -100,7 +106,7 @@ struct ChunkView {
 
 // Geometry as laid out in HBM.
 struct SceneView {
-  const float4* __restrict__ tri_isect;  // 3 per triangle, leaf order: (v0, prim_id) (e1, material) (e2, 0); analytic primitive:
+  const float4* __restrict__ tri_isect;  // RTB_TRI_F4 per triangle, leaf order: (v0, prim_id) (e1, material) (e2, 0); analytic primitive:
                                          //   (table index bits, -, -, prim_id) (-, -, -, material) (-, -, -, kind: 1 sphere, 2 box)
   const float4* __restrict__ tri_shade;  // 3 per triangle, leaf order: n0 n1 n2
   const float4* __restrict__ nodes;      // reference: 2 per node (min,leftOrFirst)(max,count); LBVH: 4 or 8 per node (see lbvh.cu)

@@ -118,11 +118,16 @@ struct Lane {
 };
 
 // Lanes are refilled (and finished lanes published) only when at least this many of the warp's 32 lanes are out of work.
-// Measured on the B200 (C4): 32 — i.e. a warp takes 32 fresh rays when all of its lanes are done — beats 8 / 16 / 24 by
-// 4-20 %: rays that start together descend the upper tree in lockstep and share its cache lines.
+// Measured on the B200 (profiles/r1e_sweep_*.log).  With 128-bit node loads, 32 — a warp takes 32 fresh rays when all of
+// its lanes are done — beat 8 / 16 / 24 by 4-20 %: every active lane costs the L1 data pipe one wavefront per load
+// instruction, so filling the idle lanes only moved the bottleneck.  With 256-bit node loads (half the wavefronts per node
+// visit) 16 wins on the global-memory variant (C3 +7 %, C4 +3 %; 8 and 2 lose again); the shared-memory variant (C2) still
+// prefers 32.
 #ifndef RTB_REFILL_MIN
-#define RTB_REFILL_MIN 32
+#define RTB_REFILL_MIN 16
 #endif
+template <bool SMEM>
+struct RefillMin { static constexpr int value = SMEM ? 32 : RTB_REFILL_MIN; };
 
 // Loads work item `item` into the lane.
 __device__ __forceinline__ void lane_load(Lane& L, const QueueView& q, int32_t item, int32_t n_closest, int in_q) {
@@ -162,7 +167,7 @@ __device__ __forceinline__ void lane_finish(Lane& L, const QueueView& q, int32_t
 
 // Stages the traversal arrays (nodes, then tri_isect) into dynamic shared memory; returns the two base pointers.
 __device__ __forceinline__ void stage_scene(const SceneView& s, int node_f4, float4* sm, const float4*& nodes, const float4*& tris) {
-  const int n_node = s.n_nodes * node_f4, n_tri = s.n_tris * 3;
+  const int n_node = s.n_nodes * node_f4, n_tri = s.n_tris * RTB_TRI_F4;
   for (int i = threadIdx.x; i < n_node; i += blockDim.x) sm[i] = __ldg(&s.nodes[i]);
   for (int i = threadIdx.x; i < n_tri; i += blockDim.x) sm[n_node + i] = __ldg(&s.tri_isect[i]);
   __syncthreads();
@@ -173,7 +178,13 @@ __device__ __forceinline__ void stage_scene(const SceneView& s, int node_f4, flo
 // Triangle test shared by both flavours.  Returns true when a shadow ray found its occluder.
 template <bool SMEM, bool ANALYTIC>
 __device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, const float4* tri_isect, int32_t tri) {
-  const float4 a = ld4<SMEM>(&tri_isect[3 * tri]), b = ld4<SMEM>(&tri_isect[3 * tri + 1]), c = ld4<SMEM>(&tri_isect[3 * tri + 2]);
+  float4 a, b;
+#if RTB_TRI_F4 == 4
+  ld8<SMEM>(&tri_isect[RTB_TRI_F4 * tri], a, b);
+#else
+  a = ld4<SMEM>(&tri_isect[RTB_TRI_F4 * tri]); b = ld4<SMEM>(&tri_isect[RTB_TRI_F4 * tri + 1]);
+#endif
+  const float4 c = ld4<SMEM>(&tri_isect[RTB_TRI_F4 * tri + 2]);
   Ray r; r.o = L.o; r.d = L.d;
   float t, u, v;
   if (ANALYTIC && __float_as_int(c.w) != 0) {  // analytic primitive: hit record = (t_world, t_object, face code)
@@ -205,8 +216,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
     if (depth > 0 && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
     if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
   }
-  int32_t stack_ref[RTB_STACK_LBVH];
-  float stack_dst[RTB_STACK_LBVH];
+  float2 stack[RTB_STACK_LBVH];  // deferred children: (entry distance, node / leaf reference) in one 8-byte local-memory access
   int sp = 0;
   int32_t cur = RTB_REF_DONE;
   f3 ood = mk3(0.0f, 0.0f, 0.0f);
@@ -219,7 +229,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
   for (;;) {
     // ---- publish finished lanes and refill, in batches ----
     const int n_out = __popc(__ballot_sync(kFull, L.item < 0 || L.done));
-    if (n_out >= RTB_REFILL_MIN) {
+    if (n_out >= RefillMin<SMEM>::value) {
       if (L.item >= 0 && L.done) lane_finish(L, q, n_closest);
       const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, L.item < 0, lane);
       if (item >= 0) {
@@ -240,14 +250,14 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
     while (cur >= 0) {
       n_nodes++;
       // closest: a box is skipped when entry >= best t (compute:246); shadow rays carry nextafter(distToLight) as bound
-      const int32_t next = lbvh_visit<SMEM>(nodes, cur, L.inv, ood, L.t, stack_ref, stack_dst, sp, overflow);
+      const int32_t next = lbvh_visit<SMEM>(nodes, cur, L.inv, ood, L.t, stack, sp, overflow);
       if (next != RTB_REF_MISS) cur = next;
       else {
         cur = RTB_REF_DONE;
         while (sp > 0) {
           sp--;
-          const float dd = stack_dst[sp];
-          if (!(dd >= L.t)) { cur = stack_ref[sp]; break; }
+          const float2 e = stack[sp];
+          if (!(e.x >= L.t)) { cur = __float_as_int(e.y); break; }
         }
       }
     }
@@ -263,8 +273,8 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
       if (!occluded)
         while (sp > 0) {
           sp--;
-          const float dd = stack_dst[sp];
-          if (!(dd >= L.t)) { cur = stack_ref[sp]; break; }
+          const float2 e = stack[sp];
+          if (!(e.x >= L.t)) { cur = __float_as_int(e.y); break; }
         }
     }
     if (cur == RTB_REF_DONE && L.item >= 0) { sp = 0; L.done = true; }
@@ -312,7 +322,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
 
   for (;;) {
     const int n_out = __popc(__ballot_sync(kFull, L.item < 0 || L.done));
-    if (n_out >= RTB_REFILL_MIN) {
+    if (n_out >= RefillMin<SMEM>::value) {
       if (L.item >= 0 && L.done) lane_finish(L, q, n_closest);
       const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, L.item < 0, lane);
       if (item >= 0) {
@@ -446,7 +456,7 @@ __device__ __forceinline__ void shade_hit(const FrameParams& f, const SceneView&
                                           int depth, Shaded& o) {
   f3 pos, nrm;
   hit_surface<ANALYTIC>(s, ray, hit, pos, nrm);  // :183-187
-  const Material m = fetch_material(s, __float_as_int(__ldg(&s.tri_isect[3 * hit.tri + 1]).w));
+  const Material m = fetch_material(s, __float_as_int(__ldg(&s.tri_isect[RTB_TRI_F4 * hit.tri + 1]).w));
   f3 local = mk3(0.0f, 0.0f, 0.0f);
   if (f.en_ambient == 1) local = local + m.color * m.ka;  // :379
   f3 light_pos = mk3(f.light[0], f.light[1], f.light[2]);
@@ -711,9 +721,9 @@ __global__ void __launch_bounds__(kBlock) k_aux(const FrameParams f, const Scene
     Hit h;
     const bool found = traverse<BVH, false, ANALYTIC>(s, ray, 0.0f, h, overflow);
     const size_t at = (size_t)py * (size_t)f.width + (size_t)px;
-    if (prim) prim[at] = found ? __float_as_int(__ldg(&s.tri_isect[3 * h.tri]).w) : -1;
+    if (prim) prim[at] = found ? __float_as_int(__ldg(&s.tri_isect[RTB_TRI_F4 * h.tri]).w) : -1;
     if (t_out) t_out[at] = h.t;
-    if (mat) mat[at] = found ? __float_as_int(__ldg(&s.tri_isect[3 * h.tri + 1]).w) : -1;
+    if (mat) mat[at] = found ? __float_as_int(__ldg(&s.tri_isect[RTB_TRI_F4 * h.tri + 1]).w) : -1;
   }
 }
 
@@ -736,7 +746,7 @@ void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const Queu
 }
 
 size_t traverse_smem_bytes(int bvh, const SceneView& s) {
-  return ((size_t)s.n_nodes * (bvh == RTB_BVH_REFERENCE ? 2 : lbvh_node_f4) + (size_t)s.n_tris * 3) * sizeof(float4);
+  return ((size_t)s.n_nodes * (bvh == RTB_BVH_REFERENCE ? 2 : lbvh_node_f4) + (size_t)s.n_tris * RTB_TRI_F4) * sizeof(float4);
 }
 
 cudaError_t traverse_enable_smem(int bvh, size_t bytes) {

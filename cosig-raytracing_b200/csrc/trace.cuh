@@ -233,7 +233,7 @@ __device__ __forceinline__ bool moller_trumbore(const Ray& r, f3 v0, f3 e1, f3 e
 // For an analytic primitive the hit record holds (t_world, t_object, face code) in (t, u, v).
 template <bool ANALYTIC>
 __device__ __forceinline__ void test_triangle_closest(const SceneView& s, const Ray& r, int32_t tri, Hit& best) {
-  const float4 a = __ldg(&s.tri_isect[3 * tri]), b = __ldg(&s.tri_isect[3 * tri + 1]), c = __ldg(&s.tri_isect[3 * tri + 2]);
+  const float4 a = __ldg(&s.tri_isect[RTB_TRI_F4 * tri]), b = __ldg(&s.tri_isect[RTB_TRI_F4 * tri + 1]), c = __ldg(&s.tri_isect[RTB_TRI_F4 * tri + 2]);
   float t, u, v;
   if (ANALYTIC && __float_as_int(c.w) != 0) {
     int face;
@@ -246,7 +246,7 @@ __device__ __forceinline__ void test_triangle_closest(const SceneView& s, const 
 }
 template <bool ANALYTIC>
 __device__ __forceinline__ bool test_triangle_any(const SceneView& s, const Ray& r, int32_t tri, float t_limit) {
-  const float4 a = __ldg(&s.tri_isect[3 * tri]), b = __ldg(&s.tri_isect[3 * tri + 1]), c = __ldg(&s.tri_isect[3 * tri + 2]);
+  const float4 a = __ldg(&s.tri_isect[RTB_TRI_F4 * tri]), b = __ldg(&s.tri_isect[RTB_TRI_F4 * tri + 1]), c = __ldg(&s.tri_isect[RTB_TRI_F4 * tri + 2]);
   float t, u, v;
   if (ANALYTIC && __float_as_int(c.w) != 0) {
     int face;
@@ -292,6 +292,23 @@ __device__ __forceinline__ bool traverse_reference(const SceneView& s, const Ray
 // from the copy the block staged in shared memory (SMEM).
 template <bool SMEM>
 __device__ __forceinline__ float4 ld4(const float4* p) { return SMEM ? *p : __ldg(p); }
+// Two consecutive float4 (32-byte aligned) in ONE 256-bit load through the read-only path (sm_100: LDG.E.ENL2.256.CONSTANT).
+// A divergent warp pays L1 wavefronts per instruction and distinct line, so fetching a 64-byte node record with two
+// instructions instead of four halves the L1 data-pipe work of a node visit (RTB_LD256=0 keeps the 128-bit loads).
+#ifndef RTB_LD256
+#define RTB_LD256 1
+#endif
+template <bool SMEM>
+__device__ __forceinline__ void ld8(const float4* p, float4& a, float4& b) {
+#if RTB_LD256
+  if (!SMEM) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+    return;
+  }
+#endif
+  a = ld4<SMEM>(p); b = ld4<SMEM>(p + 1);
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // One LBVH node visit, shared by the persistent kernel and the per-thread traversals (so both order children the same
@@ -300,7 +317,7 @@ __device__ __forceinline__ float4 ld4(const float4* p) { return SMEM ? *p : __ld
 // ---------------------------------------------------------------------------------------------------------------------
 #if RTB_LBVH_WIDTH == 4
 template <bool SMEM>
-__device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, f3 inv, f3 ood, float bound, int32_t* stack_ref, float* stack_dst,
+__device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, f3 inv, f3 ood, float bound, float2* stack,
                                               int& sp, unsigned& overflow) {
   const float4* rec = nodes + 8 * (size_t)cur;
   const float4 mnx = ld4<SMEM>(rec), mny = ld4<SMEM>(rec + 1), mnz = ld4<SMEM>(rec + 2);
@@ -323,24 +340,25 @@ __device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, 
   RTB_CE(e0, r0, e1, r1) RTB_CE(e2, r2, e3, r3) RTB_CE(e0, r0, e2, r2) RTB_CE(e1, r1, e3, r3) RTB_CE(e1, r1, e2, r2)
 #undef RTB_CE
   if (sp + n_hit - 1 > RTB_STACK_LBVH) { overflow++; return r0; }
-  if (n_hit > 3) { stack_ref[sp] = r3; stack_dst[sp] = e3; sp++; }
-  if (n_hit > 2) { stack_ref[sp] = r2; stack_dst[sp] = e2; sp++; }
-  if (n_hit > 1) { stack_ref[sp] = r1; stack_dst[sp] = e1; sp++; }
+  if (n_hit > 3) { stack[sp] = make_float2(e3, __int_as_float(r3)); sp++; }
+  if (n_hit > 2) { stack[sp] = make_float2(e2, __int_as_float(r2)); sp++; }
+  if (n_hit > 1) { stack[sp] = make_float2(e1, __int_as_float(r1)); sp++; }
   return r0;
 }
 #else
 template <bool SMEM>
-__device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, f3 inv, f3 ood, float bound, int32_t* stack_ref, float* stack_dst,
+__device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, f3 inv, f3 ood, float bound, float2* stack,
                                               int& sp, unsigned& overflow) {
-  const float4 n0 = ld4<SMEM>(&nodes[4 * cur]), n1 = ld4<SMEM>(&nodes[4 * cur + 1]);
-  const float4 n2 = ld4<SMEM>(&nodes[4 * cur + 2]), n3 = ld4<SMEM>(&nodes[4 * cur + 3]);
+  float4 n0, n1, n2, n3;
+  ld8<SMEM>(&nodes[4 * cur], n0, n1);
+  ld8<SMEM>(&nodes[4 * cur + 2], n2, n3);
   float dl, dr;
   const bool hl = slab_hit_fma(inv, ood, mk3(n0), mk3(n1), bound, dl);
   const bool hr = slab_hit_fma(inv, ood, mk3(n2), mk3(n3), bound, dr);
   const int32_t lref = __float_as_int(n0.w), rref = __float_as_int(n1.w);
   if (hl && hr) {
     const bool left_first = !(dr < dl);
-    if (sp < RTB_STACK_LBVH) { stack_ref[sp] = left_first ? rref : lref; stack_dst[sp] = left_first ? dr : dl; sp++; }
+    if (sp < RTB_STACK_LBVH) { stack[sp] = make_float2(left_first ? dr : dl, __int_as_float(left_first ? rref : lref)); sp++; }
     else overflow++;
     return left_first ? lref : rref;
   }
@@ -361,8 +379,7 @@ template <bool ANY, bool ANALYTIC>
 __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, float t_limit, Hit& best, unsigned& overflow) {
   best.t = RTB_INFINITY; best.u = 0.0f; best.v = 0.0f; best.tri = -1;
   if (s.n_tris == 0) return false;
-  int32_t stack_ref[RTB_STACK_LBVH];
-  float stack_dst[RTB_STACK_LBVH];
+  float2 stack[RTB_STACK_LBVH];  // deferred children: (entry distance, node / leaf reference) in one 8-byte local-memory access
   int sp = 0;
   int32_t cur = s.root;
   const f3 inv = safe_inverse(r.d);
@@ -371,7 +388,7 @@ __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, 
     if (cur >= 0) {
       // same box test, bound and child order as k_traverse_lbvh
       const float bound = ANY ? nextafterf(t_limit, INFINITY) : best.t;
-      const int32_t next = lbvh_visit<false>(s.nodes, cur, inv, ood, bound, stack_ref, stack_dst, sp, overflow);
+      const int32_t next = lbvh_visit<false>(s.nodes, cur, inv, ood, bound, stack, sp, overflow);
       if (next != RTB_REF_MISS) { cur = next; continue; }
     } else {
       const int32_t code = ~cur;
@@ -385,8 +402,8 @@ __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, 
     for (;;) {
       if (sp == 0) return best.tri >= 0;
       sp--;
-      const float d = stack_dst[sp];
-      if (ANY ? !(d > t_limit) : !(d >= best.t)) { cur = stack_ref[sp]; break; }
+      const float2 e = stack[sp];
+      if (ANY ? !(e.x > t_limit) : !(e.x >= best.t)) { cur = __float_as_int(e.y); break; }
     }
   }
 }
@@ -411,9 +428,9 @@ __device__ __forceinline__ f3 hit_normal(const SceneView& s, const Hit& h) {
 template <bool ANALYTIC>
 __device__ __forceinline__ void hit_surface(const SceneView& s, const Ray& ray, const Hit& h, f3& pos, f3& nrm) {
   if (ANALYTIC) {
-    const int kind = __float_as_int(__ldg(&s.tri_isect[3 * h.tri + 2]).w);
+    const int kind = __float_as_int(__ldg(&s.tri_isect[RTB_TRI_F4 * h.tri + 2]).w);
     if (kind != 0) {
-      const int idx = __float_as_int(__ldg(&s.tri_isect[3 * h.tri]).x);
+      const int idx = __float_as_int(__ldg(&s.tri_isect[RTB_TRI_F4 * h.tri]).x);
       analytic_surface(&s.prims[6 * idx], kind, ray.o, ray.d, h.u, (int)h.v, pos, nrm);
       return;
     }
