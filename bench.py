@@ -292,7 +292,7 @@ def main():
     host = np.zeros((h, w, 4), np.uint8)
     lib = abi.load()
     import ctypes as C
-    n_flight = max(2, min(4, int(os.environ.get("RTB_LANES", "4"))))  # frames in flight of the pipelined host API = the library's lanes
+    n_flight = max(2, min(8, int(os.environ.get("RTB_LANES", "4"))))  # frames in flight of the pipelined host API = the library's lanes
     pinned = [lib.rtb_alloc_pinned(frame_bytes) for _ in range(n_flight)]
     host_views = [np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_uint8)), shape=(h, w, 4)) for pp in pinned]
     host_view = host_views[0]

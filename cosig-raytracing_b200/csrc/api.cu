@@ -53,10 +53,13 @@ struct DeviceState {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_done = nullptr;  // scene upload timing / cross-device completion
   cudaEvent_t ev_resolve = nullptr;  // orders the resolve kernels of successive chunks / frames (they may share pixels)
   bool resolve_pending = false;
-  static constexpr int kMaxLanes = 4;
+  static constexpr int kMaxLanes = 8;
   LaneState lane[kMaxLanes];
   int next_lane = 0;
   int last_lane = 0;              // lane of the last chunk enqueued (where a frame's readback is ordered)
+  cudaStream_t copy_stream = nullptr;  // device->host copies of rtb_render_begin: the lanes go on with the next frames meanwhile
+  cudaEvent_t ev_copy = nullptr;
+  bool copy_pending = false;
   void* frame_async[kMaxLanes] = {};  // frames of rtb_render_begin, rotating, so a readback never races the following frames
   size_t frame_async_bytes[kMaxLanes] = {};
   float* sphere_table = nullptr;
@@ -84,13 +87,14 @@ struct rtb_context {
   const volatile int32_t* cancel = nullptr;
   bool profiling = false;
   int64_t chunk_slots = 1 << 23;
-  int n_lanes = 4;            // RTB_LANES (1..4): chunks / async frames rotate over this many streams, each with its own queues
+  int n_lanes = 4;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues
   uint64_t frame_id = 0;
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
   int32_t tail_max = 196608;  // queues smaller than this finish in k_tail (RTB_TAIL_MAX; 0 = pure wavefront)
   std::vector<void*> ipc_opened;
-  static constexpr int kTickets = 8;  // frames in flight through rtb_render_begin
-  cudaEvent_t ticket_event[kTickets] = {};
+  static constexpr int kTickets = 16;  // frames in flight through rtb_render_begin
+  cudaEvent_t ticket_event[kTickets] = {};   // frame complete in its host buffer
+  cudaEvent_t frame_ready[kTickets] = {};    // frame complete in its device buffer (the copy stream waits for it)
   uint64_t tickets_issued = 0;
 };
 
@@ -131,8 +135,10 @@ void device_sync(DeviceState& d) {
   cudaSetDevice(d.device);
   for (auto& l : d.lane)
     if (l.stream) cudaStreamSynchronize(l.stream);
+  if (d.copy_stream) cudaStreamSynchronize(d.copy_stream);
   for (auto& l : d.lane) l.used = false;
   d.resolve_pending = false;
+  d.copy_pending = false;
 }
 
 // lane 0's stream (the one the host sees) waits for everything enqueued on lane 1
@@ -143,6 +149,12 @@ cudaError_t join_lanes(DeviceState& d) {
       if (e != cudaSuccess) return e;
       d.lane[k].used = false;
     }
+  if (d.copy_pending) {  // readbacks of rtb_render_begin still in flight on the copy stream
+    cudaError_t e = cudaEventRecord(d.ev_copy, d.copy_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(d.lane[0].stream, d.ev_copy, 0);
+    if (e != cudaSuccess) return e;
+    d.copy_pending = false;
+  }
   return cudaSuccess;
 }
 
@@ -564,6 +576,8 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
       CK(nullptr, cudaEventCreateWithFlags(&l.ev_done, cudaEventDisableTiming));
     }
     d.stream = d.lane[0].stream;
+    CK(nullptr, cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+    CK(nullptr, cudaEventCreateWithFlags(&d.ev_copy, cudaEventDisableTiming));
     CK(nullptr, cudaEventCreateWithFlags(&d.ev_resolve, cudaEventDisableTiming));
     CK(nullptr, cudaEventCreate(&d.ev_begin));
     CK(nullptr, cudaEventCreate(&d.ev_end));
@@ -590,6 +604,8 @@ void rtb_destroy(rtb_context* ctx) {
   if (!ctx) return;
   for (auto& e : ctx->ticket_event)
     if (e) { cudaSetDevice(ctx->devs[0].device); cudaEventDestroy(e); }
+  for (auto& e : ctx->frame_ready)
+    if (e) { cudaSetDevice(ctx->devs[0].device); cudaEventDestroy(e); }
   for (void* p : ctx->ipc_opened) {
     cudaSetDevice(ctx->devs[0].device);
     cudaIpcCloseMemHandle(p);
@@ -605,6 +621,8 @@ void rtb_destroy(rtb_context* ctx) {
     if (d.ev_end) cudaEventDestroy(d.ev_end);
     if (d.ev_done) cudaEventDestroy(d.ev_done);
     if (d.ev_resolve) cudaEventDestroy(d.ev_resolve);
+    if (d.ev_copy) cudaEventDestroy(d.ev_copy);
+    if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     for (auto& l : d.lane) {
       if (l.ev_begin) cudaEventDestroy(l.ev_begin);
       if (l.ev_end) cudaEventDestroy(l.ev_end);
@@ -711,8 +729,9 @@ int rtb_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba
   const uint64_t n = ctx->tickets_issued;
   const int n_buf = std::max(2, ctx->n_lanes);
   const int slot = (int)(n % rtb_context::kTickets), buf = (int)(n % (uint64_t)n_buf);
+  if (!ctx->frame_ready[slot]) CK(ctx, cudaEventCreateWithFlags(&ctx->frame_ready[slot], cudaEventDisableTiming));
   if (!ctx->ticket_event[slot]) CK(ctx, cudaEventCreateWithFlags(&ctx->ticket_event[slot], cudaEventDisableTiming));
-  else CK(ctx, cudaEventSynchronize(ctx->ticket_event[slot]));  // the ring is full: wait for the frame issued 8 calls ago
+  else CK(ctx, cudaEventSynchronize(ctx->ticket_event[slot]));  // the ring is full: wait for the frame issued kTickets calls ago
   if (d.frame_async_bytes[buf] < need) {
     device_sync(d);
     dfree(d.frame_async[buf]);
@@ -730,8 +749,12 @@ int rtb_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba
   LaneState& last = d.lane[d.last_lane];
   for (int k = 0; k < DeviceState::kMaxLanes; k++)  // multi-chunk frame: every lane that carried one of its chunks
     if (k != d.last_lane && d.lane[k].stream && d.lane[k].frame_id == ctx->frame_id) CK(ctx, cudaStreamWaitEvent(last.stream, d.lane[k].ev_done, 0));
-  CK(ctx, cudaMemcpyAsync(rgba8, d.frame_async[buf], need, cudaMemcpyDeviceToHost, last.stream));
-  CK(ctx, cudaEventRecord(ctx->ticket_event[slot], last.stream));
+  // the readback runs on its own stream, so this lane can start the frame after next while the copy is on the wire
+  CK(ctx, cudaEventRecord(ctx->frame_ready[slot], last.stream));
+  CK(ctx, cudaStreamWaitEvent(d.copy_stream, ctx->frame_ready[slot], 0));
+  CK(ctx, cudaMemcpyAsync(rgba8, d.frame_async[buf], need, cudaMemcpyDeviceToHost, d.copy_stream));
+  CK(ctx, cudaEventRecord(ctx->ticket_event[slot], d.copy_stream));
+  d.copy_pending = true;
   CK(ctx, cudaEventRecord(last.ev_done, last.stream));
   last.used = true;
   ctx->stats.d2h_bytes = (int64_t)need;
