@@ -188,7 +188,7 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--prim", default="tessellated", choices=["tessellated", "analytic"],
                     help="analytic: spheres / boxes are intersected analytically (SURVEY A13) instead of tessellated like the reference")
-    ap.add_argument("--band-rows", type=int, default=32, help="N > 1: rows per band (multiple of 4); band b is rendered by rank b % N")
+    ap.add_argument("--band-rows", type=int, default=8, help="N > 1: rows per band (multiple of 4); band b is rendered by rank b % N")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--out-png", default=None, help="rank 0 writes the last frame here")
     args = ap.parse_args()

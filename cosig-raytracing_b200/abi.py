@@ -141,6 +141,16 @@ SYMBOLS = {
     "rtb_get_bvh": (C.c_int, [_VP, _VP, C.c_int64, C.POINTER(C.c_int64), _VP, C.c_int64]),
     "rtb_frame_read": (C.c_int, [_VP, _VP, C.c_size_t]),
     "rtb_build_reference_bvh": (C.c_int, [_VP, C.c_int32, _VP, C.c_int64, C.POINTER(C.c_int64), _VP]),
+    # GIF sweep (GifGenerator.cs)
+    "rtb_gif_color_table": (None, [_VP]),
+    "rtb_gif_lzw_bound": (C.c_int64, [C.c_int64]),
+    "rtb_gif_lzw": (C.c_int64, [_VP, C.c_int64, _VP, C.c_int64]),
+    "rtb_gif_index_frame": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP]),
+    "rtb_gif_index_device": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP]),
+    "rtb_render_begin_indexed": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, C.c_size_t, C.POINTER(C.c_int32)]),
+    "rtb_gif_save_indexed": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(_VP), C.c_int32, C.c_int32, C.c_int32]),
+    "rtb_gif_save": (C.c_int, [_VP, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(_VP), C.c_int32, C.c_int32, C.c_int32]),
+    "rtb_gif_render_rotation": (C.c_int, [_VP, C.POINTER(RenderParams), C.c_int32, C.c_float, C.c_char_p, C.c_int32, C.c_int32]),
 }
 
 LIB_NAME = "librtb200.so"

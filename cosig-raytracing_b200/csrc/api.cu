@@ -3,6 +3,7 @@
 // This file is the B200-native counterpart of Assets/Services/RayTracer.cs: rtb_upload_scene = RebuildBVH (:386-404) +
 // SetupMaterialBuffer (:455-499); rtb_render = RenderAsync (:212-380); rtb_render_device = RenderToTexture (:82-202).
 // There is no CPU fallback: every entry point that computes needs a CUDA device and fails with RTB_E_CUDA otherwise.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -10,8 +11,10 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
+#include "gif.hpp"
 #include "kernels.hpp"
 
 using namespace rtb;
@@ -62,6 +65,8 @@ struct DeviceState {
   bool copy_pending = false;
   void* frame_async[kMaxLanes] = {};  // frames of rtb_render_begin, rotating, so a readback never races the following frames
   size_t frame_async_bytes[kMaxLanes] = {};
+  void* index_async[kMaxLanes] = {};  // palette-index frames of rtb_render_begin_indexed (GIF sweep), same rotation
+  size_t index_async_bytes[kMaxLanes] = {};
   float* sphere_table = nullptr;
   DeviceScene scene;
   void* frame = nullptr;  // RGBA8 frame (device 0) — also the IPC-exported buffer
@@ -166,6 +171,7 @@ void free_targets(DeviceState& d) {
   }
   dfree(d.frame); d.frame_bytes = 0;
   for (int k = 0; k < DeviceState::kMaxLanes; k++) { dfree(d.frame_async[k]); d.frame_async_bytes[k] = 0; }
+  for (int k = 0; k < DeviceState::kMaxLanes; k++) { dfree(d.index_async[k]); d.index_async_bytes[k] = 0; }
   dfree(d.aux_prim); dfree(d.aux_mat); dfree(d.aux_t); d.aux_px = 0;
 }
 
@@ -712,10 +718,12 @@ int rtb_render(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, siz
   return RTB_OK;
 }
 
-// Pipelined form of rtb_render: enqueues the frame and its readback and returns; up to 8 frames may be in flight.  Successive
-// frames alternate between the two lanes (their tails overlap the next frame's bulk) and between two device frame buffers.
-int rtb_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* ticket) {
-  if (!ctx || !p || !rgba8 || !ticket) return fail(ctx, RTB_E_ARG, "null argument");
+// Pipelined form of rtb_render: enqueues the frame and its readback and returns; up to kTickets frames may be in flight.
+// Successive frames rotate over the lanes (their tails overlap the next frame's bulk) and over as many device frame buffers.
+// `indexed`: the frame is mapped to GIF palette indices on the device (gif.cu: k_palette) and 1 byte per pixel is read back.
+namespace {
+int begin_frame(rtb_context* ctx, const rtb_render_params* p, uint8_t* host_dst, size_t bytes, int32_t* ticket, bool indexed) {
+  if (!ctx || !p || !host_dst || !ticket) return fail(ctx, RTB_E_ARG, "null argument");
   if (p->band_world > 1) return fail(ctx, RTB_E_ARG, "rtb_render_begin renders whole frames");
   if (ctx->devs.size() > 1) return fail(ctx, RTB_E_ARG, "rtb_render_begin needs a single-device context (use rtb_render)");
   if (!ctx->has_scene) return fail(ctx, RTB_E_NOSCENE, "no scene uploaded (rtb_upload_scene)");
@@ -723,7 +731,8 @@ int rtb_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba
   std::string why;
   if (!resolve_frame(ctx->host.d, *p, f, why)) return fail(ctx, RTB_E_ARG, why);
   const size_t need = (size_t)f.width * f.height * 4;
-  if (bytes < need) return fail(ctx, RTB_E_SIZE, "rgba8 buffer too small for the resolved resolution");
+  const size_t need_out = indexed ? (size_t)f.width * f.height : need;
+  if (bytes < need_out) return fail(ctx, RTB_E_SIZE, indexed ? "index buffer too small for the resolved resolution" : "rgba8 buffer too small for the resolved resolution");
   DeviceState& d = ctx->devs[0];
   CK(ctx, cudaSetDevice(d.device));
   const uint64_t n = ctx->tickets_issued;
@@ -739,6 +748,13 @@ int rtb_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba
     CK(ctx, cudaMalloc(&d.frame_async[buf], need));
     d.frame_async_bytes[buf] = need;
   }
+  if (indexed && d.index_async_bytes[buf] < need_out) {
+    device_sync(d);
+    dfree(d.index_async[buf]);
+    d.index_async_bytes[buf] = 0;
+    CK(ctx, cudaMalloc(&d.index_async[buf], need_out));
+    d.index_async_bytes[buf] = need_out;
+  }
   // this frame reuses the device buffer of the frame issued n_buf calls ago: its readback must have finished
   if (n >= (uint64_t)n_buf) {
     cudaEvent_t prev = ctx->ticket_event[(n - (uint64_t)n_buf) % rtb_context::kTickets];
@@ -749,18 +765,31 @@ int rtb_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba
   LaneState& last = d.lane[d.last_lane];
   for (int k = 0; k < DeviceState::kMaxLanes; k++)  // multi-chunk frame: every lane that carried one of its chunks
     if (k != d.last_lane && d.lane[k].stream && d.lane[k].frame_id == ctx->frame_id) CK(ctx, cudaStreamWaitEvent(last.stream, d.lane[k].ev_done, 0));
+  if (indexed) {  // ConvertToIndexed, GifGenerator.cs:346-369
+    launch_palette(d.frame_async[buf], f.width, f.height, (uint8_t*)d.index_async[buf], last.stream);
+    ctx->stats.kernel_launches++;
+  }
   // the readback runs on its own stream, so this lane can start the frame after next while the copy is on the wire
   CK(ctx, cudaEventRecord(ctx->frame_ready[slot], last.stream));
   CK(ctx, cudaStreamWaitEvent(d.copy_stream, ctx->frame_ready[slot], 0));
-  CK(ctx, cudaMemcpyAsync(rgba8, d.frame_async[buf], need, cudaMemcpyDeviceToHost, d.copy_stream));
+  CK(ctx, cudaMemcpyAsync(host_dst, indexed ? d.index_async[buf] : d.frame_async[buf], need_out, cudaMemcpyDeviceToHost, d.copy_stream));
   CK(ctx, cudaEventRecord(ctx->ticket_event[slot], d.copy_stream));
   d.copy_pending = true;
   CK(ctx, cudaEventRecord(last.ev_done, last.stream));
   last.used = true;
-  ctx->stats.d2h_bytes = (int64_t)need;
+  ctx->stats.d2h_bytes = (int64_t)need_out;
   *ticket = (int32_t)(n & 0x7fffffff);
   ctx->tickets_issued++;
   return RTB_OK;
+}
+}  // namespace
+
+int rtb_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* ticket) {
+  return begin_frame(ctx, p, rgba8, bytes, ticket, /*indexed=*/false);
+}
+
+int rtb_render_begin_indexed(rtb_context* ctx, const rtb_render_params* p, uint8_t* indexed, size_t bytes, int32_t* ticket) {
+  return begin_frame(ctx, p, indexed, bytes, ticket, /*indexed=*/true);
 }
 
 // Waits until the frame of `ticket` is complete in its host buffer.
@@ -1006,5 +1035,115 @@ int rtb_scene_load(const char* path, rtb_scene** out, char* err, size_t err_cap)
 
 const rtb_scene_desc* rtb_scene_get(const rtb_scene* s) { return s ? &s->h.d : nullptr; }
 void rtb_scene_free(rtb_scene* s) { delete s; }
+
+// ---- GIF sweep (GifGenerator.cs; host coder and container in gif.cu) -------------------------------------------------------
+
+int rtb_gif_index_frame(rtb_context* ctx, const uint8_t* rgba8, int32_t width, int32_t height, uint8_t* indexed) {
+  if (!ctx || !rgba8 || !indexed || width <= 0 || height <= 0) return fail(ctx, RTB_E_ARG, "bad argument");
+  DeviceState& d = ctx->devs[0];
+  CK(ctx, cudaSetDevice(d.device));
+  const size_t n_px = (size_t)width * height;
+  void *src = nullptr, *dst = nullptr;
+  CK(ctx, cudaMalloc(&src, n_px * 4));
+  cudaError_t e = cudaMalloc(&dst, n_px);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(src, rgba8, n_px * 4, cudaMemcpyHostToDevice, d.stream);
+  if (e == cudaSuccess) { launch_palette(src, width, height, (uint8_t*)dst, d.stream); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(indexed, dst, n_px, cudaMemcpyDeviceToHost, d.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+  cudaFree(src);
+  cudaFree(dst);
+  if (e != cudaSuccess) return fail(ctx, RTB_E_CUDA, std::string("rtb_gif_index_frame: ") + cudaGetErrorString(e));
+  return RTB_OK;
+}
+
+int rtb_gif_index_device(rtb_context* ctx, const void* rgba8_device, int32_t width, int32_t height, void* indexed_device) {
+  if (!ctx || !rgba8_device || !indexed_device || width <= 0 || height <= 0) return fail(ctx, RTB_E_ARG, "bad argument");
+  DeviceState& d = ctx->devs[0];
+  CK(ctx, cudaSetDevice(d.device));
+  launch_palette(rgba8_device, width, height, (uint8_t*)indexed_device, d.stream);
+  CK(ctx, cudaGetLastError());
+  return RTB_OK;
+}
+
+int rtb_gif_save(rtb_context* ctx, const char* path, int32_t width, int32_t height, const uint8_t* const* rgba8_frames, int32_t n_frames,
+                 int32_t frame_delay_cs, int32_t threads) {
+  if (!path || !rgba8_frames || n_frames <= 0 || width <= 0 || height <= 0) return ctx ? fail(ctx, RTB_E_ARG, "bad argument") : RTB_E_ARG;
+  const size_t n_px = (size_t)width * height;
+  std::vector<std::vector<uint8_t>> indexed((size_t)n_frames, std::vector<uint8_t>(n_px));
+  std::vector<const uint8_t*> ptrs((size_t)n_frames);
+  for (int k = 0; k < n_frames; k++) {
+    if (!rgba8_frames[k]) return ctx ? fail(ctx, RTB_E_ARG, "null frame") : RTB_E_ARG;
+    if (ctx) {
+      const int rc = rtb_gif_index_frame(ctx, rgba8_frames[k], width, height, indexed[(size_t)k].data());
+      if (rc != RTB_OK) return rc;
+    } else {
+      gif_index_frame_host(rgba8_frames[k], width, height, indexed[(size_t)k].data());
+    }
+    ptrs[(size_t)k] = indexed[(size_t)k].data();
+  }
+  const int rc = rtb_gif_save_indexed(path, width, height, ptrs.data(), n_frames, frame_delay_cs, threads);
+  return (rc != RTB_OK && ctx) ? fail(ctx, rc, std::string("cannot write ") + path) : rc;
+}
+
+int rtb_gif_render_rotation(rtb_context* ctx, const rtb_render_params* base, int32_t n_frames, float step_deg, const char* path,
+                            int32_t frame_delay_cs, int32_t threads) {
+  if (!ctx || !base || !path || n_frames <= 0) return fail(ctx, RTB_E_ARG, "bad argument");
+  if (!ctx->has_scene) return fail(ctx, RTB_E_NOSCENE, "no scene uploaded (rtb_upload_scene)");
+  FrameParams f;
+  std::string why;
+  if (!resolve_frame(ctx->host.d, *base, f, why)) return fail(ctx, RTB_E_ARG, why);
+  const int width = f.width, height = f.height;
+  const size_t n_px = (size_t)width * height;
+  uint8_t* host = (uint8_t*)rtb_alloc_pinned(n_px * (size_t)n_frames);  // every frame's indices: 1 byte per pixel
+  if (!host) return fail(ctx, RTB_E_CUDA, "cannot allocate pinned host memory for the frames");
+  // frame k becomes ready when its rtb_render_end returned; workers compress ready frames in order of arrival
+  std::vector<std::vector<uint8_t>> compressed((size_t)n_frames);
+  std::atomic<int> n_ready{0}, next{0};
+  std::atomic<bool> abort_flag{false};
+  auto work = [&] {
+    for (int k = next.fetch_add(1); k < n_frames; k = next.fetch_add(1)) {
+      while (n_ready.load(std::memory_order_acquire) <= k) {
+        if (abort_flag.load()) return;
+        std::this_thread::yield();
+      }
+      compressed[(size_t)k].resize(gif_lzw_bound(n_px));
+      compressed[(size_t)k].resize(gif_lzw(host + (size_t)k * n_px, n_px, compressed[(size_t)k].data()));
+    }
+  };
+  const int t = gif_threads(threads, n_frames);
+  std::vector<std::thread> pool;
+  for (int i = 0; i < t; i++) pool.emplace_back(work);
+  const int in_flight = std::max(2, ctx->n_lanes);
+  std::vector<int32_t> tickets((size_t)n_frames, -1);
+  int rc = RTB_OK, ended = 0;
+  for (int k = 0; k < n_frames && rc == RTB_OK; k++) {
+    rtb_render_params p = *base;  // GifGenerator.cs:59-61: (base.x, base.y, angle)
+    const float bx = base->has_cam_rot ? base->cam_rot_euler_deg[0] : 0.0f, by = base->has_cam_rot ? base->cam_rot_euler_deg[1] : 0.0f;
+    p.has_cam_rot = 1;
+    p.cam_rot_euler_deg[0] = bx; p.cam_rot_euler_deg[1] = by; p.cam_rot_euler_deg[2] = (float)k * step_deg;
+    if (k - ended >= in_flight) {
+      rc = rtb_render_end(ctx, tickets[(size_t)ended]);
+      if (rc == RTB_OK) { ended++; n_ready.store(ended, std::memory_order_release); }
+    }
+    if (rc == RTB_OK) rc = rtb_render_begin_indexed(ctx, &p, host + (size_t)k * n_px, n_px, &tickets[(size_t)k]);
+  }
+  while (rc == RTB_OK && ended < n_frames) {
+    rc = rtb_render_end(ctx, tickets[(size_t)ended]);
+    if (rc == RTB_OK) { ended++; n_ready.store(ended, std::memory_order_release); }
+  }
+  if (rc != RTB_OK) abort_flag.store(true);
+  for (auto& th : pool) th.join();
+  if (rc != RTB_OK) { rtb_synchronize(ctx); rtb_free_pinned(host); return rc; }
+  std::vector<uint8_t> file;
+  gif_append_prologue(file, width, height);
+  for (int k = 0; k < n_frames; k++) gif_append_frame(file, width, height, compressed[(size_t)k].data(), compressed[(size_t)k].size(), frame_delay_cs);
+  file.push_back(0x3B);
+  rtb_free_pinned(host);
+  FILE* out = std::fopen(path, "wb");
+  if (!out) return fail(ctx, RTB_E_IO, std::string("cannot open ") + path);
+  const size_t wrote = std::fwrite(file.data(), 1, file.size(), out);
+  if (std::fclose(out) != 0 || wrote != file.size()) return fail(ctx, RTB_E_IO, std::string("cannot write ") + path);
+  return RTB_OK;
+}
 
 }  // extern "C"

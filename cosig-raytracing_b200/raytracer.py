@@ -195,6 +195,16 @@ class RayTracer:
     def RenderEnd(self, ticket: int) -> None:
         self._check(self._lib.rtb_render_end(self._ctx, ticket))
 
+    def RenderBeginIndexed(self, scene, settings, out: np.ndarray) -> int:
+        """RenderBegin whose frame is mapped to GIF palette indices on the device (GifGenerator.ConvertToIndexed): `out` receives
+        width*height bytes, top row first."""
+        if not self._ensure_scene(scene):
+            raise RtbError(abi.RTB_E_NOSCENE, "no scene")
+        p = self._params(settings)
+        ticket = C.c_int32()
+        self._check(self._lib.rtb_render_begin_indexed(self._ctx, C.byref(p), out.ctypes.data, out.nbytes, C.byref(ticket)))
+        return ticket.value
+
     def RenderToTexture(self, scene, settings, dst_ptr: Optional[int] = None, dst_bytes: int = 0, sync: bool = True) -> Optional[DeviceTexture]:
         """RayTracer.cs:82-202: render and leave the frame on the device.  With dst_ptr the frame (or this rank's bands) is
         written there — a torch tensor's data_ptr(), or a peer mapping from frame_import for the NVLink gather."""

@@ -149,7 +149,7 @@ int rtb_render(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, siz
 /* Pipelined RenderAsync for hosts that render a stream of frames (the reference's realtime mode calls its renderer once per
  * Unity frame, SceneBuilder.cs:521-537): rtb_render_begin enqueues the frame and its readback into `rgba8` (page-locked memory,
  * see rtb_alloc_pinned, for a truly asynchronous copy) and returns a ticket; rtb_render_end blocks until that frame is in
- * `rgba8`.  Up to 8 frames may be in flight; `rgba8` must stay valid until its rtb_render_end.  Single-device contexts. */
+ * `rgba8`.  Up to 16 frames may be in flight; `rgba8` must stay valid until its rtb_render_end.  Single-device contexts. */
 int rtb_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* ticket);
 int rtb_render_end(rtb_context* ctx, int32_t ticket);
 
@@ -219,6 +219,36 @@ int rtb_scene_load(const char* path, rtb_scene** out, char* err, size_t err_cap)
 int rtb_scene_parse(const char* text, size_t len, rtb_scene** out, char* err, size_t err_cap);
 const rtb_scene_desc* rtb_scene_get(const rtb_scene* s);
 void rtb_scene_free(rtb_scene* s);
+
+/* ---- GIF sweep: GifGenerator, Assets/Services/GifGenerator.cs -------------------------------------------------
+ * The reference renders 36 frames (camera rotation override Z = 0, 10, ... 350 degrees, :49-63), maps every pixel to a
+ * 6x6x6 colour-cube index with a vertical flip (ConvertToIndexed :346-369), LZW-compresses each frame (:411-501, Parallel.For
+ * over frames :123-130) and writes GIF89a (:82-155).  Here the palette mapping is a device kernel, so a frame leaves the GPU
+ * as 1 byte per pixel; LZW runs on host threads while later frames render.  Output files are byte-identical to the reference
+ * algorithm's (tests/test_gif_*.py). */
+void rtb_gif_color_table(uint8_t rgb768[768]);                       /* GenerateColorTable :219-247 */
+int64_t rtb_gif_lzw_bound(int64_t n);                                /* capacity rtb_gif_lzw needs for n input bytes */
+int64_t rtb_gif_lzw(const uint8_t* indexed, int64_t n, uint8_t* out, int64_t capacity); /* LzwCompress :411-501 (host); bytes written or < 0 */
+/* ConvertToIndexed :346-369 on the device: host RGBA8 frame (row 0 = bottom, Texture2D order) -> width*height palette indices,
+ * top row first. */
+int rtb_gif_index_frame(rtb_context* ctx, const uint8_t* rgba8, int32_t width, int32_t height, uint8_t* indexed);
+/* The same for a frame already on device 0 (e.g. the target of rtb_render_device): device pointers, asynchronous on
+ * rtb_get_stream(ctx, 0). */
+int rtb_gif_index_device(rtb_context* ctx, const void* rgba8_device, int32_t width, int32_t height, void* indexed_device);
+/* Like rtb_render_begin, but the frame is converted on the device (ConvertToIndexed) and only the width*height palette
+ * indices are read back into `indexed` (top row first).  Shares the ticket ring with rtb_render_begin; wait with rtb_render_end. */
+int rtb_render_begin_indexed(rtb_context* ctx, const rtb_render_params* p, uint8_t* indexed, size_t bytes, int32_t* ticket);
+/* SaveGifAsync :82-155 for frames given as palette indices (top row first) / as RGBA8 Texture2D data (row 0 = bottom; ctx may
+ * be NULL: then the palette mapping also runs on the host).  threads <= 0: all host cores. */
+int rtb_gif_save_indexed(const char* path, int32_t width, int32_t height, const uint8_t* const* frames, int32_t n_frames,
+                         int32_t frame_delay_cs, int32_t threads);
+int rtb_gif_save(rtb_context* ctx, const char* path, int32_t width, int32_t height, const uint8_t* const* rgba8_frames, int32_t n_frames,
+                 int32_t frame_delay_cs, int32_t threads);
+/* GenerateRotationFrames :40-72 + SaveGifAsync fused: frame k renders with CameraRotationOverride = (base.x, base.y, k*step_deg)
+ * (the reference: n_frames 36, step 10), is palette-mapped on the device, read back as indices and compressed on a host thread
+ * while the following frames render; the file is written when all frames are in.  Honors the cancel flag (RTB_E_CANCELLED). */
+int rtb_gif_render_rotation(rtb_context* ctx, const rtb_render_params* base, int32_t n_frames, float step_deg, const char* path,
+                            int32_t frame_delay_cs, int32_t threads);
 
 int rtb_api_version(void);
 

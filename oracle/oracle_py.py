@@ -28,9 +28,8 @@ class Counters(C.Structure):
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "oracle.cpp")
-    hdr = os.path.join(_HERE, "..", "include", "rtb.h")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    srcs = [os.path.join(_HERE, "oracle.cpp"), os.path.join(_HERE, "gif_oracle.cpp"), os.path.join(_HERE, "..", "include", "rtb.h")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -67,6 +66,11 @@ def lib():
                                  C.POINTER(Counters)]
         L.orc_primary_ray.argtypes = [VP, C.POINTER(_abi.RenderParams), C.c_int32, C.c_int32, VP, VP]
         L.orc_brute_closest.argtypes = [VP, VP, VP, VP, VP, C.c_int32]
+        L.orc_gif_color_table.argtypes = [VP]
+        L.orc_gif_convert_to_indexed.argtypes = [VP, C.c_int32, C.c_int32, VP]
+        L.orc_gif_lzw.argtypes = [VP, C.c_int64, VP, C.c_int64]
+        L.orc_gif_lzw.restype = C.c_int64
+        L.orc_gif_save.argtypes = [C.c_char_p, C.c_int32, C.c_int32, VP, C.c_int32, C.c_int32]
         _lib = L
     return _lib
 
@@ -181,3 +185,37 @@ class OracleScene:
         ids = np.zeros(cap, np.int32)
         n = lib().orc_brute_closest(self.h, o.ctypes.data, d.ctypes.data, C.byref(t), ids.ctypes.data, cap)
         return t.value, ids[:min(n, cap)].copy(), n
+
+
+# ---- GIF writer restatement (oracle/gif_oracle.cpp: GifGenerator.cs) ------------------------------------------------------
+def gif_color_table() -> np.ndarray:
+    t = np.zeros(768, np.uint8)
+    lib().orc_gif_color_table(t.ctypes.data)
+    return t
+
+
+def gif_convert_to_indexed(rgba8: np.ndarray) -> np.ndarray:
+    """rgba8: [h, w, 4] uint8, row 0 = bottom.  Returns [h, w] palette indices, top row first."""
+    rgba8 = np.ascontiguousarray(rgba8, np.uint8)
+    h, w = rgba8.shape[:2]
+    out = np.zeros((h, w), np.uint8)
+    lib().orc_gif_convert_to_indexed(rgba8.ctypes.data, w, h, out.ctypes.data)
+    return out
+
+
+def gif_lzw(indexed: np.ndarray) -> bytes:
+    data = np.ascontiguousarray(indexed, np.uint8).reshape(-1)
+    cap = (data.size + 2) * 2 + 16
+    out = np.zeros(cap, np.uint8)
+    n = lib().orc_gif_lzw(data.ctypes.data, data.size, out.ctypes.data, cap)
+    assert 0 <= n <= cap
+    return out[:n].tobytes()
+
+
+def gif_save(path: str, frames: np.ndarray, frame_delay: int = 10) -> None:
+    """frames: [n, h, w, 4] uint8 RGBA, row 0 = bottom (Texture2D order)."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape[:3]
+    rc = lib().orc_gif_save(path.encode(), w, h, frames.ctypes.data, n, frame_delay)
+    if rc != 0:
+        raise OSError(f"orc_gif_save failed: {rc}")

@@ -77,8 +77,8 @@ def test_packed_scenes_match_reference_files(oracle, name):
 def test_library_exports_every_declared_symbol(pkg):
     lib = abi.load()
     header = open(os.path.join(ROOT, "include", "rtb.h")).read()
-    declared = set(re.findall(r"^(?:int|void\*?|const [a-z_ ]+\*)\s+(rtb_[a-z0-9_]+)\s*\(", header, re.M))
-    assert len(declared) >= 29
+    declared = set(re.findall(r"^(?:int|int64_t|void\*?|const [a-z_ ]+\*)\s+(rtb_[a-z0-9_]+)\s*\(", header, re.M))
+    assert len(declared) >= 37
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in rtb.h but not exported"
     assert declared == set(abi.SYMBOLS), declared ^ set(abi.SYMBOLS)

@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""tools/gif_bench.py — measurement of the GIF sweep: the reference's 36-frame rotation GIF of the sample scene.
+
+    python tools/gif_bench.py [--width 1920 --height 1080 --depth 6] [--cpu-frames 2]
+
+Prints one JSON line: seconds and frames/s of (a) the fused library call rtb_gif_render_rotation (render -> device palette
+kernel -> 1 byte/pixel readback -> host LZW threads -> file), (b) the two-step mirror (36 pipelined RGBA readbacks, then
+SaveGif), the k_palette kernel alone against the HBM roofline (5 algorithmic bytes per pixel: 4 read, 1 written), and the CPU
+oracle's restatement of GifGenerator (render + ConvertToIndexed + LzwCompress, `--cpu-frames` frames, all host threads for the
+render, one thread for the GIF part as written in the restatement) extrapolated to 36 frames.
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--depth", type=int, default=6)
+    ap.add_argument("--scene", default="test_scene_1")
+    ap.add_argument("--cpu-frames", type=int, default=2)
+    ap.add_argument("--repeat", type=int, default=3)
+    args = ap.parse_args()
+
+    import torch
+    abi = importlib.import_module("cosig-raytracing_b200.abi")
+    rt_mod = importlib.import_module("cosig-raytracing_b200.raytracer")
+    scene_mod = importlib.import_module("cosig-raytracing_b200.scene")
+    synth = importlib.import_module("cosig-raytracing_b200.synth")
+    gif = importlib.import_module("cosig-raytracing_b200.gif_generator")
+    if not torch.cuda.is_available():
+        raise SystemExit("needs a CUDA device")
+    w, h = args.width, args.height
+    obj = synth.sample_scene(args.scene)
+    st = scene_mod.RenderSettings(ResolutionOverride=(w, h), MaxDepth=args.depth, CameraPositionOverride=(0.0, 0.0, 0.0),
+                                  CameraRotationOverride=(-60.0, 0.0, 0.0))
+    rt = rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH)
+    g = gif.GifGenerator(rt, obj)
+    tmp = tempfile.mkdtemp()
+    fused_path, two_path = os.path.join(tmp, "fused.gif"), os.path.join(tmp, "two.gif")
+    g.RenderRotationGif(st, fused_path)  # warm-up: scene upload, queues, pinned memory
+    fused = []
+    for _ in range(args.repeat):
+        t0 = time.perf_counter()
+        g.RenderRotationGif(st, fused_path)
+        fused.append(time.perf_counter() - t0)
+    two = []
+    for _ in range(args.repeat):
+        t0 = time.perf_counter()
+        frames = g.GenerateRotationFrames(st)
+        t1 = time.perf_counter()
+        g.SaveGif(frames, two_path)
+        two.append((time.perf_counter() - t0, t1 - t0))
+    same = open(fused_path, "rb").read() == open(two_path, "rb").read()
+
+    # k_palette alone: CUDA events on the library's stream, frame resident on the device; every launch is preceded by a 256 MB
+    # write that evicts the frame from the 126 MB L2, so the kernel streams from HBM
+    lib = abi.load()
+    stream = torch.cuda.ExternalStream(rt.stream(0))
+    frame = torch.randint(0, 256, (h, w, 4), dtype=torch.uint8, device="cuda")
+    out = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    pal_ms = []
+    with torch.cuda.stream(stream):
+        for i in range(8):
+            flush.fill_(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rt._check(lib.rtb_gif_index_device(rt._ctx, frame.data_ptr(), w, h, out.data_ptr()))
+            e1.record(stream)
+            stream.synchronize()
+            if i >= 3:
+                pal_ms.append(e0.elapsed_time(e1))
+    idx_host = np.zeros((h, w), np.uint8)
+    host_frame = frame.cpu().numpy()
+    rt._check(lib.rtb_gif_index_frame(rt._ctx, host_frame.ctypes.data, w, h, idx_host.ctypes.data))
+    assert (idx_host == out.cpu().numpy()).all()
+    peak = 6454.9
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except (OSError, KeyError, ValueError):
+        pass
+    pal = {"ms": float(np.mean(pal_ms)), "bytes": 5 * w * h, "achieved_gbs": 5 * w * h / (np.mean(pal_ms) * 1e-3) / 1e9, "peak_gbs": peak}
+    pal["frac"] = pal["achieved_gbs"] / peak
+
+    # CPU oracle on a bounded sample
+    from oracle import oracle_py as O
+    O.build()
+    packed = scene_mod.pack_scene(obj)
+    osc = O.OracleScene.from_desc(packed.desc)
+    cpu_render = cpu_gif = 0.0
+    cpu_frames = []
+    for k in range(args.cpu_frames):
+        s = scene_mod.RenderSettings(ResolutionOverride=(w, h), MaxDepth=args.depth, CameraPositionOverride=(0.0, 0.0, 0.0),
+                                     CameraRotationOverride=(-60.0, 0.0, 10.0 * k))
+        t0 = time.perf_counter()
+        r = osc.render(s.to_params(), threads=0)
+        cpu_render += time.perf_counter() - t0
+        cpu_frames.append(r["rgba8"])
+    t0 = time.perf_counter()
+    O.gif_save(os.path.join(tmp, "oracle.gif"), np.stack(cpu_frames), 10)
+    cpu_gif = time.perf_counter() - t0
+    cpu_total_36 = (cpu_render + cpu_gif) / max(1, args.cpu_frames) * 36
+
+    line = {
+        "metric": "36-frame rotation GIF, seconds", "workload": f"{args.scene} {w}x{h} depth {args.depth}, 36 frames (GifGenerator.cs:40-155)",
+        "fused_s": min(fused), "fused_frames_per_s": 36 / min(fused),
+        "two_step_s": min(t for t, _ in two), "two_step_render_s": min(r for _, r in two), "files_identical": same,
+        "gif_bytes": os.path.getsize(fused_path),
+        "d2h_bytes_per_frame": {"fused": w * h, "two_step": w * h * 4},
+        "cpu_oracle": {"frames_timed": args.cpu_frames, "render_s_per_frame": cpu_render / max(1, args.cpu_frames),
+                       "gif_s_per_frame": cpu_gif / max(1, args.cpu_frames), "extrapolated_36_frames_s": cpu_total_36, "kind": "port"},
+        "speedup_vs_cpu_oracle": cpu_total_36 / min(fused),
+        "k_palette_roofline": pal,
+    }
+    print(json.dumps(line), flush=True)
+    rt.close()
+
+
+if __name__ == "__main__":
+    main()
