@@ -66,6 +66,9 @@ internal static class RtbNative
     [DllImport(Lib)] public static extern unsafe int rtb_set_cancel_flag(IntPtr ctx, int* flag);
     [DllImport(Lib)] public static extern IntPtr rtb_last_error(IntPtr ctx);
     [DllImport(Lib)] public static extern void rtb_abi_sizes(int[] sizes, int n);
+    // GIF sweep (GifGenerator.cs): device palette mapping + host LZW inside the library
+    [DllImport(Lib)] public static extern unsafe int rtb_gif_save(IntPtr ctx, string path, int width, int height, byte** rgba8Frames, int nFrames, int frameDelayCs, int threads);
+    [DllImport(Lib)] public static extern int rtb_gif_render_rotation(IntPtr ctx, ref RenderParams baseParams, int nFrames, float stepDeg, string path, int frameDelayCs, int threads);
 }
 
 public sealed class RayTracerNative : IDisposable
@@ -154,4 +157,27 @@ public sealed class RayTracerNative : IDisposable
     }
 
     public void Dispose() { if (ctx != IntPtr.Zero) { RtbNative.rtb_destroy(ctx); ctx = IntPtr.Zero; } }
+
+    // ---- what GifGenerator.cs needs beyond RenderAsync ---------------------------------------------------------------------
+    // GifGenerator.SaveGifAsync (:82-155) body becomes one call: pin the frames' raw RGBA32 data (GetRawTextureData<byte>()),
+    // pass the pointers.  The palette mapping (:346-369) runs on the GPU, LZW (:411-501) on the library's host threads.
+    public unsafe void SaveGif(List<Texture2D> frames, string filePath, int frameDelay = 10)
+    {
+        if (frames == null || frames.Count == 0) return;                              // :84
+        var ptrs = stackalloc byte*[frames.Count];
+        for (int i = 0; i < frames.Count; i++)
+            ptrs[i] = (byte*)Unity.Collections.LowLevel.Unsafe.NativeArrayUnsafeUtility.GetUnsafeReadOnlyPtr(frames[i].GetRawTextureData<byte>());
+        int rc = RtbNative.rtb_gif_save(ctx, filePath, frames[0].width, frames[0].height, ptrs, frames.Count, frameDelay, 0);
+        if (rc != 0) throw new InvalidOperationException(Marshal.PtrToStringAnsi(RtbNative.rtb_last_error(ctx)));
+    }
+
+    // GenerateRotationFrames (:40-72) + SaveGifAsync fused: SceneBuilder.OnGifClicked (SceneBuilder.cs:965-1030) can call this
+    // instead of the two steps when it does not need the frames for playback.
+    public void RenderRotationGif(ObjectData scene, RenderSettings baseSettings, string filePath, int frameDelay = 10)
+    {
+        EnsureScene(scene);
+        var p = ToParams(baseSettings);
+        int rc = RtbNative.rtb_gif_render_rotation(ctx, ref p, 36, 10f, filePath, frameDelay, 0);
+        if (rc != 0) throw new InvalidOperationException(Marshal.PtrToStringAnsi(RtbNative.rtb_last_error(ctx)));
+    }
 }

@@ -17,6 +17,7 @@
 #include <array>
 #include <cstring>
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <optional>
 #include <stdexcept>
@@ -200,6 +201,7 @@ class RayTracer {
 
   rtb_stats Stats() { rtb_stats s; check(rtb_get_stats(ctx_, &s)); return s; }
   rtb_context* Context() { return ctx_; }
+  bool EnsureScene(const ObjectData* scene) { return ensure_scene(scene); }  // uploads when the scene object changed (RayTracer.cs:118-123)
 
  private:
   bool ensure_scene(const ObjectData* scene) {
@@ -220,6 +222,55 @@ class RayTracer {
   const ObjectData* cached_ = nullptr;
   bool needs_rebuild_ = true;
   std::unique_ptr<PackedScene> packed_;
+};
+
+// GifGenerator, Assets/Services/GifGenerator.cs:17-31: the 36-frame rotation sweep and the GIF89a writer.
+class GifGenerator {
+ public:
+  GifGenerator(RayTracer& rayTracer, const ObjectData* scene) : rayTracer_(rayTracer), scene_(scene) {}
+
+  // GenerateRotationFrames :40-72: frame k renders with CameraRotationOverride = (base.x, base.y, 10 k), k = 0..35.
+  std::vector<Texture2D> GenerateRotationFrames(const RenderSettings& baseSettings, const std::function<void(float, const std::string&)>& progress = nullptr,
+                                                const volatile int32_t* cancel = nullptr) {
+    std::vector<Texture2D> frames;
+    const int totalFrames = 36;
+    for (int angle = 0; angle < 360; angle += 10) {
+      if (cancel && *cancel) break;
+      const int frameIndex = angle / 10;
+      if (progress) progress((float)frameIndex / totalFrames, "Rendering frame " + std::to_string(frameIndex + 1) + "/" + std::to_string(totalFrames) + " (Z=" + std::to_string(angle) + "\xC2\xB0)");
+      RenderSettings frameSettings = baseSettings;
+      const Vector3 baseRotation = baseSettings.CameraRotationOverride.value_or(Vector3{0, 0, 0});
+      frameSettings.CameraRotationOverride = Vector3{baseRotation.x, baseRotation.y, (float)angle};
+      auto frame = rayTracer_.RenderAsync(scene_, frameSettings, cancel);
+      if (frame) frames.push_back(std::move(*frame));
+    }
+    return frames;
+  }
+
+  // SaveGif :160-184 / SaveGifAsync :82-155: palette mapping on the device, LZW on host threads inside the library.
+  void SaveGif(const std::vector<Texture2D>& frames, const std::string& filePath, int frameDelay = 10) {
+    if (frames.empty()) return;
+    std::vector<const uint8_t*> ptrs;
+    for (const Texture2D& f : frames) {
+      if (f.width != frames[0].width || f.height != frames[0].height) throw Error(RTB_E_ARG, "frames differ in size");
+      ptrs.push_back(f.pixels.data());
+    }
+    const int rc = rtb_gif_save(rayTracer_.Context(), filePath.c_str(), frames[0].width, frames[0].height, ptrs.data(), (int32_t)ptrs.size(), frameDelay, 0);
+    if (rc != RTB_OK) throw Error(rc, rtb_last_error(rayTracer_.Context()));
+  }
+
+  // Both halves in one library call: frames leave the GPU as palette indices (1 byte per pixel) and are compressed while the
+  // following frames render.
+  void RenderRotationGif(const RenderSettings& baseSettings, const std::string& filePath, int frameDelay = 10, int totalFrames = 36, float stepDeg = 10.0f) {
+    if (!rayTracer_.EnsureScene(scene_)) throw Error(RTB_E_NOSCENE, "no scene");
+    const rtb_render_params p = baseSettings.ToParams();
+    const int rc = rtb_gif_render_rotation(rayTracer_.Context(), &p, totalFrames, stepDeg, filePath.c_str(), frameDelay, 0);
+    if (rc != RTB_OK) throw Error(rc, rtb_last_error(rayTracer_.Context()));
+  }
+
+ private:
+  RayTracer& rayTracer_;
+  const ObjectData* scene_;
 };
 
 // SceneService.cs:26 — a missing file yields an empty ObjectData, as in the reference (:28-33).

@@ -3,10 +3,12 @@
 //
 //   host_mirror_test host  <scene.txt>                 host-only checks (no GPU): parse, pack, resolve; RayTracer() must fail loudly
 //   host_mirror_test render <scene.txt> <out.rgba> W H depth   RenderAsync -> raw RGBA8 (row 0 = bottom), then cache checks
+//   host_mirror_test gif    <scene.txt> <out.gif>  W H depth   GifGenerator: 36-frame sweep -> SaveGif, and the fused RenderRotationGif
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iterator>
 
 #include "../../include/rtb_raytracer.hpp"
 
@@ -48,6 +50,25 @@ int main(int argc, char** argv) {
   REQUIRE(argc >= 7);
   settings.ResolutionOverride = std::array<int, 2>{std::atoi(argv[4]), std::atoi(argv[5])};
   settings.MaxDepth = std::atoi(argv[6]);
+  if (mode == "gif") {  // SceneBuilder.OnGifClicked, SceneBuilder.cs:965-1030
+    RayTracer rt;
+    GifGenerator gen(rt, &scene);
+    settings.CameraPositionOverride = Vector3{0, 0, 0};
+    settings.CameraRotationOverride = Vector3{-60, 0, 0};
+    int reports = 0;
+    std::vector<Texture2D> frames = gen.GenerateRotationFrames(settings, [&](float, const std::string&) { reports++; });
+    REQUIRE(frames.size() == 36 && reports == 36);
+    gen.SaveGif(frames, argv[3]);
+    const std::string fused = std::string(argv[3]) + ".fused";
+    gen.RenderRotationGif(settings, fused);
+    std::ifstream a(argv[3], std::ios::binary), b(fused, std::ios::binary);
+    const std::string sa((std::istreambuf_iterator<char>(a)), std::istreambuf_iterator<char>()), sb((std::istreambuf_iterator<char>(b)), std::istreambuf_iterator<char>());
+    REQUIRE(sa.size() > 800 && sa == sb);
+    gen.SaveGif({}, std::string(argv[3]) + ".none");  // empty list: no file (GifGenerator.cs:162)
+    REQUIRE(!std::ifstream(std::string(argv[3]) + ".none").good());
+    std::printf("gif OK %zu bytes\n", sa.size());
+    return 0;
+  }
   RayTracer rt;
   REQUIRE(!rt.RenderAsync(nullptr, settings));  // nothing to render -> null, like the reference
   auto tex = rt.RenderAsync(&scene, settings);

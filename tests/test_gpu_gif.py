@@ -95,3 +95,24 @@ def test_rotation_gif_honours_frame_count_step_and_delay(rt, oracle, tmp_path):
     ref = str(tmp_path / "five_oracle.gif")
     oracle.gif_save(ref, np.stack(frames), 4)
     assert open(path, "rb").read() == open(ref, "rb").read()
+
+
+def test_cpp_gif_generator_mirror(oracle, tmp_path):
+    """include/rtb_raytracer.hpp: rtb::GifGenerator (sweep + SaveGif, and the fused call) writes the oracle's file."""
+    import subprocess
+    from test_host_cpu import build_cpp_test
+    exe = build_cpp_test()
+    obj = synth.sample_scene("test_scene_1")
+    scene_file, out = tmp_path / "scene.txt", tmp_path / "out.gif"
+    scene_file.write_bytes(synth.scene_to_text(obj).encode())
+    r = subprocess.run([exe, "gif", str(scene_file), str(out), "96", "72", "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    packed = scene_mod.pack_scene(obj)
+    osc = oracle.OracleScene.from_desc(packed.desc)
+    frames = []
+    for k in range(36):
+        st = scene_mod.RenderSettings(ResolutionOverride=(96, 72), MaxDepth=2, CameraPositionOverride=(0.0, 0.0, 0.0), CameraRotationOverride=(-60.0, 0.0, 10.0 * k))
+        frames.append(osc.render(st.to_params())["rgba8"])
+    ref = str(tmp_path / "oracle.gif")
+    oracle.gif_save(ref, np.stack(frames), 10)
+    assert open(out, "rb").read() == open(ref, "rb").read()
