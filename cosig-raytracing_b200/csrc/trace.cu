@@ -41,6 +41,11 @@ constexpr int kBlock = 256;
 #define RTB_TRAVERSE_MIN_BLOCKS 10
 #endif
 constexpr int kTravBlock = RTB_TRAVERSE_BLOCK;
+// Streaming kernels that compact into queues (k_raygen, k_shade): threads per block = length of a contiguous queue run.
+#ifndef RTB_STREAM_BLOCK
+#define RTB_STREAM_BLOCK 256
+#endif
+constexpr int kStreamBlock = RTB_STREAM_BLOCK;
 constexpr int kBlockSmem = 1024;  // shared-memory staged k_traverse: one block per SM
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -66,6 +71,39 @@ __device__ __forceinline__ bool primary_ray_of_slot(const FrameParams& f, const 
   py = band_global_row(local_row, f.band_rank, f.band_world, f.band_rows);
   ray = generate_ray(f, px, py, sample);
   return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Queue reservation for the streaming kernels (k_raygen, k_shade).  One atomicAdd per WARP on a single queue counter makes
+// 10^5 same-address atomics per launch, which serialise in L2: ncu showed them as the top stall of k_shade and k_raygen
+// (profiles/r1e_ncu_shade_raygen.csv).  Here the warps of a block add their counts up in shared memory and ONE thread per
+// queue reserves the block's range: 8 times fewer atomics.  Every thread of the block must call it the same number of times
+// (block-strided loops); `it` is the caller's iteration number (buffers alternate, so two barriers per call suffice).
+// Returns the first queue index of the calling warp's entries for queue Q.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NQ>
+struct BlockReserve {
+  int32_t count[2][NQ][kStreamBlock / 32];
+  int32_t base[2][NQ];
+};
+template <int NQ>
+__device__ __forceinline__ void block_reserve(BlockReserve<NQ>& sh, int it, const unsigned (&mask)[NQ], int32_t* const (&counter)[NQ], int32_t (&first)[NQ]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, buf = it & 1;
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; q++) sh.count[buf][q][warp] = __popc(mask[q]);
+  }
+  __syncthreads();
+  if (threadIdx.x < NQ) {
+    const int q = threadIdx.x;
+    int32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < kStreamBlock / 32; w++) { const int32_t c = sh.count[buf][q][w]; sh.count[buf][q][w] = total; total += c; }
+    sh.base[buf][q] = total ? atomicAdd(counter[q], total) : 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NQ; q++) first[q] = sh.base[buf][q] + sh.count[buf][q][warp];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -378,10 +416,8 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
 // so it takes the background now (:364-368) and never enters the queue.  sampleColor starts at 0 (:356).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int BVH>
-__global__ void __launch_bounds__(kBlock) k_raygen(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c) {
+__global__ void __launch_bounds__(kStreamBlock) k_raygen(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c) {
   const int lane = threadIdx.x & 31;
-  const int32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-  const int32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned below = (1u << lane) - 1u;
   // root box: reference BVH = node 0's own box; LBVH = union of the root record's two (padded) child boxes
   f3 rmn = mk3(0.0f, 0.0f, 0.0f), rmx = rmn;
@@ -404,8 +440,10 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const FrameParams f, const Sc
   }
   const bool empty = (BVH == RTB_BVH_REFERENCE) ? s.n_nodes == 0 : s.n_tris == 0;
   unsigned n_valid = 0;
-  for (int32_t base = warp_id * 32; base < c.n_slots; base += warps_total * 32) {
-    const int32_t slot = base + lane;
+  __shared__ BlockReserve<1> reserve;
+  int it = 0;
+  for (int32_t base = blockIdx.x * kStreamBlock; base < c.n_slots; base += gridDim.x * kStreamBlock, it++) {  // block-uniform trip count
+    const int32_t slot = base + threadIdx.x;
     Ray ray;
     int px, py, sample;
     const bool valid = primary_ray_of_slot(f, c, slot, ray, px, py, sample);
@@ -424,12 +462,12 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const FrameParams f, const Sc
       const f3 first = survives ? mk3(0.0f, 0.0f, 0.0f) : mk3(0.0f, 0.0f, 0.0f) + bg;
       q.accum[slot] = make_float4(first.x, first.y, first.z, 0.0f);
     }
-    const unsigned m = __ballot_sync(kFull, survives);
-    int32_t b = 0;
-    if (lane == 0 && m) b = atomicAdd(&RTB_CNT_RAY(q, 0), __popc(m));
-    b = __shfl_sync(kFull, b, 0);
+    const unsigned m[1] = {__ballot_sync(kFull, survives)};
+    int32_t* const counters[1] = {&RTB_CNT_RAY(q, 0)};
+    int32_t first[1];
+    block_reserve<1>(reserve, it, m, counters, first);
     if (survives) {
-      const int32_t at = b + __popc(m & below);
+      const int32_t at = first[0] + __popc(m[0] & below);
       __stcs(&q.ray_o[0][at], make_float4(ray.o.x, ray.o.y, ray.o.z, __int_as_float(slot)));
       __stcs(&q.ray_d[0][at], make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f));
       __stcs(&q.ray_att[0][at], make_float4(1.0f, 1.0f, 1.0f, 0.0f));
@@ -524,20 +562,23 @@ __device__ __forceinline__ void shade_hit(const FrameParams& f, const SceneView&
 // ---------------------------------------------------------------------------------------------------------------------
 // k_shade: everything the reference does with a closest-hit result at one depth, for queues of at least `tail_max` rays.
 // ---------------------------------------------------------------------------------------------------------------------
+#ifndef RTB_SHADE_MIN_BLOCKS
+#define RTB_SHADE_MIN_BLOCKS (1024 / RTB_STREAM_BLOCK)  /* 64 registers: measured best (profiles/r1e_sweep_shade*.log) */
+#endif
 template <bool ANALYTIC>
-__global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth,
+__global__ void __launch_bounds__(kStreamBlock, RTB_SHADE_MIN_BLOCKS) k_shade(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c, const int depth,
                                                   const int32_t tail_max) {
   const int lane = threadIdx.x & 31;
   const int32_t n = RTB_CNT_RAY(q, depth);
   if (n < tail_max) return;  // k_tail finishes these paths
   const int in_q = depth & 1, out_q = in_q ^ 1;
-  const int32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-  const int32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned below = (1u << lane) - 1u;
   unsigned n_hits = 0;
+  __shared__ BlockReserve<2> reserve;
+  int it = 0;
 
-  for (int32_t base = warp_id * 32; base < n; base += warps_total * 32) {
-    const int32_t idx = base + lane;
+  for (int32_t base = blockIdx.x * kStreamBlock; base < n; base += gridDim.x * kStreamBlock, it++) {  // block-uniform trip count
+    const int32_t idx = base + threadIdx.x;
     const bool active = idx < n;
     int32_t slot = idx;
     int px = 0, py = 0, sample = 0;
@@ -574,16 +615,14 @@ __global__ void __launch_bounds__(kBlock) k_shade(const FrameParams f, const Sce
         q.accum[slot] = make_float4(sum.x, sum.y, sum.z, 0.0f);
       }
     }
-    // queue compaction: one atomicAdd per warp and queue
+    // queue compaction: warp ballots, one atomicAdd per BLOCK and queue
     const unsigned m_sh = __ballot_sync(kFull, o.emit_shadow);
     const unsigned m_nx = __ballot_sync(kFull, o.emit_ray);
-    int32_t b_sh = 0, b_nx = 0;
-    if (lane == 0) {
-      if (m_sh) b_sh = atomicAdd(&RTB_CNT_SHADOW(q, depth), __popc(m_sh));
-      if (m_nx) b_nx = atomicAdd(&RTB_CNT_RAY(q, depth + 1), __popc(m_nx));
-    }
-    b_sh = __shfl_sync(kFull, b_sh, 0);
-    b_nx = __shfl_sync(kFull, b_nx, 0);
+    const unsigned masks[2] = {m_sh, m_nx};
+    int32_t* const counters[2] = {&RTB_CNT_SHADOW(q, depth), &RTB_CNT_RAY(q, depth + 1)};
+    int32_t first[2];
+    block_reserve<2>(reserve, it, masks, counters, first);
+    const int32_t b_sh = first[0], b_nx = first[1];
     if (o.emit_shadow) {
       const int32_t at = b_sh + __popc(m_sh & below);
       __stcs(&q.sh_o[at], make_float4(o.sh_origin.x, o.sh_origin.y, o.sh_origin.z, o.sh_dist));
@@ -741,8 +780,8 @@ int traverse_blocks_per_sm(int bvh) {
 }
 
 void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st) {
-  if (bvh == RTB_BVH_REFERENCE) k_raygen<RTB_BVH_REFERENCE><<<grid, kBlock, 0, st>>>(f, s, q, c);
-  else k_raygen<RTB_BVH_LBVH><<<grid, kBlock, 0, st>>>(f, s, q, c);
+  if (bvh == RTB_BVH_REFERENCE) k_raygen<RTB_BVH_REFERENCE><<<grid * kBlock / kStreamBlock, kStreamBlock, 0, st>>>(f, s, q, c);
+  else k_raygen<RTB_BVH_LBVH><<<grid * kBlock / kStreamBlock, kStreamBlock, 0, st>>>(f, s, q, c);
 }
 
 size_t traverse_smem_bytes(int bvh, const SceneView& s) {
@@ -772,8 +811,8 @@ void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth,
 
 void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,
                   cudaStream_t st) {
-  if (s.n_prims > 0) k_shade<true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
-  else k_shade<false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+  if (s.n_prims > 0) k_shade<true><<<grid * kBlock / kStreamBlock, kStreamBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+  else k_shade<false><<<grid * kBlock / kStreamBlock, kStreamBlock, 0, st>>>(f, s, q, c, depth, tail_max);
 }
 
 void launch_tail(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,
