@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--prim", default="tessellated", choices=["tessellated", "analytic"],
                     help="analytic: spheres / boxes are intersected analytically (SURVEY A13) instead of tessellated like the reference")
     ap.add_argument("--band-rows", type=int, default=8, help="N > 1: rows per band (multiple of 4); band b is rendered by rank b % N")
+    ap.add_argument("--emulate-world", type=int, default=0,
+                    help="diagnostic, N = 1 only: render just rank 0's bands of an N-way sharded frame (to profile one rank's share under ncu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--out-png", default=None, help="rank 0 writes the last frame here")
     args = ap.parse_args()
@@ -201,6 +203,9 @@ def main():
         run_reference(args, rank, world)
         return
 
+    if world >= 4:  # a rank's share of the frame is short: more lanes (streams with their own queues) overlap its per-depth tails (+5 % at N = 8)
+        os.environ.setdefault("RTB_LANES", "6")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version / debug lines must not share stdout with the JSON line
     import torch
     import torch.distributed as dist
     abi = importlib.import_module("cosig-raytracing_b200.abi")
@@ -230,6 +235,9 @@ def main():
     p = st.to_params()
     BR = args.band_rows
     local = None
+    if world == 1 and args.emulate_world > 1:
+        p.band_rank, p.band_world, p.band_rows = 0, args.emulate_world, BR
+        args.no_cpu_baseline = True
     if world > 1:
         p.band_rank, p.band_world, p.band_rows = rank, world, BR
     if world > 1 and args.gather == "peer":
@@ -273,8 +281,10 @@ def main():
     torch.cuda.synchronize(); rt.synchronize(); barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
+    t_enq = time.perf_counter()
     for _ in range(args.steps):
         step_device(sync=False)
+    enqueue_ms = (time.perf_counter() - t_enq) / args.steps * 1e3  # host time to enqueue one frame (launch-bound when ~ ms_per_step)
     rt.flush()  # the library alternates frames over two streams: make the timed stream wait for both
     ev1.record(stream)
     rt.synchronize(); torch.cuda.synchronize(); barrier()
@@ -431,7 +441,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "bvh": args.bvh, "primitives": args.prim, "rays_per_frame": rays_frame, "frame_ms": ms_per_step,
                        "sharding": f"{world} rank(s), {BR}-row bands round-robin, gather={args.gather if world > 1 else 'none'}",
-                       "rank_ms_per_step": [round(x, 4) for x in rank_ms],
+                       "rank_ms_per_step": [round(x, 4) for x in rank_ms], "host_enqueue_ms_per_frame": round(enqueue_ms, 4),
+                       **({"emulated": f"rank 0 of {args.emulate_world} only (diagnostic run)"} if world == 1 and args.emulate_world > 1 else {}),
                        "l2": "no explicit flush: scene arrays (160 MB) plus ~1.4 GB of wavefront queues streamed per frame exceed the 126 MB L2",
                        "n_triangles": int(sl.n_triangles), "first_frame_s": first_frame_s},
             "clocks": clocks,

@@ -181,6 +181,10 @@ struct Lane {
 #ifndef RTB_REFILL_MIN
 #define RTB_REFILL_MIN 16
 #endif
+// Queues shorter than RTB_MIN_BATCHES 32-ray batches per resident warp leave the surplus blocks idle (0 = always use the whole grid).
+#ifndef RTB_MIN_BATCHES
+#define RTB_MIN_BATCHES 0
+#endif
 template <bool SMEM>
 struct RefillMin { static constexpr int value = SMEM ? 32 : RTB_REFILL_MIN; };
 
@@ -267,6 +271,12 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
   const int32_t n_shadow = depth == 0 ? 0 : RTB_CNT_SHADOW(q, depth - 1);
   const int32_t total = n_closest + n_shadow;
   const int in_q = depth & 1;
+#if RTB_MIN_BATCHES > 0
+  if (!SMEM) {  // short queue: fewer resident warps, each with several batches, balance better than one batch on every warp
+    const int32_t want_warps = max((total + 32 * RTB_MIN_BATCHES - 1) / (32 * RTB_MIN_BATCHES), (int32_t)(gridDim.x / RTB_TRAVERSE_MIN_BLOCKS) * 4);
+    if ((int32_t)(blockIdx.x * (blockDim.x >> 5)) >= want_warps && blockIdx.x != 0) return;
+  }
+#endif
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (depth > 0 && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
     if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
@@ -362,6 +372,12 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
   const int32_t n_shadow = depth == 0 ? 0 : RTB_CNT_SHADOW(q, depth - 1);
   const int32_t total = n_closest + n_shadow;
   const int in_q = depth & 1;
+#if RTB_MIN_BATCHES > 0
+  if (!SMEM) {  // short queue: fewer resident warps, each with several batches, balance better than one batch on every warp
+    const int32_t want_warps = max((total + 32 * RTB_MIN_BATCHES - 1) / (32 * RTB_MIN_BATCHES), (int32_t)(gridDim.x / RTB_TRAVERSE_MIN_BLOCKS) * 4);
+    if ((int32_t)(blockIdx.x * (blockDim.x >> 5)) >= want_warps && blockIdx.x != 0) return;
+  }
+#endif
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (depth > 0 && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
     if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
