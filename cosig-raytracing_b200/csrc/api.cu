@@ -65,6 +65,8 @@ struct DeviceState {
   bool copy_pending = false;
   void* frame_async[kMaxLanes] = {};  // frames of rtb_render_begin, rotating, so a readback never races the following frames
   size_t frame_async_bytes[kMaxLanes] = {};
+  void* gif_scratch = nullptr;        // rtb_gif_index_frame: one RGBA8 frame + its palette indices
+  size_t gif_scratch_bytes = 0;
   void* index_async[kMaxLanes] = {};  // palette-index frames of rtb_render_begin_indexed (GIF sweep), same rotation
   size_t index_async_bytes[kMaxLanes] = {};
   float* sphere_table = nullptr;
@@ -95,7 +97,7 @@ struct rtb_context {
   int n_lanes = 4;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues
   uint64_t frame_id = 0;
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
-  int32_t tail_max = 196608;  // queues smaller than this finish in k_tail (RTB_TAIL_MAX; 0 = pure wavefront)
+  int32_t tail_max = 65536;   // queues smaller than this finish in k_tail (RTB_TAIL_MAX; 0 = pure wavefront); sweep: profiles/r1e_sweep_tail_max.log
   std::vector<void*> ipc_opened;
   static constexpr int kTickets = 16;  // frames in flight through rtb_render_begin
   cudaEvent_t ticket_event[kTickets] = {};   // frame complete in its host buffer
@@ -172,6 +174,7 @@ void free_targets(DeviceState& d) {
   dfree(d.frame); d.frame_bytes = 0;
   for (int k = 0; k < DeviceState::kMaxLanes; k++) { dfree(d.frame_async[k]); d.frame_async_bytes[k] = 0; }
   for (int k = 0; k < DeviceState::kMaxLanes; k++) { dfree(d.index_async[k]); d.index_async_bytes[k] = 0; }
+  dfree(d.gif_scratch); d.gif_scratch_bytes = 0;
   dfree(d.aux_prim); dfree(d.aux_mat); dfree(d.aux_t); d.aux_px = 0;
 }
 
@@ -360,7 +363,7 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
   for (int32_t row0 = 0; row0 < local_rows; row0 += rows_per_chunk) {
     LaneState& L = d.lane[d.next_lane];
     d.last_lane = d.next_lane;
-    d.next_lane = (d.next_lane + 1) % ctx->n_lanes;
+    d.next_lane = ctx->profiling ? d.next_lane : (d.next_lane + 1) % ctx->n_lanes;  // profiling: one lane, so per-launch event intervals do not overlap
     cudaStream_t stream = L.stream;
     if (ctx->cancel && *ctx->cancel) { device_sync(d); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
     {
@@ -1043,16 +1046,20 @@ int rtb_gif_index_frame(rtb_context* ctx, const uint8_t* rgba8, int32_t width, i
   DeviceState& d = ctx->devs[0];
   CK(ctx, cudaSetDevice(d.device));
   const size_t n_px = (size_t)width * height;
-  void *src = nullptr, *dst = nullptr;
-  CK(ctx, cudaMalloc(&src, n_px * 4));
-  cudaError_t e = cudaMalloc(&dst, n_px);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(src, rgba8, n_px * 4, cudaMemcpyHostToDevice, d.stream);
-  if (e == cudaSuccess) { launch_palette(src, width, height, (uint8_t*)dst, d.stream); e = cudaGetLastError(); }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(indexed, dst, n_px, cudaMemcpyDeviceToHost, d.stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
-  cudaFree(src);
-  cudaFree(dst);
-  if (e != cudaSuccess) return fail(ctx, RTB_E_CUDA, std::string("rtb_gif_index_frame: ") + cudaGetErrorString(e));
+  if (d.gif_scratch_bytes < n_px * 5) {  // RGBA8 in + indices out, kept for the following frames of the same GIF
+    CK(ctx, cudaStreamSynchronize(d.stream));
+    dfree(d.gif_scratch);
+    d.gif_scratch_bytes = 0;
+    CK(ctx, cudaMalloc(&d.gif_scratch, n_px * 5));
+    d.gif_scratch_bytes = n_px * 5;
+  }
+  uint8_t* src = (uint8_t*)d.gif_scratch;
+  uint8_t* dst = src + n_px * 4;
+  CK(ctx, cudaMemcpyAsync(src, rgba8, n_px * 4, cudaMemcpyHostToDevice, d.stream));
+  launch_palette(src, width, height, dst, d.stream);
+  CK(ctx, cudaGetLastError());
+  CK(ctx, cudaMemcpyAsync(indexed, dst, n_px, cudaMemcpyDeviceToHost, d.stream));
+  CK(ctx, cudaStreamSynchronize(d.stream));
   return RTB_OK;
 }
 
