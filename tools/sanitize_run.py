@@ -30,6 +30,17 @@ for mode in (abi.RTB_BVH_REFERENCE, abi.RTB_BVH_LBVH):
     run(f"analytic mode{mode}", {"RTB_TAIL_MAX": "2000"}, mode, 1, s1, params(96, 64, 4, soft_shadows=1, light_size=2.0, glossy=1, roughness=0.1))
     run(f"heightfield mode{mode}", {}, mode, 0, hf, params(128, 72, 6))
     run(f"tiny mode{mode}", {}, mode, 0, tiny_scene(1), params(33, 17, 2, debug_mode=2))
+# GIF sweep: palette kernel (vector and scalar paths), indexed pipelined readback, fused rotation call
+gif = importlib.import_module("cosig-raytracing_b200.gif_generator")
+rt = rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH)
+for (h, w) in ((24, 32), (17, 19)):
+    frame = np.random.RandomState(h).randint(0, 256, size=(h, w, 4)).astype(np.uint8)
+    out = np.zeros((h, w), np.uint8)
+    rt._check(abi.load().rtb_gif_index_frame(rt._ctx, frame.ctypes.data, w, h, out.ctypes.data))
+import tempfile
+gif.GifGenerator(rt, s1).RenderRotationGif(scene_mod.RenderSettings(ResolutionOverride=(48, 32), MaxDepth=2), os.path.join(tempfile.mkdtemp(), "s.gif"), totalFrames=6, stepDeg=60.0)
+rt.close()
+print("gif ok", flush=True)
 empty = scene_mod.ObjectData(); synth._sample_camera_and_light(empty)
 run("empty", {}, abi.RTB_BVH_LBVH, 0, empty, params(40, 24, 3))
 print("sanitize run complete")
