@@ -93,7 +93,7 @@ struct rtb_context {
   rtb_stats stats{};
   const volatile int32_t* cancel = nullptr;
   bool profiling = false;
-  int64_t chunk_slots = 1 << 23;
+  int64_t chunk_slots = 1 << 24;  // RTB_CHUNK_SLOTS: pixel-samples per chunk (192 B of queues each, per lane); C5 sweep: profiles/r1e_sweep_chunk_slots_c5.log
   int n_lanes = 4;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues
   uint64_t frame_id = 0;
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
