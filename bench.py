@@ -174,7 +174,28 @@ def run_reference(args, rank, world):
             "data": "synthetic", "config": {"workload": desc, "note": "CPU restatement of the reference kernel (oracle/): the reference is Unity C# + HLSL and cannot run here"},
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout.  NCCL (its version banner), torch or the CUDA runtime may print to fd 1 as
+    well, so fd 1 is pointed at stderr for the whole run and the JSON line goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -199,6 +220,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -456,7 +478,7 @@ def main():
             "kernel_ms_per_frame": {"traverse": float(fam[0]), "shade": float(fam[1]), "resolve": float(fam[2])},
             "roofline": roof, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
         if args.out_png:
             from PIL import Image
             Image.fromarray(np.ascontiguousarray(host[::-1, :, :3])).save(args.out_png)

@@ -37,6 +37,9 @@ struct Queues {
   int32_t* counters = nullptr;
   unsigned long long* totals = nullptr;
   int32_t capacity = 0, depth_cap = 0;
+  float4* park = nullptr;      // drain compaction of k_traverse (LBVH flavour): parked ray records + their stacks
+  float2* park_stack = nullptr;
+  int32_t park_cap = 0;
 };
 
 // A lane = a stream with its own wavefront queues.  Chunks (and, for asynchronous renders, whole frames) alternate between
@@ -96,6 +99,7 @@ struct rtb_context {
   int64_t chunk_slots = 1 << 24;  // RTB_CHUNK_SLOTS: pixel-samples per chunk (192 B of queues each, per lane); C5 sweep: profiles/r1e_sweep_chunk_slots_c5.log
   int n_lanes = 4;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues
   uint64_t frame_id = 0;
+  int park_mode = 0;          // RTB_PARK: 1 = drain compaction of k_traverse (rays parked when the queue runs dry, resumed in full warps)
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
   int32_t tail_max = 65536;   // queues smaller than this finish in k_tail (RTB_TAIL_MAX; 0 = pure wavefront); sweep: profiles/r1e_sweep_tail_max.log
   std::vector<void*> ipc_opened;
@@ -168,7 +172,7 @@ cudaError_t join_lanes(DeviceState& d) {
 void free_targets(DeviceState& d) {
   cudaSetDevice(d.device);
   for (auto& l : d.lane) {
-    dfree(l.q.base); dfree(l.q.counters); dfree(l.q.totals);
+    dfree(l.q.base); dfree(l.q.counters); dfree(l.q.totals); dfree(l.q.park); dfree(l.q.park_stack);
     l.q = Queues();
   }
   dfree(d.frame); d.frame_bytes = 0;
@@ -178,14 +182,19 @@ void free_targets(DeviceState& d) {
   dfree(d.aux_prim); dfree(d.aux_mat); dfree(d.aux_t); d.aux_px = 0;
 }
 
-int ensure_queues(rtb_context* ctx, LaneState& l, int32_t capacity, int32_t depth_cap) {
-  if (l.q.capacity >= capacity && l.q.depth_cap >= depth_cap) return RTB_OK;
+int ensure_queues(rtb_context* ctx, LaneState& l, int32_t capacity, int32_t depth_cap, int32_t park_cap) {
+  if (l.q.capacity >= capacity && l.q.depth_cap >= depth_cap && l.q.park_cap >= park_cap) return RTB_OK;
   CK(ctx, cudaStreamSynchronize(l.stream));
-  dfree(l.q.base); dfree(l.q.counters); dfree(l.q.totals);
+  dfree(l.q.base); dfree(l.q.counters); dfree(l.q.totals); dfree(l.q.park); dfree(l.q.park_stack);
   l.q = Queues();
   CK(ctx, cudaMalloc(&l.q.base, (size_t)capacity * 12 * sizeof(float4)));
-  CK(ctx, cudaMalloc(&l.q.counters, (size_t)depth_cap * 4 * sizeof(int32_t)));
-  CK(ctx, cudaMalloc(&l.q.totals, 8 * sizeof(unsigned long long)));
+  CK(ctx, cudaMalloc(&l.q.counters, (size_t)depth_cap * RTB_CNT_BLOCKS * sizeof(int32_t)));
+  if (park_cap > 0) {
+    CK(ctx, cudaMalloc(&l.q.park, (size_t)park_cap * 4 * sizeof(float4)));
+    CK(ctx, cudaMalloc(&l.q.park_stack, (size_t)park_cap * RTB_PARK_STACK * sizeof(float2)));
+  }
+  l.q.park_cap = park_cap;
+  CK(ctx, cudaMalloc(&l.q.totals, RTB_TOTALS * sizeof(unsigned long long)));
   l.q.capacity = capacity;
   l.q.depth_cap = depth_cap;
   l.frame_id = 0;
@@ -201,6 +210,7 @@ QueueView queue_view(const Queues& q) {
   v.hits = p + 10 * c;
   v.accum = p + 11 * c;
   v.counters = q.counters;
+  v.park = q.park; v.park_stack = q.park_stack; v.park_cap = q.park_cap;
   v.totals = q.totals;
   v.depth_cap = q.depth_cap;
   return v;
@@ -351,6 +361,8 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
   const int32_t depth_cap = f.max_depth + 2;
   if (!d.grid_traverse[bvh]) d.grid_traverse[bvh] = d.sm_count * traverse_blocks_per_sm(bvh);
   const int shade_grid = d.sm_count * 8;
+  // parking needs a record per ray the persistent grid can hold; LBVH flavour, global-memory variant, triangle scenes only
+  const bool can_park = ctx->park_mode != 0 && bvh == RTB_BVH_LBVH && d.scene.n_prims == 0;
   size_t smem_bytes = 0;  // small scenes: k_traverse works out of a shared-memory copy of nodes + triangles
   if (ctx->smem_mode != 0 && d.scene.n_tris > 0 && d.scene.n_prims == 0) {
     const size_t need = traverse_smem_bytes(bvh, sv);
@@ -359,6 +371,8 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
       smem_bytes = need;
     }
   }
+  // one record for every ray the persistent grid can hold at once (128 threads per block)
+  const int32_t park_cap = (can_park && smem_bytes == 0) ? d.grid_traverse[bvh] * traverse_block_threads() : 0;
   d.prof_used[0] = d.prof_used[1] = d.prof_used[2] = 0;
   for (int32_t row0 = 0; row0 < local_rows; row0 += rows_per_chunk) {
     LaneState& L = d.lane[d.next_lane];
@@ -367,14 +381,14 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
     cudaStream_t stream = L.stream;
     if (ctx->cancel && *ctx->cancel) { device_sync(d); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
     {
-      const int rc = ensure_queues(ctx, L, capacity, depth_cap);
+      const int rc = ensure_queues(ctx, L, capacity, depth_cap, park_cap);
       if (rc != RTB_OK) return rc;
     }
     const QueueView qv = queue_view(L.q);
     if (L.frame_id != ctx->frame_id) {  // first chunk of this frame on this lane
       L.frame_id = ctx->frame_id;
       CK(ctx, cudaEventRecord(L.ev_begin, stream));
-      CK(ctx, cudaMemsetAsync(L.q.totals, 0, 8 * sizeof(unsigned long long), stream));
+      CK(ctx, cudaMemsetAsync(L.q.totals, 0, RTB_TOTALS * sizeof(unsigned long long), stream));
     }
     L.used = true;
     auto timed = [&](int family, auto&& launch) {
@@ -406,7 +420,7 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
       if (f.max_depth <= 0) {  // the depth loop never runs: sampleColor stays 0
         CK(ctx, cudaMemsetAsync(qv.accum, 0, (size_t)c.n_slots * sizeof(float4), stream));
       } else {
-        CK(ctx, cudaMemsetAsync(L.q.counters, 0, (size_t)L.q.depth_cap * 4 * sizeof(int32_t), stream));
+        CK(ctx, cudaMemsetAsync(L.q.counters, 0, (size_t)L.q.depth_cap * RTB_CNT_BLOCKS * sizeof(int32_t), stream));
         // raygen fills the depth-0 queue; depth d: traverse (closest-hit rays of depth d + shadow rays emitted at depth d-1),
         // then shade (or, for short queues, k_tail).  One more traverse at the end serves the last depth's shadow rays.
         timed(1, [&] { launch_raygen(bvh, f, sv, qv, c, shade_grid, stream); });
@@ -414,6 +428,9 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
           if (depth > 0 && ctx->cancel && *ctx->cancel) { device_sync(d); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
           if (depth < f.max_depth || f.en_diffuse == 1)
             timed(0, [&] { launch_traverse(bvh, sv, qv, depth, smem_bytes ? d.sm_count : d.grid_traverse[bvh], smem_bytes, stream); });
+          // drain compaction: the rays the first pass parked once the queue ran dry, re-packed into full warps
+          if (park_cap > 0 && (depth < f.max_depth || f.en_diffuse == 1))
+            timed(0, [&] { launch_traverse_resume(sv, qv, depth, std::max(d.sm_count, d.grid_traverse[bvh] / 2), stream); });
           if (depth < f.max_depth) {
             timed(1, [&] { launch_shade(f, sv, qv, c, depth, ctx->tail_max, shade_grid, stream); });
             if (ctx->tail_max > 0) timed(0, [&] { launch_tail(bvh, f, sv, qv, c, depth, ctx->tail_max, d.sm_count * 4, stream); });
@@ -494,16 +511,26 @@ int collect_stats(rtb_context* ctx) {
   st.rays_primary = st.rays_continuation = st.rays_shadow = st.paths_hit_primary = 0;
   st.ms_render_device = 0.0f;
   st.ms_traverse = st.ms_shade = st.ms_resolve = 0.0f;
-  int64_t overflow = 0, nodes = 0, tris = 0;
+  int64_t overflow = 0, nodes = 0, tris = 0, longest = 0;
   for (auto& d : ctx->devs) {
     device_sync(d);
     CK(ctx, cudaGetLastError());
     for (auto& l : d.lane) {
       if (!l.q.totals || l.frame_id != ctx->frame_id || ctx->frame_id == 0) continue;
-      unsigned long long t[8];
+      unsigned long long t[RTB_TOTALS];
       CK(ctx, cudaMemcpy(t, l.q.totals, sizeof t, cudaMemcpyDeviceToHost));
+      if (std::getenv("RTB_TIMELINE")) {  // diagnostic builds (-DRTB_RAY_STATS=1): per k_traverse launch, ns since its first block started
+        for (int dd = 0; dd < 16; dd++) {
+          const unsigned long long* w = t + 8 + 4 * dd;
+          if (!w[0]) continue;
+          const unsigned long long start = ~w[0];
+          std::fprintf(stderr, "k_traverse depth %d: queue exhausted first at %.1f us, last warp saw it at %.1f us, last warp done at %.1f us\n", dd,
+                       (~w[1] - start) * 1e-3, (w[3] - start) * 1e-3, (w[2] - start) * 1e-3);
+        }
+      }
       st.rays_primary += (int64_t)t[0]; st.rays_continuation += (int64_t)t[1]; st.rays_shadow += (int64_t)t[2];
       st.paths_hit_primary += (int64_t)t[3]; overflow += (int64_t)t[4]; nodes += (int64_t)t[5]; tris += (int64_t)t[6];
+      longest = std::max(longest, (int64_t)t[7]);
       float ms = 0.0f;
       if (cudaEventElapsedTime(&ms, l.ev_begin, l.ev_end) == cudaSuccess) st.ms_render_device = std::max(st.ms_render_device, ms);
       else cudaGetLastError();
@@ -517,6 +544,7 @@ int collect_stats(rtb_context* ctx) {
   st.reserved[0] = overflow;
   st.reserved[1] = nodes;
   st.reserved[2] = tris;
+  st.reserved[3] = longest;
   cudaSetDevice(ctx->devs[0].device);
   return RTB_OK;
 }
@@ -567,6 +595,7 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
   }
   if (const char* env = std::getenv("RTB_LANES")) ctx->n_lanes = std::min((int)DeviceState::kMaxLanes, std::max(1, std::atoi(env)));
   if (const char* env = std::getenv("RTB_SMEM")) ctx->smem_mode = std::atoi(env);
+  if (const char* env = std::getenv("RTB_PARK")) ctx->park_mode = std::atoi(env);
   if (const char* env = std::getenv("RTB_TAIL_MAX")) ctx->tail_max = (int32_t)std::max(0LL, std::atoll(env));
   ctx->devs.resize(ids.size());
   for (size_t k = 0; k < ids.size(); k++) {

@@ -182,6 +182,12 @@ struct Lane {
 #define RTB_REFILL_MIN 16
 #endif
 // Queues shorter than RTB_MIN_BATCHES 32-ray batches per resident warp leave the surplus blocks idle (0 = always use the whole grid).
+#ifndef RTB_RAY_STATS
+#define RTB_RAY_STATS 0  /* 1: diagnostic build, rtb_stats.reserved[3] = node visits of the frame's longest ray; RTB_TIMELINE=1 prints launch timelines */
+#endif
+#if RTB_RAY_STATS
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 #ifndef RTB_MIN_BATCHES
 #define RTB_MIN_BATCHES 0
 #endif
@@ -260,7 +266,18 @@ __device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_traverse, LBVH flavour: ordered traversal over 64-byte two-box nodes (see lbvh.cu for the layout).
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool SMEM, bool ANALYTIC>
+// RESUME = false: the launch proper.  Once the queue has run dry every warp only drains what it holds, at ever fewer live lanes but
+// full instruction cost — measured (tools/timeline.py) as 50-75 % of a short launch.  So a warp that knows the queue is dry and
+// is down to RTB_PARK_MAX_LIVE live rays PARKS them: each ray's state and deferred-node stack go to q.park / q.park_stack and the
+// warp exits.  RESUME = true: the follow-up launch, whose work items are the parked records: rays continue exactly where they
+// stopped (same stack, same order, same bits) in re-packed, full warps.
+#ifndef RTB_PARK_MAX_LIVE
+#define RTB_PARK_MAX_LIVE 24
+#endif
+#ifndef RTB_PARK_MIN_TOTAL
+#define RTB_PARK_MIN_TOTAL 8192  /* shorter queues are not worth a second pass */
+#endif
+template <bool SMEM, bool ANALYTIC, bool RESUME>
 __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB_TRAVERSE_MIN_BLOCKS) k_traverse_lbvh(const SceneView s, const QueueView q, const int depth) {
   extern __shared__ float4 sm_scene[];
   const float4* nodes = s.nodes;
@@ -269,7 +286,11 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
   const int lane = threadIdx.x & 31;
   const int32_t n_closest = RTB_CNT_RAY(q, depth);
   const int32_t n_shadow = depth == 0 ? 0 : RTB_CNT_SHADOW(q, depth - 1);
-  const int32_t total = n_closest + n_shadow;
+  const int32_t total = RESUME ? RTB_CNT_PARK(q, depth) : n_closest + n_shadow;
+  if (RESUME && total == 0) return;
+  int32_t* const fetch_counter = RESUME ? &RTB_CNT_PARK_FETCH(q, depth) : &RTB_CNT_FETCH(q, depth);
+  const bool may_park = !SMEM && !RESUME && q.park_cap > 0 && total >= RTB_PARK_MIN_TOTAL;
+  unsigned park_tick = 0;
   const int in_q = depth & 1;
 #if RTB_MIN_BATCHES > 0
   if (!SMEM) {  // short queue: fewer resident warps, each with several batches, balance better than one batch on every warp
@@ -277,13 +298,20 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
     if ((int32_t)(blockIdx.x * (blockDim.x >> 5)) >= want_warps && blockIdx.x != 0) return;
   }
 #endif
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (!RESUME && blockIdx.x == 0 && threadIdx.x == 0) {
     if (depth > 0 && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
     if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
   }
   float2 stack[RTB_STACK_LBVH];  // deferred children: (entry distance, node / leaf reference) in one 8-byte local-memory access
   int sp = 0;
   int32_t cur = RTB_REF_DONE;
+#if RTB_RAY_STATS
+  unsigned ray_steps = 0;  // diagnostic build: node visits of the lane's current ray; totals[7] = the longest ray of the frame
+  // ... and a timeline of the launch in totals[8 + 4 depth ..]: ~(first start), ~(first exhaustion seen), last end, last exhaustion seen
+  unsigned long long* tl = q.totals + 8 + 4 * (depth < 16 ? depth : 15);
+  bool saw_exhausted = false;
+  if (lane == 0 && total > 0) atomicMax(&tl[0], ~global_ns());
+#endif
   f3 ood = mk3(0.0f, 0.0f, 0.0f);
   Lane L;
   L.item = -1; L.shadow = false; L.done = false; L.t = 0.0f; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
@@ -296,14 +324,33 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
     const int n_out = __popc(__ballot_sync(kFull, L.item < 0 || L.done));
     if (n_out >= RefillMin<SMEM>::value) {
       if (L.item >= 0 && L.done) lane_finish(L, q, n_closest);
-      const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, L.item < 0, lane);
+      const int32_t item = pool_take(pool, fetch_counter, total, L.item < 0, lane);
+#if RTB_RAY_STATS
+      if (pool.exhausted && !saw_exhausted) {
+        saw_exhausted = true;
+        if (lane == 0) { const unsigned long long now = global_ns(); atomicMax(&tl[1], ~now); atomicMax(&tl[3], now); }
+      }
+#endif
       if (item >= 0) {
-        lane_load(L, q, item, n_closest, in_q);
+#if RTB_RAY_STATS
+        if (L.item >= 0 || ray_steps) atomicMax(&q.totals[7], (unsigned long long)ray_steps);
+        ray_steps = 0;
+#endif
+        if (RESUME) {  // a parked ray: state, current node / leaf and deferred nodes as they were
+          const float4 a = __ldcs(&q.park[4 * item]), b = __ldcs(&q.park[4 * item + 1]), c = __ldcs(&q.park[4 * item + 2]), e = __ldcs(&q.park[4 * item + 3]);
+          L.o = mk3(a); L.t = a.w; L.d = mk3(b); L.u = b.w; L.v = c.x; L.tri = __float_as_int(c.y); L.item = __float_as_int(c.z);
+          const int packed = __float_as_int(c.w);
+          L.shadow = (packed & 1) != 0; sp = packed >> 1; L.done = false;
+          cur = __float_as_int(e.x);
+          for (int i = 0; i < sp; i++) stack[i] = __ldcs(&q.park_stack[(size_t)item * RTB_PARK_STACK + i]);
+        } else {
+          lane_load(L, q, item, n_closest, in_q);
+          sp = 0;
+          cur = s.n_tris > 0 ? s.root : RTB_REF_DONE;
+          L.done = cur == RTB_REF_DONE;
+        }
         L.inv = safe_inverse(L.d);
         ood = L.o * L.inv;
-        sp = 0;
-        cur = s.n_tris > 0 ? s.root : RTB_REF_DONE;
-        L.done = cur == RTB_REF_DONE;
       }
       if (__ballot_sync(kFull, L.item >= 0 && !L.done) == 0) {
         if (__ballot_sync(kFull, L.item >= 0) == 0 && pool.exhausted) break;
@@ -311,9 +358,38 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
       }
     }
 
+    // ---- drain: the queue is dry and this warp is thin -> park its rays for the resume pass ----
+    if (may_park) {
+      if (!pool.exhausted && ((++park_tick) & 7u) == 0u && *(volatile int32_t*)fetch_counter >= total) pool.exhausted = true;
+      if (pool.exhausted && pool.at >= pool.end) {
+        const int n_live = __popc(__ballot_sync(kFull, L.item >= 0 && !L.done));
+        if (n_live <= RTB_PARK_MAX_LIVE) {
+          if (L.item >= 0 && L.done) lane_finish(L, q, n_closest);
+          const bool mine = L.item >= 0 && sp <= RTB_PARK_STACK;
+          const unsigned pm = __ballot_sync(kFull, mine);
+          int32_t base = 0;
+          if (lane == 0 && pm) base = atomicAdd(&RTB_CNT_PARK(q, depth), __popc(pm));
+          base = __shfl_sync(kFull, base, 0);
+          if (mine) {
+            const int32_t at = base + __popc(pm & ((1u << lane) - 1u));
+            __stcs(&q.park[4 * at], make_float4(L.o.x, L.o.y, L.o.z, L.t));
+            __stcs(&q.park[4 * at + 1], make_float4(L.d.x, L.d.y, L.d.z, L.u));
+            __stcs(&q.park[4 * at + 2], make_float4(L.v, __int_as_float(L.tri), __int_as_float(L.item), __int_as_float((sp << 1) | (L.shadow ? 1 : 0))));
+            __stcs(&q.park[4 * at + 3], make_float4(__int_as_float(cur), 0.0f, 0.0f, 0.0f));
+            for (int i = 0; i < sp; i++) __stcs(&q.park_stack[(size_t)at * RTB_PARK_STACK + i], stack[i]);
+            L.item = -1; L.done = false; cur = RTB_REF_DONE; sp = 0;
+          }
+          if (__ballot_sync(kFull, L.item >= 0) == 0) break;  // everything parked or published: this warp is done
+        }
+      }
+    }
+
     // ---- inner nodes: descend until this lane holds a leaf (or runs out of work) ----
     while (cur >= 0) {
       n_nodes++;
+#if RTB_RAY_STATS
+      ray_steps++;
+#endif
       // closest: a box is skipped when entry >= best t (compute:246); shadow rays carry nextafter(distToLight) as bound
       const int32_t next = lbvh_visit<SMEM>(nodes, cur, L.inv, ood, L.t, stack, sp, overflow);
       if (next != RTB_REF_MISS) cur = next;
@@ -345,6 +421,10 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
     if (cur == RTB_REF_DONE && L.item >= 0) { sp = 0; L.done = true; }
   }
 
+#if RTB_RAY_STATS
+  if (ray_steps) atomicMax(&q.totals[7], (unsigned long long)ray_steps);
+  if (lane == 0 && total > 0) atomicMax(&tl[2], global_ns());
+#endif
   for (int o = 16; o > 0; o >>= 1) {
     overflow += __shfl_xor_sync(kFull, overflow, o);
     n_nodes += __shfl_xor_sync(kFull, n_nodes, o);
@@ -809,7 +889,7 @@ int blocks_per_sm(K kernel) {
 }  // namespace
 
 int traverse_blocks_per_sm(int bvh) {
-  return bvh == RTB_BVH_REFERENCE ? blocks_per_sm(k_traverse_ref<false, false>) : blocks_per_sm(k_traverse_lbvh<false, false>);
+  return bvh == RTB_BVH_REFERENCE ? blocks_per_sm(k_traverse_ref<false, false>) : blocks_per_sm(k_traverse_lbvh<false, false, false>);
 }
 
 void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st) {
@@ -823,7 +903,7 @@ size_t traverse_smem_bytes(int bvh, const SceneView& s) {
 
 cudaError_t traverse_enable_smem(int bvh, size_t bytes) {
   if (bvh == RTB_BVH_REFERENCE) return cudaFuncSetAttribute(k_traverse_ref<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  return cudaFuncSetAttribute(k_traverse_lbvh<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaFuncSetAttribute(k_traverse_lbvh<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 // Scenes with analytic primitives (s.n_prims > 0) run the ANALYTIC instantiations; everything else keeps the leaner
@@ -832,15 +912,21 @@ void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth,
   const bool ref = bvh == RTB_BVH_REFERENCE;
   if (s.n_prims > 0) {
     if (ref) k_traverse_ref<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth);
-    else k_traverse_lbvh<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth);
+    else k_traverse_lbvh<false, true, false><<<grid, kTravBlock, 0, st>>>(s, q, depth);
   } else if (smem_bytes > 0) {  // small scene: one 1024-thread block per SM works out of its shared-memory copy
     if (ref) k_traverse_ref<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
-    else k_traverse_lbvh<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
+    else k_traverse_lbvh<true, false, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
   } else {
     if (ref) k_traverse_ref<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth);
-    else k_traverse_lbvh<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth);
+    else k_traverse_lbvh<false, false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth);
   }
 }
+
+void launch_traverse_resume(const SceneView& s, const QueueView& q, int depth, int grid, cudaStream_t st) {
+  k_traverse_lbvh<false, false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth);
+}
+
+int traverse_block_threads() { return kTravBlock; }
 
 void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,
                   cudaStream_t st) {

@@ -496,14 +496,14 @@ def test_rotation_sweep_matches_frame_by_frame_renders(samples, oracle):
 
 
 def test_c5_shape_8k_16spp_many_chunks(tracers, samples):
-    """BASELINE config C5's shape (7680x4320, 16 spp, depth 6: 531 M pixel-samples in 64 chunks over two lanes) on the sample
+    """BASELINE config C5's shape (7680x4320, 16 spp, depth 6: 531 M pixel-samples in 32 chunks over the lanes) on the sample
     scene; the oracle checks 16 rows spread over the frame, which cross chunk and lane boundaries."""
     obj, osc, _ = samples["test_scene_1"]
     p = params(7680, 4320, 6, 16)
     rt = tracers(abi.RTB_BVH_REFERENCE)
     tex = rt.RenderAsync(obj, p).pixels
     st = rt.stats()
-    assert st.chunks >= 60 and st.rays_primary == 7680 * 4320 * 16 and st.reserved[0] == 0
+    assert st.chunks >= 30 and st.rays_primary == 7680 * 4320 * 16 and st.reserved[0] == 0
     rows = np.arange(7, 4320, 270)
     ref = osc.render(p, rows=(7, -1, 270))
     assert (tex[rows] == ref["rgba8"][rows]).all()
