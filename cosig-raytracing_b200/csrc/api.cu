@@ -37,9 +37,6 @@ struct Queues {
   int32_t* counters = nullptr;
   unsigned long long* totals = nullptr;
   int32_t capacity = 0, depth_cap = 0;
-  float4* park = nullptr;      // drain compaction of k_traverse (LBVH flavour): parked ray records + their stacks
-  float2* park_stack = nullptr;
-  int32_t park_cap = 0;
 };
 
 // A lane = a stream with its own wavefront queues.  Chunks (and, for asynchronous renders, whole frames) alternate between
@@ -99,7 +96,6 @@ struct rtb_context {
   int64_t chunk_slots = 1 << 24;  // RTB_CHUNK_SLOTS: pixel-samples per chunk (192 B of queues each, per lane); C5 sweep: profiles/r1e_sweep_chunk_slots_c5.log
   int n_lanes = 4;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues
   uint64_t frame_id = 0;
-  int park_mode = 0;          // RTB_PARK: 1 = drain compaction of k_traverse (rays parked when the queue runs dry, resumed in full warps)
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
   int32_t tail_max = 65536;   // queues smaller than this finish in k_tail (RTB_TAIL_MAX; 0 = pure wavefront); sweep: profiles/r1e_sweep_tail_max.log
   std::vector<void*> ipc_opened;
@@ -172,7 +168,7 @@ cudaError_t join_lanes(DeviceState& d) {
 void free_targets(DeviceState& d) {
   cudaSetDevice(d.device);
   for (auto& l : d.lane) {
-    dfree(l.q.base); dfree(l.q.counters); dfree(l.q.totals); dfree(l.q.park); dfree(l.q.park_stack);
+    dfree(l.q.base); dfree(l.q.counters); dfree(l.q.totals);
     l.q = Queues();
   }
   dfree(d.frame); d.frame_bytes = 0;
@@ -182,18 +178,13 @@ void free_targets(DeviceState& d) {
   dfree(d.aux_prim); dfree(d.aux_mat); dfree(d.aux_t); d.aux_px = 0;
 }
 
-int ensure_queues(rtb_context* ctx, LaneState& l, int32_t capacity, int32_t depth_cap, int32_t park_cap) {
-  if (l.q.capacity >= capacity && l.q.depth_cap >= depth_cap && l.q.park_cap >= park_cap) return RTB_OK;
+int ensure_queues(rtb_context* ctx, LaneState& l, int32_t capacity, int32_t depth_cap) {
+  if (l.q.capacity >= capacity && l.q.depth_cap >= depth_cap) return RTB_OK;
   CK(ctx, cudaStreamSynchronize(l.stream));
-  dfree(l.q.base); dfree(l.q.counters); dfree(l.q.totals); dfree(l.q.park); dfree(l.q.park_stack);
+  dfree(l.q.base); dfree(l.q.counters); dfree(l.q.totals);
   l.q = Queues();
   CK(ctx, cudaMalloc(&l.q.base, (size_t)capacity * 12 * sizeof(float4)));
   CK(ctx, cudaMalloc(&l.q.counters, (size_t)depth_cap * RTB_CNT_BLOCKS * sizeof(int32_t)));
-  if (park_cap > 0) {
-    CK(ctx, cudaMalloc(&l.q.park, (size_t)park_cap * 4 * sizeof(float4)));
-    CK(ctx, cudaMalloc(&l.q.park_stack, (size_t)park_cap * RTB_PARK_STACK * sizeof(float2)));
-  }
-  l.q.park_cap = park_cap;
   CK(ctx, cudaMalloc(&l.q.totals, RTB_TOTALS * sizeof(unsigned long long)));
   l.q.capacity = capacity;
   l.q.depth_cap = depth_cap;
@@ -210,7 +201,6 @@ QueueView queue_view(const Queues& q) {
   v.hits = p + 10 * c;
   v.accum = p + 11 * c;
   v.counters = q.counters;
-  v.park = q.park; v.park_stack = q.park_stack; v.park_cap = q.park_cap;
   v.totals = q.totals;
   v.depth_cap = q.depth_cap;
   return v;
@@ -361,8 +351,6 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
   const int32_t depth_cap = f.max_depth + 2;
   if (!d.grid_traverse[bvh]) d.grid_traverse[bvh] = d.sm_count * traverse_blocks_per_sm(bvh);
   const int shade_grid = d.sm_count * 8;
-  // parking needs a record per ray the persistent grid can hold; LBVH flavour, global-memory variant, triangle scenes only
-  const bool can_park = ctx->park_mode != 0 && bvh == RTB_BVH_LBVH && d.scene.n_prims == 0;
   size_t smem_bytes = 0;  // small scenes: k_traverse works out of a shared-memory copy of nodes + triangles
   if (ctx->smem_mode != 0 && d.scene.n_tris > 0 && d.scene.n_prims == 0) {
     const size_t need = traverse_smem_bytes(bvh, sv);
@@ -371,8 +359,6 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
       smem_bytes = need;
     }
   }
-  // one record for every ray the persistent grid can hold at once (128 threads per block)
-  const int32_t park_cap = (can_park && smem_bytes == 0) ? d.grid_traverse[bvh] * traverse_block_threads() : 0;
   d.prof_used[0] = d.prof_used[1] = d.prof_used[2] = 0;
   for (int32_t row0 = 0; row0 < local_rows; row0 += rows_per_chunk) {
     LaneState& L = d.lane[d.next_lane];
@@ -381,7 +367,7 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
     cudaStream_t stream = L.stream;
     if (ctx->cancel && *ctx->cancel) { device_sync(d); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
     {
-      const int rc = ensure_queues(ctx, L, capacity, depth_cap, park_cap);
+      const int rc = ensure_queues(ctx, L, capacity, depth_cap);
       if (rc != RTB_OK) return rc;
     }
     const QueueView qv = queue_view(L.q);
@@ -428,9 +414,6 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
           if (depth > 0 && ctx->cancel && *ctx->cancel) { device_sync(d); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
           if (depth < f.max_depth || f.en_diffuse == 1)
             timed(0, [&] { launch_traverse(bvh, sv, qv, depth, smem_bytes ? d.sm_count : d.grid_traverse[bvh], smem_bytes, stream); });
-          // drain compaction: the rays the first pass parked once the queue ran dry, re-packed into full warps
-          if (park_cap > 0 && (depth < f.max_depth || f.en_diffuse == 1))
-            timed(0, [&] { launch_traverse_resume(sv, qv, depth, std::max(d.sm_count, d.grid_traverse[bvh] / 2), stream); });
           if (depth < f.max_depth) {
             timed(1, [&] { launch_shade(f, sv, qv, c, depth, ctx->tail_max, shade_grid, stream); });
             if (ctx->tail_max > 0) timed(0, [&] { launch_tail(bvh, f, sv, qv, c, depth, ctx->tail_max, d.sm_count * 4, stream); });
@@ -595,7 +578,6 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
   }
   if (const char* env = std::getenv("RTB_LANES")) ctx->n_lanes = std::min((int)DeviceState::kMaxLanes, std::max(1, std::atoi(env)));
   if (const char* env = std::getenv("RTB_SMEM")) ctx->smem_mode = std::atoi(env);
-  if (const char* env = std::getenv("RTB_PARK")) ctx->park_mode = std::atoi(env);
   if (const char* env = std::getenv("RTB_TAIL_MAX")) ctx->tail_max = (int32_t)std::max(0LL, std::atoll(env));
   ctx->devs.resize(ids.size());
   for (size_t k = 0; k < ids.size(); k++) {

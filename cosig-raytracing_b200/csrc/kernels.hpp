@@ -36,9 +36,6 @@ void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const Queu
 // smem_bytes > 0 selects the shared-memory staged variant (grid = sm_count blocks of 1024 threads); it must have been
 // enabled for that size with traverse_enable_smem and equal traverse_smem_bytes(bvh, s).
 void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int grid, size_t smem_bytes, cudaStream_t st);
-// Second pass of a depth's traversal (LBVH flavour): resumes the rays the first pass parked (q.park) in re-packed warps.
-void launch_traverse_resume(const SceneView& s, const QueueView& q, int depth, int grid, cudaStream_t st);
-int traverse_block_threads();
 size_t traverse_smem_bytes(int bvh, const SceneView& s);
 cudaError_t traverse_enable_smem(int bvh, size_t bytes);
 // k_shade handles depth `depth` when its queue holds >= tail_max rays; otherwise k_tail runs the remaining paths to their

@@ -131,11 +131,7 @@ struct QueueView {
   float4* sh_o; float4* sh_d; float4* sh_lit; float4* sh_unlit;
   float4* hits;           // per ray-queue entry of the current depth: (t, u, v, leaf-order triangle index bits; -1 = miss)
   float4* accum;          // per slot: running sampleColor
-  int32_t* counters;      // RTB_CNT_BLOCKS blocks of depth_cap ints: ray queue sizes | shadow queue sizes | traverse fetch | parked rays |
-                          // parked fetch | (spare)
-  float4* park;           // rays parked at the end of a k_traverse launch (drain compaction): 4 float4 per record ...
-  float2* park_stack;     // ... and RTB_PARK_STACK deferred-node entries each
-  int32_t park_cap;       // records available (0 = parking disabled)
+  int32_t* counters;      // RTB_CNT_BLOCKS blocks of depth_cap ints: ray queue sizes | shadow queue sizes | traverse fetch | (spare)
   unsigned long long* totals;  // [0] primary rays [1] continuation rays [2] shadow rays [3] primary hits [4] stack overflows
                                // [5] BVH nodes fetched [6] triangles tested (all rays of the frame)
   int32_t depth_cap;      // D (>= max_depth + 1)
@@ -143,9 +139,6 @@ struct QueueView {
 #define RTB_CNT_RAY(q, d) ((q).counters[(d)])
 #define RTB_CNT_SHADOW(q, d) ((q).counters[(q).depth_cap + (d)])
 #define RTB_CNT_FETCH(q, d) ((q).counters[2 * (q).depth_cap + (d)])
-#define RTB_CNT_PARK(q, d) ((q).counters[3 * (q).depth_cap + (d)])
-#define RTB_CNT_PARK_FETCH(q, d) ((q).counters[4 * (q).depth_cap + (d)])
-#define RTB_CNT_BLOCKS 6
-#define RTB_PARK_STACK 32 /* a parked ray carries at most this many stack entries; deeper ones finish where they are */
+#define RTB_CNT_BLOCKS 4
 
 }  // namespace rtb

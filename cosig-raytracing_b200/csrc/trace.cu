@@ -266,18 +266,7 @@ __device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_traverse, LBVH flavour: ordered traversal over 64-byte two-box nodes (see lbvh.cu for the layout).
 // ---------------------------------------------------------------------------------------------------------------------
-// RESUME = false: the launch proper.  Once the queue has run dry every warp only drains what it holds, at ever fewer live lanes but
-// full instruction cost — measured (tools/timeline.py) as 50-75 % of a short launch.  So a warp that knows the queue is dry and
-// is down to RTB_PARK_MAX_LIVE live rays PARKS them: each ray's state and deferred-node stack go to q.park / q.park_stack and the
-// warp exits.  RESUME = true: the follow-up launch, whose work items are the parked records: rays continue exactly where they
-// stopped (same stack, same order, same bits) in re-packed, full warps.
-#ifndef RTB_PARK_MAX_LIVE
-#define RTB_PARK_MAX_LIVE 24
-#endif
-#ifndef RTB_PARK_MIN_TOTAL
-#define RTB_PARK_MIN_TOTAL 8192  /* shorter queues are not worth a second pass */
-#endif
-template <bool SMEM, bool ANALYTIC, bool RESUME>
+template <bool SMEM, bool ANALYTIC>
 __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB_TRAVERSE_MIN_BLOCKS) k_traverse_lbvh(const SceneView s, const QueueView q, const int depth) {
   extern __shared__ float4 sm_scene[];
   const float4* nodes = s.nodes;
@@ -286,11 +275,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
   const int lane = threadIdx.x & 31;
   const int32_t n_closest = RTB_CNT_RAY(q, depth);
   const int32_t n_shadow = depth == 0 ? 0 : RTB_CNT_SHADOW(q, depth - 1);
-  const int32_t total = RESUME ? RTB_CNT_PARK(q, depth) : n_closest + n_shadow;
-  if (RESUME && total == 0) return;
-  int32_t* const fetch_counter = RESUME ? &RTB_CNT_PARK_FETCH(q, depth) : &RTB_CNT_FETCH(q, depth);
-  const bool may_park = !SMEM && !RESUME && q.park_cap > 0 && total >= RTB_PARK_MIN_TOTAL;
-  unsigned park_tick = 0;
+  const int32_t total = n_closest + n_shadow;
   const int in_q = depth & 1;
 #if RTB_MIN_BATCHES > 0
   if (!SMEM) {  // short queue: fewer resident warps, each with several batches, balance better than one batch on every warp
@@ -298,7 +283,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
     if ((int32_t)(blockIdx.x * (blockDim.x >> 5)) >= want_warps && blockIdx.x != 0) return;
   }
 #endif
-  if (!RESUME && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (depth > 0 && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
     if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
   }
@@ -324,7 +309,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
     const int n_out = __popc(__ballot_sync(kFull, L.item < 0 || L.done));
     if (n_out >= RefillMin<SMEM>::value) {
       if (L.item >= 0 && L.done) lane_finish(L, q, n_closest);
-      const int32_t item = pool_take(pool, fetch_counter, total, L.item < 0, lane);
+      const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, L.item < 0, lane);
 #if RTB_RAY_STATS
       if (pool.exhausted && !saw_exhausted) {
         saw_exhausted = true;
@@ -336,51 +321,16 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
         if (L.item >= 0 || ray_steps) atomicMax(&q.totals[7], (unsigned long long)ray_steps);
         ray_steps = 0;
 #endif
-        if (RESUME) {  // a parked ray: state, current node / leaf and deferred nodes as they were
-          const float4 a = __ldcs(&q.park[4 * item]), b = __ldcs(&q.park[4 * item + 1]), c = __ldcs(&q.park[4 * item + 2]), e = __ldcs(&q.park[4 * item + 3]);
-          L.o = mk3(a); L.t = a.w; L.d = mk3(b); L.u = b.w; L.v = c.x; L.tri = __float_as_int(c.y); L.item = __float_as_int(c.z);
-          const int packed = __float_as_int(c.w);
-          L.shadow = (packed & 1) != 0; sp = packed >> 1; L.done = false;
-          cur = __float_as_int(e.x);
-          for (int i = 0; i < sp; i++) stack[i] = __ldcs(&q.park_stack[(size_t)item * RTB_PARK_STACK + i]);
-        } else {
-          lane_load(L, q, item, n_closest, in_q);
-          sp = 0;
-          cur = s.n_tris > 0 ? s.root : RTB_REF_DONE;
-          L.done = cur == RTB_REF_DONE;
-        }
+        lane_load(L, q, item, n_closest, in_q);
+        sp = 0;
+        cur = s.n_tris > 0 ? s.root : RTB_REF_DONE;
+        L.done = cur == RTB_REF_DONE;
         L.inv = safe_inverse(L.d);
         ood = L.o * L.inv;
       }
       if (__ballot_sync(kFull, L.item >= 0 && !L.done) == 0) {
         if (__ballot_sync(kFull, L.item >= 0) == 0 && pool.exhausted) break;
         continue;  // only padding slots / trivially finished items were drawn: publish and take more
-      }
-    }
-
-    // ---- drain: the queue is dry and this warp is thin -> park its rays for the resume pass ----
-    if (may_park) {
-      if (!pool.exhausted && ((++park_tick) & 7u) == 0u && *(volatile int32_t*)fetch_counter >= total) pool.exhausted = true;
-      if (pool.exhausted && pool.at >= pool.end) {
-        const int n_live = __popc(__ballot_sync(kFull, L.item >= 0 && !L.done));
-        if (n_live <= RTB_PARK_MAX_LIVE) {
-          if (L.item >= 0 && L.done) lane_finish(L, q, n_closest);
-          const bool mine = L.item >= 0 && sp <= RTB_PARK_STACK;
-          const unsigned pm = __ballot_sync(kFull, mine);
-          int32_t base = 0;
-          if (lane == 0 && pm) base = atomicAdd(&RTB_CNT_PARK(q, depth), __popc(pm));
-          base = __shfl_sync(kFull, base, 0);
-          if (mine) {
-            const int32_t at = base + __popc(pm & ((1u << lane) - 1u));
-            __stcs(&q.park[4 * at], make_float4(L.o.x, L.o.y, L.o.z, L.t));
-            __stcs(&q.park[4 * at + 1], make_float4(L.d.x, L.d.y, L.d.z, L.u));
-            __stcs(&q.park[4 * at + 2], make_float4(L.v, __int_as_float(L.tri), __int_as_float(L.item), __int_as_float((sp << 1) | (L.shadow ? 1 : 0))));
-            __stcs(&q.park[4 * at + 3], make_float4(__int_as_float(cur), 0.0f, 0.0f, 0.0f));
-            for (int i = 0; i < sp; i++) __stcs(&q.park_stack[(size_t)at * RTB_PARK_STACK + i], stack[i]);
-            L.item = -1; L.done = false; cur = RTB_REF_DONE; sp = 0;
-          }
-          if (__ballot_sync(kFull, L.item >= 0) == 0) break;  // everything parked or published: this warp is done
-        }
       }
     }
 
@@ -889,7 +839,7 @@ int blocks_per_sm(K kernel) {
 }  // namespace
 
 int traverse_blocks_per_sm(int bvh) {
-  return bvh == RTB_BVH_REFERENCE ? blocks_per_sm(k_traverse_ref<false, false>) : blocks_per_sm(k_traverse_lbvh<false, false, false>);
+  return bvh == RTB_BVH_REFERENCE ? blocks_per_sm(k_traverse_ref<false, false>) : blocks_per_sm(k_traverse_lbvh<false, false>);
 }
 
 void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st) {
@@ -903,7 +853,7 @@ size_t traverse_smem_bytes(int bvh, const SceneView& s) {
 
 cudaError_t traverse_enable_smem(int bvh, size_t bytes) {
   if (bvh == RTB_BVH_REFERENCE) return cudaFuncSetAttribute(k_traverse_ref<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  return cudaFuncSetAttribute(k_traverse_lbvh<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaFuncSetAttribute(k_traverse_lbvh<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 // Scenes with analytic primitives (s.n_prims > 0) run the ANALYTIC instantiations; everything else keeps the leaner
@@ -912,21 +862,15 @@ void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth,
   const bool ref = bvh == RTB_BVH_REFERENCE;
   if (s.n_prims > 0) {
     if (ref) k_traverse_ref<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth);
-    else k_traverse_lbvh<false, true, false><<<grid, kTravBlock, 0, st>>>(s, q, depth);
+    else k_traverse_lbvh<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth);
   } else if (smem_bytes > 0) {  // small scene: one 1024-thread block per SM works out of its shared-memory copy
     if (ref) k_traverse_ref<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
-    else k_traverse_lbvh<true, false, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
+    else k_traverse_lbvh<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
   } else {
     if (ref) k_traverse_ref<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth);
-    else k_traverse_lbvh<false, false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth);
+    else k_traverse_lbvh<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth);
   }
 }
-
-void launch_traverse_resume(const SceneView& s, const QueueView& q, int depth, int grid, cudaStream_t st) {
-  k_traverse_lbvh<false, false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth);
-}
-
-int traverse_block_threads() { return kTravBlock; }
 
 void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,
                   cudaStream_t st) {
