@@ -4,11 +4,13 @@
 // SetupMaterialBuffer (:455-499); rtb_render = RenderAsync (:212-380); rtb_render_device = RenderToTexture (:82-202).
 // There is no CPU fallback: every entry point that computes needs a CUDA device and fails with RTB_E_CUDA otherwise.
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -1116,17 +1118,25 @@ int rtb_gif_render_rotation(rtb_context* ctx, const rtb_render_params* base, int
   if (!host) return fail(ctx, RTB_E_CUDA, "cannot allocate pinned host memory for the frames");
   // frame k becomes ready when its rtb_render_end returned; workers compress ready frames in order of arrival
   std::vector<std::vector<uint8_t>> compressed((size_t)n_frames);
-  std::atomic<int> n_ready{0}, next{0};
-  std::atomic<bool> abort_flag{false};
+  std::mutex mu;
+  std::condition_variable cv;
+  int n_ready = 0;          // guarded by mu
+  bool abort_flag = false;  // guarded by mu
+  std::atomic<int> next{0};
   auto work = [&] {
     for (int k = next.fetch_add(1); k < n_frames; k = next.fetch_add(1)) {
-      while (n_ready.load(std::memory_order_acquire) <= k) {
-        if (abort_flag.load()) return;
-        std::this_thread::yield();
+      {
+        std::unique_lock<std::mutex> lock(mu);
+        cv.wait(lock, [&] { return n_ready > k || abort_flag; });
+        if (abort_flag) return;
       }
       compressed[(size_t)k].resize(gif_lzw_bound(n_px));
       compressed[(size_t)k].resize(gif_lzw(host + (size_t)k * n_px, n_px, compressed[(size_t)k].data()));
     }
+  };
+  auto publish = [&](int ready, bool failed) {
+    { std::lock_guard<std::mutex> lock(mu); n_ready = ready; abort_flag = abort_flag || failed; }
+    cv.notify_all();
   };
   const int t = gif_threads(threads, n_frames);
   std::vector<std::thread> pool;
@@ -1141,15 +1151,15 @@ int rtb_gif_render_rotation(rtb_context* ctx, const rtb_render_params* base, int
     p.cam_rot_euler_deg[0] = bx; p.cam_rot_euler_deg[1] = by; p.cam_rot_euler_deg[2] = (float)k * step_deg;
     if (k - ended >= in_flight) {
       rc = rtb_render_end(ctx, tickets[(size_t)ended]);
-      if (rc == RTB_OK) { ended++; n_ready.store(ended, std::memory_order_release); }
+      if (rc == RTB_OK) publish(++ended, false);
     }
     if (rc == RTB_OK) rc = rtb_render_begin_indexed(ctx, &p, host + (size_t)k * n_px, n_px, &tickets[(size_t)k]);
   }
   while (rc == RTB_OK && ended < n_frames) {
     rc = rtb_render_end(ctx, tickets[(size_t)ended]);
-    if (rc == RTB_OK) { ended++; n_ready.store(ended, std::memory_order_release); }
+    if (rc == RTB_OK) publish(++ended, false);
   }
-  if (rc != RTB_OK) abort_flag.store(true);
+  if (rc != RTB_OK) publish(ended, true);
   for (auto& th : pool) th.join();
   if (rc != RTB_OK) { rtb_synchronize(ctx); rtb_free_pinned(host); return rc; }
   std::vector<uint8_t> file;

@@ -8,13 +8,13 @@
 //
 //   k_traverse_{ref,lbvh}      every BVH query pending at this point, in ONE persistent kernel: the closest-hit rays of
 //                              depth d (:362) and the shadow rays emitted at depth d-1 (:395-406, as any-hit queries).
-//                              Warps claim 32 work items with one atomicAdd (RTB_REFILL_MIN < 32 additionally refills
-//                              individual lanes); traversal is "while-while": all lanes descend inner nodes, then all
-//                              lanes intersect their leaf.  A closest-hit ray ends by writing a 16-byte hit record, a
+//                              Warps claim up to 64 consecutive work items with one atomicAdd (fewer towards the end of the
+//                              queue) and refill their lanes as soon as 16 of them are idle; traversal is "while-while":
+//                              all lanes descend inner nodes, then all lanes intersect their leaf.  A closest-hit ray ends by writing a 16-byte hit record, a
 //                              shadow ray by adding the lit or unlit increment of :418 to its slot's sampleColor.
 //   k_shade                    miss/background :364-368, shading :370-418 (emits the shadow ray with both candidate
-//                              increments), continuation :420-473, compacted into the next depth's ray queue with one
-//                              ballot + one atomicAdd per warp and queue.
+//                              increments), continuation :420-473, compacted into the next depth's ray queue: warp ballots,
+//                              then one atomicAdd per BLOCK and queue (block_reserve), which keeps 256-entry runs contiguous.
 //
 //   k_resolve                  :475-478,510: average the spp slots of a pixel, saturate, UNORM8, store (possibly into a peer
 //                              GPU's frame: the NVLink gather is this store).

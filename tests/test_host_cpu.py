@@ -250,7 +250,7 @@ def test_band_partition_covers_every_row_once():
     bands = __import__("importlib").import_module("cosig-raytracing_b200.bands")
     for h in (1, 31, 32, 33, 150, 2160, 4320):
         for world in (1, 2, 3, 4, 8):
-            for band_rows in (4, 16, 32):
+            for band_rows in (4, 8, 16, 32):
                 seen = np.zeros(h, np.int32)
                 for rank in range(world):
                     rows = bands.owned_rows(h, rank, world, band_rows)
@@ -259,7 +259,7 @@ def test_band_partition_covers_every_row_once():
                 assert (seen == 1).all()
 
 
-def _gloo_worker(rank, world, port, h, w, out_q):
+def _gloo_worker(rank, world, port, h, w, out_q, band_rows=32):
     import importlib
     import torch
     import torch.distributed as dist
@@ -267,20 +267,20 @@ def _gloo_worker(rank, world, port, h, w, out_q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     bands = importlib.import_module("cosig-raytracing_b200.bands")
     full = (np.arange(h * w * 4, dtype=np.int64) % 251).astype(np.uint8).reshape(h, w, 4)  # the frame every rank would render
-    mine = torch.from_numpy(full[bands.owned_rows(h, rank, world, 32)].copy())
-    frame = bands.gather_bands(mine, h, w, rank, world, 32, dst=0)
+    mine = torch.from_numpy(full[bands.owned_rows(h, rank, world, band_rows)].copy())
+    frame = bands.gather_bands(mine, h, w, rank, world, band_rows, dst=0)
     if rank == 0:
         out_q.put(bool((frame.numpy() == full).all()))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("h", [64, 150])
-def test_gather_bands_world_size_2_gloo(h):
+@pytest.mark.parametrize("h,band_rows", [(64, 32), (150, 32), (150, 8)])  # bench.py shards by 8-row bands
+def test_gather_bands_world_size_2_gloo(h, band_rows):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() + h) % 2000
-    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, h, 48, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + h + band_rows) % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, h, 48, q, band_rows)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
@@ -304,3 +304,23 @@ def test_cpp_host_mirror_builds_and_runs_host_checks(pkg, tmp_path):
     r = subprocess.run([exe, "host", str(scene_file)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert "host OK 8 transformations" in r.stdout
+
+
+# ---- bench.py contract: one JSON line on stdout ------------------------------------------------------------------------------------
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """`bench.py --impl reference` (the CPU restatement on the host cores; needs no GPU) must put ONE JSON line on stdout with the
+    driver's keys; everything else (library banners, warnings) goes to stderr."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "cpu_baseline", "e2e", "impl"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
