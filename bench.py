@@ -325,7 +325,7 @@ def main():
     lib = abi.load()
     import ctypes as C
     n_flight = max(2, min(8, int(os.environ.get("RTB_LANES", "4"))))  # frames in flight of the pipelined host API = the library's lanes
-    pinned = [lib.rtb_alloc_pinned(frame_bytes) for _ in range(n_flight)]
+    pinned = [lib.rtb_alloc_pinned(frame_bytes) for _ in range(max(n_flight, 5))]
     host_views = [np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_uint8)), shape=(h, w, 4)) for pp in pinned]
     host_view = host_views[0]
     e2e_mode = f"rtb_render_begin/end, {n_flight} frames in flight, pinned host buffers" if world == 1 else "blocking per frame (barrier across ranks)"
@@ -347,31 +347,49 @@ def main():
                 if rank == 0:
                     host_view[:] = fr.cpu().numpy()
             return
-        # peer-store gather, software-pipelined over two contexts per rank: while every rank renders frame k into frame buffer
-        # k % 2 of rank 0, rank 0 reads frame k-1 back (its ranks finished it: context sync + barrier).
-        for k in range(n_steps + 1):
-            if k < n_steps:
-                if k >= 2:
-                    barrier()  # frame k reuses the buffer of frame k-2: rank 0 must have finished reading it
-                twin[k & 1].RenderToTexture(packed, p, twin_dst[k & 1], frame_bytes, sync=False)
-            if k >= 1:
-                twin[(k - 1) & 1].synchronize()
-                barrier()
-                if rank == 0:
-                    twin[(k - 1) & 1].frame_read(host_views[(k - 1) & 1])
-        host_view[:] = host_views[(n_steps - 1) & 1]
+        # peer-store gather, software-pipelined over R contexts per rank: D frames are in flight on every rank; a frame's
+        # bands land in frame buffer k % R of rank 0; once every rank has finished frame k-D (context sync + ONE barrier per
+        # frame) a host thread of rank 0 reads it back while the following frames render.  The same barrier certifies that
+        # rank 0 has finished reading frame k-R, whose buffer frame k overwrites.
+        import threading
+        readers = [None] * R
 
-    twin, twin_dst = [rt, None], [dst_ptr, None]
+        def read_back(j):
+            ring[j].frame_read(host_views[j])
+
+        for k in range(n_steps + D):
+            j = k % R
+            if readers[j] is not None:
+                readers[j].join()  # rank 0: frame k-R is in host memory
+                readers[j] = None
+            if k >= D:
+                ring[(k - D) % R].synchronize()  # this rank's bands of frame k-D are stored
+                barrier()
+            if k < n_steps:
+                ring[j].RenderToTexture(packed, p, ring_dst[j], frame_bytes, sync=False)
+            if k >= D and rank == 0:
+                j1 = (k - D) % R
+                readers[j1] = threading.Thread(target=read_back, args=(j1,))
+                readers[j1].start()
+        for t in readers:
+            if t is not None:
+                t.join()
+        host_view[:] = host_views[(n_steps - 1) % R]
+
+    D, R = 3, 5  # frames in flight per rank, frame buffers (contexts) per rank
+    ring, ring_dst = [rt] + [None] * (R - 1), [dst_ptr] + [None] * (R - 1)
     if world > 1 and args.gather == "peer":
-        e2e_mode = "two contexts per rank: frame k renders on all ranks while rank 0 reads frame k-1 back (barrier per frame)"
-        twin[1] = rt_mod.RayTracer(devices=[local_rank], bvh_mode=rt.bvh_mode, primitive_mode=rt.primitive_mode)
-        handle2 = [None]
-        if rank == 0:
-            ptr1, hb = twin[1].frame_export(frame_bytes)
-            handle2[0] = hb
-        dist.broadcast_object_list(handle2, src=0)
-        twin_dst[1] = ptr1 if rank == 0 else twin[1].frame_import(handle2[0])
-        twin[1].RenderToTexture(packed, p, twin_dst[1], frame_bytes, sync=True)  # uploads the scene to the second context
+        e2e_mode = (f"{R} contexts per rank, {D} frames in flight: frames k-{D - 1}..k render on all ranks while a host thread of rank 0 reads "
+                    f"frame k-{D} back (one barrier per frame)")
+        for j in range(1, R):
+            ring[j] = rt_mod.RayTracer(devices=[local_rank], bvh_mode=rt.bvh_mode, primitive_mode=rt.primitive_mode)
+            handle_j = [None]
+            if rank == 0:
+                ptr_j, hb = ring[j].frame_export(frame_bytes)
+                handle_j[0] = hb
+            dist.broadcast_object_list(handle_j, src=0)
+            ring_dst[j] = ptr_j if rank == 0 else ring[j].frame_import(handle_j[0])
+            ring[j].RenderToTexture(packed, p, ring_dst[j], frame_bytes, sync=True)  # uploads the scene to this context
 
     run_e2e(n_flight)
     torch.cuda.synchronize(); rt.synchronize(); barrier()
@@ -485,8 +503,9 @@ def main():
     for pp in pinned:
         lib.rtb_free_pinned(pp)
     barrier()
-    if twin[1] is not None:
-        twin[1].close()
+    for extra in ring[1:]:
+        if extra is not None:
+            extra.close()
     rt.close()
     if world > 1:
         dist.destroy_process_group()
