@@ -7,13 +7,15 @@
 A "step" is one frame of the workload.  1 ray = one TraverseBVH-equivalent query (primary, continuation or shadow ray),
 counted on the device and identical to the CPU oracle's count in parity mode.  Default workload = C4 (BASELINE.json
 configs[3], the config the >= 1 Grays/s target is quoted on: synthetic 1 000 000-triangle height field, GPU-built LBVH,
-3840x2160, depth 6, 1 spp).  With N > 1 the SAME frame is sharded by 32-row bands over the ranks (strong scaling) and
-gathered on rank 0 over NVLink: by default each rank's resolve kernel stores straight into rank 0's frame through a
-CUDA-IPC peer mapping (no collective), `--gather nccl` uses torch.distributed.gather of packed bands instead.
+3840x2160, depth 6, 1 spp).  With N > 1 the SAME frame is sharded by bands of `--band-rows` rows (default 8) over the ranks
+(strong scaling) and gathered on rank 0 over NVLink: by default each rank's resolve kernel stores straight into rank 0's
+frame through a CUDA-IPC peer mapping (no collective), `--gather nccl` uses torch.distributed.gather of packed bands instead.
 
-Printed JSON (rank 0, one line): the driver's contract plus `roofline` (dominant kernel family k_trace_shade, algorithmic
-bytes per SURVEY.md §8d ÷ CUDA-event time), `cpu_baseline` (the CPU oracle on a bounded sample of the same frame) and
-`e2e` (the same metric through rtb_render with a HOST output buffer, readback inside the timed region).
+Printed JSON (rank 0, ONE line on stdout; everything else goes to stderr): the driver's contract plus `roofline` (dominant kernel
+family k_traverse, algorithmic bytes per SURVEY.md §8d ÷ CUDA-event time), `cpu_baseline` (the CPU oracle on a bounded sample of
+the same frame) and `e2e` (the same metric through the host API with HOST output buffers, readback inside the timed region:
+N = 1 rtb_render_begin / rtb_render_end with as many frames in flight as lanes; N > 1 five frame buffers on rank 0, three frames
+in flight per rank, one barrier per frame, rank 0 reads every frame back on a host thread).
 `--impl reference` times the CPU restatement of the reference renderer (oracle/) on the host cores: the reference itself
 is Unity C# + HLSL and cannot run here.
 """
