@@ -1087,22 +1087,19 @@ int rtb_gif_index_device(rtb_context* ctx, const void* rgba8_device, int32_t wid
 
 int rtb_gif_save(rtb_context* ctx, const char* path, int32_t width, int32_t height, const uint8_t* const* rgba8_frames, int32_t n_frames,
                  int32_t frame_delay_cs, int32_t threads) {
-  if (!path || !rgba8_frames || n_frames <= 0 || width <= 0 || height <= 0) return ctx ? fail(ctx, RTB_E_ARG, "bad argument") : RTB_E_ARG;
+  if (!ctx) return RTB_E_ARG;  // the palette mapping is a device kernel: there is no host fallback
+  if (!path || !rgba8_frames || n_frames <= 0 || width <= 0 || height <= 0) return fail(ctx, RTB_E_ARG, "bad argument");
   const size_t n_px = (size_t)width * height;
   std::vector<std::vector<uint8_t>> indexed((size_t)n_frames, std::vector<uint8_t>(n_px));
   std::vector<const uint8_t*> ptrs((size_t)n_frames);
   for (int k = 0; k < n_frames; k++) {
-    if (!rgba8_frames[k]) return ctx ? fail(ctx, RTB_E_ARG, "null frame") : RTB_E_ARG;
-    if (ctx) {
-      const int rc = rtb_gif_index_frame(ctx, rgba8_frames[k], width, height, indexed[(size_t)k].data());
-      if (rc != RTB_OK) return rc;
-    } else {
-      gif_index_frame_host(rgba8_frames[k], width, height, indexed[(size_t)k].data());
-    }
+    if (!rgba8_frames[k]) return fail(ctx, RTB_E_ARG, "null frame");
+    const int rc_k = rtb_gif_index_frame(ctx, rgba8_frames[k], width, height, indexed[(size_t)k].data());
+    if (rc_k != RTB_OK) return rc_k;
     ptrs[(size_t)k] = indexed[(size_t)k].data();
   }
   const int rc = rtb_gif_save_indexed(path, width, height, ptrs.data(), n_frames, frame_delay_cs, threads);
-  return (rc != RTB_OK && ctx) ? fail(ctx, rc, std::string("cannot write ") + path) : rc;
+  return rc != RTB_OK ? fail(ctx, rc, std::string("cannot write ") + path) : rc;
 }
 
 int rtb_gif_render_rotation(rtb_context* ctx, const rtb_render_params* base, int32_t n_frames, float step_deg, const char* path,

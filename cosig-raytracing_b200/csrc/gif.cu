@@ -24,16 +24,10 @@ namespace rtb {
 
 namespace {
 
-// (int)(channel * 5.99f) clamped to 0..5, channel = byte / 255f as Texture2D.GetPixels() hands it out (GifGenerator.cs:353-356)
-__host__ __device__ __forceinline__ int cube_level(unsigned b) {
-#ifdef __CUDA_ARCH__
-  const float c = __fdiv_rn((float)b, 255.0f);
-  const int v = (int)__fmul_rn(c, 5.99f);
-#else
-  const float c = (float)b / 255.0f;
-  volatile float m = c * 5.99f;  // one FP32 rounding, no contraction with the division
-  const int v = (int)m;
-#endif
+// (int)(channel * 5.99f) clamped to 0..5, channel = byte / 255f as Texture2D.GetPixels() hands it out (GifGenerator.cs:353-356);
+// individually rounded FP32 division and product, like the C# expression
+__device__ __forceinline__ int cube_level(unsigned b) {
+  const int v = (int)__fmul_rn(__fdiv_rn((float)b, 255.0f), 5.99f);
   return v < 0 ? 0 : (v > 5 ? 5 : v);
 }
 
@@ -108,16 +102,6 @@ void launch_palette(const void* rgba8, int width, int height, uint8_t* indexed, 
   int64_t grid = (work + kBlock - 1) / kBlock;
   if (grid > 148 * 16) grid = 148 * 16;
   k_palette<<<(int)grid, kBlock, 0, st>>>((const uchar4*)rgba8, width, height, indexed);
-}
-
-void gif_index_frame_host(const uint8_t* rgba8, int width, int height, uint8_t* indexed) {
-  uint8_t level[256];
-  for (int i = 0; i < 256; i++) level[i] = (uint8_t)cube_level((unsigned)i);
-  for (int y = 0; y < height; y++) {
-    const uint8_t* src = rgba8 + (size_t)(height - 1 - y) * width * 4;
-    uint8_t* dst = indexed + (size_t)y * width;
-    for (int x = 0; x < width; x++) dst[x] = (uint8_t)(level[src[4 * x]] * 36 + level[src[4 * x + 1]] * 6 + level[src[4 * x + 2]]);
-  }
 }
 
 void gif_color_table(uint8_t* table) {  // :219-247

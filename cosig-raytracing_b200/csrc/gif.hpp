@@ -13,8 +13,6 @@ namespace rtb {
 // ConvertToIndexed (GifGenerator.cs:346-369) on the device: rgba8 = RGBA8 frame with row 0 = bottom; indexed = width*height
 // palette indices, top row first.  Asynchronous on `st`.
 void launch_palette(const void* rgba8, int width, int height, uint8_t* indexed, cudaStream_t st);
-// The same on the host (rtb_gif_save without a context; also what the device kernel is tested against besides the oracle).
-void gif_index_frame_host(const uint8_t* rgba8, int width, int height, uint8_t* indexed);
 void gif_color_table(uint8_t* rgb768);
 size_t gif_lzw_bound(size_t n);
 size_t gif_lzw(const uint8_t* data, size_t n, uint8_t* out);  // LzwCompress, :411-501; returns bytes written

@@ -121,13 +121,3 @@ def save_indexed(filePath: str, frames: Sequence[np.ndarray], frameDelay: int = 
     rc = abi.load().rtb_gif_save_indexed(filePath.encode(), w, h, ptrs, len(arrs), int(frameDelay), int(threads))
     if rc != abi.RTB_OK:
         raise RtbError(rc, f"rtb_gif_save_indexed failed for {filePath}")
-
-
-def save_rgba_host(filePath: str, frames: Sequence[np.ndarray], frameDelay: int = 10, threads: int = 0) -> None:
-    """rtb_gif_save with a NULL context: palette mapping on the host too (no GPU needed; used by the CPU tests)."""
-    arrs = [np.ascontiguousarray(f, np.uint8) for f in frames]
-    h, w = arrs[0].shape[:2]
-    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
-    rc = abi.load().rtb_gif_save(None, filePath.encode(), w, h, ptrs, len(arrs), int(frameDelay), int(threads))
-    if rc != abi.RTB_OK:
-        raise RtbError(rc, f"rtb_gif_save failed for {filePath}")

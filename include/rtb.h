@@ -238,8 +238,8 @@ int rtb_gif_index_device(rtb_context* ctx, const void* rgba8_device, int32_t wid
 /* Like rtb_render_begin, but the frame is converted on the device (ConvertToIndexed) and only the width*height palette
  * indices are read back into `indexed` (top row first).  Shares the ticket ring with rtb_render_begin; wait with rtb_render_end. */
 int rtb_render_begin_indexed(rtb_context* ctx, const rtb_render_params* p, uint8_t* indexed, size_t bytes, int32_t* ticket);
-/* SaveGifAsync :82-155 for frames given as palette indices (top row first) / as RGBA8 Texture2D data (row 0 = bottom; ctx may
- * be NULL: then the palette mapping also runs on the host).  threads <= 0: all host cores. */
+/* SaveGifAsync :82-155 for frames given as palette indices (top row first; host-only: LZW + container) / as RGBA8 Texture2D data
+ * (row 0 = bottom; the palette mapping runs on the device, so a context is required).  threads <= 0: all host cores. */
 int rtb_gif_save_indexed(const char* path, int32_t width, int32_t height, const uint8_t* const* frames, int32_t n_frames,
                          int32_t frame_delay_cs, int32_t threads);
 int rtb_gif_save(rtb_context* ctx, const char* path, int32_t width, int32_t height, const uint8_t* const* rgba8_frames, int32_t n_frames,

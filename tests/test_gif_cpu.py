@@ -1,6 +1,7 @@
 """GIF sweep, CPU part: the library's host coder / container writer against the oracle's restatement of
 GifGenerator.cs, and BOTH against an independent GIF decoder (PIL) — the only externally pinned check this repo can make,
-because the reference ships no GIF fixtures.  No CUDA device is needed: rtb_gif_save with a NULL context maps pixels on the host.
+because the reference ships no GIF fixtures.  No CUDA device is needed here: the palette mapping (a device kernel, no host
+fallback) is covered by tests/test_gpu_gif.py; these tests feed the library palette indices.
 """
 import importlib
 import io
@@ -74,7 +75,7 @@ def test_file_matches_oracle_and_decodes(pkg, oracle, tmp_path, shape, smooth):
     n, h, w = shape
     frames = _frames(n, h, w, seed=n * 100 + w, smooth=smooth)
     ours, theirs = str(tmp_path / "ours.gif"), str(tmp_path / "oracle.gif")
-    gif.save_rgba_host(ours, list(frames), frameDelay=10, threads=2)
+    gif.save_indexed(ours, [oracle.gif_convert_to_indexed(f) for f in frames], frameDelay=10, threads=2)
     oracle.gif_save(theirs, frames, 10)
     a, b = open(ours, "rb").read(), open(theirs, "rb").read()
     assert a == b, "library GIF differs from the restated GifGenerator.SaveGif output"
@@ -92,13 +93,23 @@ def test_file_matches_oracle_and_decodes(pkg, oracle, tmp_path, shape, smooth):
         assert (decoded_rgb == table.reshape(256, 3)[expected]).all(), f"frame {k}: PIL decodes other pixels than were encoded"
 
 
-def test_save_indexed_equals_rgba_path(pkg, oracle, tmp_path):
+def test_save_indexed_is_independent_of_thread_count(pkg, oracle, tmp_path):
     frames = _frames(3, 20, 28, seed=5)
     indexed = [oracle.gif_convert_to_indexed(f) for f in frames]
     a, b = str(tmp_path / "a.gif"), str(tmp_path / "b.gif")
     gif.save_indexed(a, indexed, frameDelay=7, threads=1)
-    gif.save_rgba_host(b, list(frames), frameDelay=7, threads=3)
+    gif.save_indexed(b, indexed, frameDelay=7, threads=3)
     assert open(a, "rb").read() == open(b, "rb").read()
+
+
+def test_rgba_frames_need_a_context(pkg, tmp_path):
+    # palette mapping is a CUDA kernel: without a context the call is refused instead of falling back to the host
+    import ctypes as C
+    lib = importlib.import_module("cosig-raytracing_b200.abi").load()
+    frame = _frames(1, 4, 4)[0]
+    ptrs = (C.c_void_p * 1)(frame.ctypes.data)
+    assert lib.rtb_gif_save(None, str(tmp_path / "x.gif").encode(), 4, 4, ptrs, 1, 10, 1) == -1  # RTB_E_ARG
+    assert not (tmp_path / "x.gif").exists()
 
 
 def test_save_gif_empty_is_a_no_op(pkg, tmp_path):
