@@ -67,6 +67,8 @@ struct DeviceState {
   bool copy_pending = false;
   void* frame_async[kMaxLanes] = {};  // frames of rtb_render_begin, rotating, so a readback never races the following frames
   size_t frame_async_bytes[kMaxLanes] = {};
+  struct ChunkRows { int lane, row0, rows; };
+  std::vector<ChunkRows> last_chunks;  // chunks of the frame enqueued last (rtb_render copies them back one by one)
   void* gif_scratch = nullptr;        // rtb_gif_index_frame: one RGBA8 frame + its palette indices
   size_t gif_scratch_bytes = 0;
   void* index_async[kMaxLanes] = {};  // palette-index frames of rtb_render_begin_indexed (GIF sweep), same rotation
@@ -95,6 +97,8 @@ struct rtb_context {
   rtb_stats stats{};
   const volatile int32_t* cancel = nullptr;
   bool profiling = false;
+  int64_t chunk_slots_once = 0;  // rtb_render: chunk size of the frame being enqueued (a blocking frame is split over the lanes), 0 = chunk_slots
+  int split_blocking = 1;        // RTB_SPLIT_BLOCKING: 0 = one chunk per blocking frame as long as it fits chunk_slots
   int64_t chunk_slots = 1 << 24;  // RTB_CHUNK_SLOTS: pixel-samples per chunk (192 B of queues each, per lane); C5 sweep: profiles/r1e_sweep_chunk_slots_c5.log
   int n_lanes = 4;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues
   uint64_t frame_id = 0;
@@ -345,7 +349,7 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
   const int32_t local_rows = band_local_rows(f.height, f.band_rank, f.band_world, f.band_rows);
   const int32_t tiles_x = (f.width + 7) / 8;
   const int64_t slots_per_tile_row = (int64_t)tiles_x * 32 * f.spp;  // 4 pixel rows
-  int64_t tile_rows_per_chunk = ctx->chunk_slots / slots_per_tile_row;
+  int64_t tile_rows_per_chunk = (ctx->chunk_slots_once > 0 ? std::min(ctx->chunk_slots_once, ctx->chunk_slots) : ctx->chunk_slots) / slots_per_tile_row;
   if (tile_rows_per_chunk < 1) tile_rows_per_chunk = 1;
   if (tile_rows_per_chunk * slots_per_tile_row > (int64_t)INT32_MAX - 64) return fail(ctx, RTB_E_ARG, "a 4-row strip of this frame exceeds 2^31 samples");
   const int32_t rows_per_chunk = (int32_t)std::min<int64_t>(tile_rows_per_chunk * 4, ((int64_t)local_rows + 3) / 4 * 4);
@@ -362,9 +366,11 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
     }
   }
   d.prof_used[0] = d.prof_used[1] = d.prof_used[2] = 0;
+  d.last_chunks.clear();
   for (int32_t row0 = 0; row0 < local_rows; row0 += rows_per_chunk) {
     LaneState& L = d.lane[d.next_lane];
     d.last_lane = d.next_lane;
+    d.last_chunks.push_back({d.next_lane, row0, std::min(rows_per_chunk, local_rows - row0)});
     d.next_lane = ctx->profiling ? d.next_lane : (d.next_lane + 1) % ctx->n_lanes;  // profiling: one lane, so per-launch event intervals do not overlap
     cudaStream_t stream = L.stream;
     if (ctx->cancel && *ctx->cancel) { device_sync(d); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
@@ -580,6 +586,7 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
   }
   if (const char* env = std::getenv("RTB_LANES")) ctx->n_lanes = std::min((int)DeviceState::kMaxLanes, std::max(1, std::atoi(env)));
   if (const char* env = std::getenv("RTB_SMEM")) ctx->smem_mode = std::atoi(env);
+  if (const char* env = std::getenv("RTB_SPLIT_BLOCKING")) ctx->split_blocking = std::atoi(env);
   if (const char* env = std::getenv("RTB_TAIL_MAX")) ctx->tail_max = (int32_t)std::max(0LL, std::atoll(env));
   ctx->devs.resize(ids.size());
   for (size_t k = 0; k < ids.size(); k++) {
@@ -720,13 +727,37 @@ int rtb_render(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, siz
     if (bytes < (size_t)f.width * f.height * 4) return fail(ctx, RTB_E_SIZE, "rgba8 buffer too small for the resolved resolution");
   }
   FrameParams f;
+  // A blocking frame has nothing else in flight to hide the end of its launches behind, so a large one is split into one row
+  // range per lane: the ranges render concurrently and each is copied back as soon as its resolve kernel has finished (C4:
+  // 5.2 -> 4.9 ms).  Small frames lose more to the four-fold launch count than they gain (1080p sample scene: 0.89 -> 1.24 ms),
+  // hence the 4 M pixel-sample threshold.
+  const bool split = ctx->split_blocking != 0 && ctx->devs.size() == 1 && ctx->n_lanes > 1 && !ctx->profiling && ctx->has_scene;
+  if (split) {
+    FrameParams g;
+    std::string why;
+    if (!resolve_frame(ctx->host.d, *p, g, why)) return fail(ctx, RTB_E_ARG, why);
+    const int64_t slots = (int64_t)((g.width + 7) / 8) * ((g.height + 3) / 4) * 32 * g.spp;
+    if (slots >= (1 << 22) && g.debug == 0) ctx->chunk_slots_once = (slots + ctx->n_lanes - 1) / ctx->n_lanes;
+  }
   const int rc = render_frame(ctx, p, nullptr, 0, /*to_internal_frame=*/true, /*sync=*/false, f);
+  const bool was_split = ctx->chunk_slots_once > 0;
+  ctx->chunk_slots_once = 0;
   if (rc != RTB_OK) return rc;
   DeviceState& d0 = ctx->devs[0];
   const size_t need = (size_t)f.width * f.height * 4;
   CK(ctx, cudaSetDevice(d0.device));
-  CK(ctx, join_lanes(d0));
-  CK(ctx, cudaMemcpyAsync(rgba8, d0.frame, need, cudaMemcpyDeviceToHost, d0.stream));  // ReadPixels, RayTracer.cs:371-375
+  if (was_split && !d0.last_chunks.empty()) {  // ReadPixels (RayTracer.cs:371-375), one row range at a time, on the copy stream
+    const size_t row_bytes = (size_t)f.width * 4;
+    for (const auto& c : d0.last_chunks) {
+      CK(ctx, cudaStreamWaitEvent(d0.copy_stream, d0.lane[c.lane].ev_done, 0));
+      CK(ctx, cudaMemcpyAsync(rgba8 + (size_t)c.row0 * row_bytes, (const uint8_t*)d0.frame + (size_t)c.row0 * row_bytes, (size_t)c.rows * row_bytes,
+                              cudaMemcpyDeviceToHost, d0.copy_stream));
+    }
+    d0.copy_pending = true;
+  } else {
+    CK(ctx, join_lanes(d0));
+    CK(ctx, cudaMemcpyAsync(rgba8, d0.frame, need, cudaMemcpyDeviceToHost, d0.stream));  // ReadPixels, RayTracer.cs:371-375
+  }
   for (auto& d : ctx->devs) device_sync(d);
   CK(ctx, cudaSetDevice(d0.device));
   CK(ctx, cudaGetLastError());
