@@ -120,3 +120,25 @@ def test_save_gif_empty_is_a_no_op(pkg, tmp_path):
     g.SaveGif([], str(tmp_path / "none.gif"))
     g.SaveGifAsync([], str(tmp_path / "none.gif"))
     assert not (tmp_path / "none.gif").exists()
+
+
+def test_golden_rotation_gif(pkg, oracle, tmp_path):
+    """tests/golden/rotation_test_scene_1_48x36.gif (make_golden_gif.py): the oracle still writes these bytes, the library's coder
+    writes them from the oracle's indices, and PIL reads 4 frames of 48x36 out of them."""
+    import os
+    import sys
+    from PIL import Image
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import make_golden_gif as G
+    want = open(G.PATH, "rb").read()
+    frames = G.oracle_frames()
+    again = str(tmp_path / "oracle.gif")
+    oracle.gif_save(again, frames, 10)
+    assert open(again, "rb").read() == want, "the oracle no longer reproduces its golden GIF"
+    ours = str(tmp_path / "ours.gif")
+    gif.save_indexed(ours, [oracle.gif_convert_to_indexed(f) for f in frames], frameDelay=10)
+    assert open(ours, "rb").read() == want
+    im = Image.open(G.PATH)
+    assert im.n_frames == 4 and im.size == (48, 36)
+    assert len({np.asarray(im.convert("RGB")).tobytes() for _ in [im.seek(k) for k in range(4)]}) >= 1

@@ -116,3 +116,15 @@ def test_cpp_gif_generator_mirror(oracle, tmp_path):
     ref = str(tmp_path / "oracle.gif")
     oracle.gif_save(ref, np.stack(frames), 10)
     assert open(out, "rb").read() == open(ref, "rb").read()
+
+
+def test_fused_sweep_reproduces_the_committed_golden_gif(rt, tmp_path):
+    """No oracle at run time: rtb_gif_render_rotation (4 frames, 90-degree steps, 48x36, depth 2) must write exactly
+    tests/golden/rotation_test_scene_1_48x36.gif."""
+    import os
+    want = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rotation_test_scene_1_48x36.gif"), "rb").read()
+    obj = synth.sample_scene("test_scene_1")
+    st = scene_mod.RenderSettings(ResolutionOverride=(48, 36), MaxDepth=2, CameraPositionOverride=(0.0, 0.0, 0.0), CameraRotationOverride=(-60.0, 0.0, 0.0))
+    path = str(tmp_path / "golden_check.gif")
+    gif.GifGenerator(rt, obj).RenderRotationGif(st, path, frameDelay=10, totalFrames=4, stepDeg=90.0)
+    assert open(path, "rb").read() == want
