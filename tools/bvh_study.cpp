@@ -144,6 +144,7 @@ static inline bool hit_tri(const Tri& t, V3 o, V3 d, float& tt) {
 }
 
 struct Counts { double records = 0, tris = 0, hits = 0; long long rays = 0; int max_records = 0; };
+static std::vector<int> per_ray;  // node records + triangle tests of every ray (steps of the while-while loop)
 
 static void trace(int32_t root, const float* rays, long long m, Counts& c) {
 #pragma omp parallel
@@ -188,6 +189,7 @@ static void trace(int32_t root, const float* rays, long long m, Counts& c) {
         while (sp > 0) { sp--; if (!(stack_d[sp] >= best)) { cur = stack_ref[sp]; break; } }
         if (cur == INT32_MIN) break;
       }
+      per_ray[(size_t)r] = recs;
       local.records += recs; local.rays++; local.hits += found; local.max_records = std::max(local.max_records, recs);
     }
 #pragma omp critical
@@ -261,9 +263,14 @@ int main(int argc, char** argv) {
     Box rb = range_box(0, (int)n);
     for (const Node& nd : nodes) sah += nd.box[0].area() + nd.box[1].area();
     Counts c;
+    per_ray.assign((size_t)m, 0);
     trace(root, rays.data(), m, c);
-    std::printf("%-6s nodes %zu  sum(child area)/root area %.1f | rays %lld: records/ray %.2f, triangles/ray %.2f, hit fraction %.3f, longest ray %d records\n",
-                names[how], nodes.size(), sah / rb.area(), c.rays, c.records / c.rays, c.tris / c.rays, c.hits / c.rays, c.max_records);
+    // lock-step bound: 32 consecutive rays share a warp; without refill the warp runs as long as its longest ray
+    double sum_max = 0.0; long long groups = 0;
+    for (long long g = 0; g + 32 <= m; g += 32) { int mx = 0; for (int k = 0; k < 32; k++) mx = std::max(mx, per_ray[(size_t)(g + k)]); sum_max += mx; groups++; }
+    const double lockstep = groups ? (c.records / c.rays) / (sum_max / groups) : 0.0;
+    std::printf("%-6s nodes %zu  sum(child area)/root area %.1f | rays %lld: records/ray %.2f, triangles/ray %.2f, hit fraction %.3f, longest ray %d records, mean/max over 32 consecutive rays %.2f\n",
+                names[how], nodes.size(), sah / rb.area(), c.rays, c.records / c.rays, c.tris / c.rays, c.hits / c.rays, c.max_records, lockstep);
   }
   return 0;
 }
