@@ -1075,6 +1075,13 @@ void orc_primary_ray(const orc_scene* s, const rtb_render_params* p, int32_t px,
   o3[0] = r.o.x; o3[1] = r.o.y; o3[2] = r.o.z; d3[0] = r.d.x; d3[1] = r.d.y; d3[2] = r.d.z;
 }
 
+// The primary ray of AA sample `sample` of pixel (px,py) (stratified cell + Hash22 jitter, compute:296-340); sample = -1: centre ray.
+void orc_sample_ray(const orc_scene* s, const rtb_render_params* p, int32_t px, int32_t py, int32_t sample, float* o3, float* d3) {
+  Frame f = resolve_frame(s->s, *p);
+  Ray r = gen_ray(f, px, py, sample);
+  o3[0] = r.o.x; o3[1] = r.o.y; o3[2] = r.o.z; d3[0] = r.d.x; d3[1] = r.d.y; d3[2] = r.d.z;
+}
+
 // Brute force over ALL triangles in emission order (no BVH): closest t, and the emission ids attaining exactly that t.
 // Returns the number of ties (>=1 on a hit, 0 on a miss); at most `cap` ids are written.
 int32_t orc_brute_closest(const orc_scene* s, const float* o3, const float* d3, float* t_out, int32_t* ids, int32_t cap) {

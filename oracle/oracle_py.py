@@ -66,6 +66,7 @@ def lib():
                                  C.POINTER(Counters)]
         L.orc_primary_ray.argtypes = [VP, C.POINTER(_abi.RenderParams), C.c_int32, C.c_int32, VP, VP]
         L.orc_brute_closest.argtypes = [VP, VP, VP, VP, VP, C.c_int32]
+        L.orc_sample_ray.argtypes = [VP, C.POINTER(_abi.RenderParams), C.c_int32, C.c_int32, C.c_int32, VP, VP]
         L.orc_gif_color_table.argtypes = [VP]
         L.orc_gif_convert_to_indexed.argtypes = [VP, C.c_int32, C.c_int32, VP]
         L.orc_gif_lzw.argtypes = [VP, C.c_int64, VP, C.c_int64]
@@ -176,6 +177,12 @@ class OracleScene:
         o = np.zeros(3, np.float32)
         d = np.zeros(3, np.float32)
         lib().orc_primary_ray(self.h, C.byref(params), px, py, o.ctypes.data, d.ctypes.data)
+        return o, d
+
+    def sample_ray(self, params, px, py, sample):
+        o = np.zeros(3, np.float32)
+        d = np.zeros(3, np.float32)
+        lib().orc_sample_ray(self.h, C.byref(params), px, py, sample, o.ctypes.data, d.ctypes.data)
         return o, d
 
     def brute_closest(self, o, d, cap=16):

@@ -295,3 +295,72 @@ def test_whole_frame_against_float64_brute_force(pkg, oracle, name, w, h, depth)
     within = float((diff <= 1).mean())
     assert within >= 0.99, f"{name}: only {within * 100:.2f}% of pixels within 1/255 (worst {int(diff.max())})"
     assert len(np.unique(ref.reshape(-1, 3), axis=0)) > 20  # a real picture, not a constant frame
+
+
+# ---- anti-aliasing samples: Hash22 jitter and ray generation in FP32, written from the shader text --------------------------------
+def _f(x):
+    return np.float32(x)
+
+
+def _frac32(x):
+    return _f(x - np.floor(x))
+
+
+def _hash22_f32(px, py):
+    """Hash22, BVHRayTracing.compute:108-113, every operation individually rounded to FP32 (dot = (a.x b.x + a.y b.y) + a.z b.z)."""
+    a, b, c = _frac32(_f(px) * _f(.1031)), _frac32(_f(py) * _f(.1030)), _frac32(_f(px) * _f(.0973))
+    k = _f(33.33)
+    d = _f(_f(_f(a * _f(b + k)) + _f(b * _f(c + k))) + _f(c * _f(a + k)))  # dot(p3, p3.yzx + 33.33)
+    a, b, c = _f(a + d), _f(b + d), _f(c + d)
+    return _frac32(_f(_f(a + b) * c)), _frac32(_f(_f(a + c) * b))             # frac((p3.xx + p3.yz) * p3.zy)
+
+
+def _normalize_f32(v):
+    d = _f(_f(_f(v[0] * v[0]) + _f(v[1] * v[1])) + _f(v[2] * v[2]))
+    r = _f(_f(1.0) / np.sqrt(d, dtype=np.float32))
+    return np.array([_f(v[0] * r), _f(v[1] * r), _f(v[2] * r)], np.float32)
+
+
+def _sample_ray_f32(u25, w, h, n_samples, px, py, i):
+    """compute:283-340 for AA sample i of pixel (px, py), perspective camera."""
+    M = u25[:16].reshape(4, 4)
+    cam_d, tan_half = _f(u25[16]), _f(u25[17])
+    grid_w = int(np.ceil(np.sqrt(np.float32(n_samples))))
+    grid_h = int(np.ceil(np.float32(n_samples) / np.float32(grid_w)))
+    aspect = _f(_f(w) / _f(h))
+    plane_h = _f(_f(2.0) * _f(cam_d * tan_half))
+    plane_w = _f(plane_h * aspect)
+    ox, oy = _f(0.5), _f(0.5)
+    if n_samples > 1:
+        gy, gx = i // grid_w, i % grid_w
+        jx, jy = _hash22_f32(_f(_f(px) + _f(_f(i) * _f(13.0))), _f(_f(py) + _f(_f(i) * _f(7.0))))
+        ox = _f(_f(_f(gx) + jx) / _f(grid_w))
+        oy = _f(_f(_f(gy) + jy) / _f(grid_h))
+    u = _f(_f(_f(_f(_f(px) + ox) / _f(w)) - _f(0.5)) * plane_w)
+    v = _f(_f(_f(_f(_f(py) + oy) / _f(h)) - _f(0.5)) * plane_h)
+    dc = _normalize_f32(np.array([_f(u - _f(0.0)), _f(v - _f(0.0)), _f(_f(0.0) - cam_d)], np.float32))
+    oc = np.array([0.0, 0.0, cam_d], np.float32)
+    o = np.array([_f(_f(_f(_f(M[r, 0] * oc[0]) + _f(M[r, 1] * oc[1])) + _f(M[r, 2] * oc[2])) + _f(M[r, 3] * _f(1.0))) for r in range(3)], np.float32)
+    d = _normalize_f32(np.array([_f(_f(_f(M[r, 0] * dc[0]) + _f(M[r, 1] * dc[1])) + _f(M[r, 2] * dc[2])) for r in range(3)], np.float32))
+    return o, d
+
+
+@pytest.mark.parametrize("n_samples", [1, 4, 9, 16, 5])
+def test_aa_sample_rays_bit_exact_against_fp32_numpy(pkg, oracle, n_samples):
+    """Stratified grid + Hash22 jitter + camera transform of every AA sample (compute:283-340), restated in numpy FP32 from the
+    shader text with the rounding conventions of SURVEY App. D: origin and direction bits must equal the oracle's."""
+    obj = synth.sample_scene("test_scene_1")
+    osc, holder = oracle_scene(oracle, obj)
+    w, h = 200, 150
+    p = params(w, h, 1, n_samples)
+    u25 = np.zeros(25, np.float32)
+    wh = (C.c_int32 * 2)()
+    assert abi.load().rtb_resolve_frame(holder.ptr(), C.byref(p), u25.ctypes.data_as(C.POINTER(C.c_float)), wh) == abi.RTB_OK
+    rng = np.random.RandomState(n_samples)
+    with np.errstate(over="ignore"):
+        for _ in range(60):
+            px, py, i = int(rng.randint(0, w)), int(rng.randint(0, h)), int(rng.randint(0, n_samples))
+            o, d = osc.sample_ray(p, px, py, i)
+            o2, d2 = _sample_ray_f32(u25, w, h, n_samples, px, py, i)
+            assert o.tobytes() == o2.tobytes(), (px, py, i, o, o2)
+            assert d.tobytes() == d2.tobytes(), (px, py, i, d, d2)
