@@ -1075,6 +1075,12 @@ void orc_primary_ray(const orc_scene* s, const rtb_render_params* p, int32_t px,
   o3[0] = r.o.x; o3[1] = r.o.y; o3[2] = r.o.z; d3[0] = r.d.x; d3[1] = r.d.y; d3[2] = r.d.z;
 }
 
+// RandomUnitVector (compute:124-131) as the oracle evaluates it: Hash33 in FP32 and the fixed polynomial sin / cos.
+void orc_random_unit_vector(const float* seed3, float* out3) {
+  const V3 r = RandomUnitVector(v3(seed3[0], seed3[1], seed3[2]));
+  out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+
 // The primary ray of AA sample `sample` of pixel (px,py) (stratified cell + Hash22 jitter, compute:296-340); sample = -1: centre ray.
 void orc_sample_ray(const orc_scene* s, const rtb_render_params* p, int32_t px, int32_t py, int32_t sample, float* o3, float* d3) {
   Frame f = resolve_frame(s->s, *p);

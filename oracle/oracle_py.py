@@ -66,6 +66,7 @@ def lib():
                                  C.POINTER(Counters)]
         L.orc_primary_ray.argtypes = [VP, C.POINTER(_abi.RenderParams), C.c_int32, C.c_int32, VP, VP]
         L.orc_brute_closest.argtypes = [VP, VP, VP, VP, VP, C.c_int32]
+        L.orc_random_unit_vector.argtypes = [VP, VP]
         L.orc_sample_ray.argtypes = [VP, C.POINTER(_abi.RenderParams), C.c_int32, C.c_int32, C.c_int32, VP, VP]
         L.orc_gif_color_table.argtypes = [VP]
         L.orc_gif_convert_to_indexed.argtypes = [VP, C.c_int32, C.c_int32, VP]
@@ -192,6 +193,13 @@ class OracleScene:
         ids = np.zeros(cap, np.int32)
         n = lib().orc_brute_closest(self.h, o.ctypes.data, d.ctypes.data, C.byref(t), ids.ctypes.data, cap)
         return t.value, ids[:min(n, cap)].copy(), n
+
+
+def random_unit_vector(seed) -> np.ndarray:
+    s = np.ascontiguousarray(seed, np.float32)
+    out = np.zeros(3, np.float32)
+    lib().orc_random_unit_vector(s.ctypes.data, out.ctypes.data)
+    return out
 
 
 # ---- GIF writer restatement (oracle/gif_oracle.cpp: GifGenerator.cs) ------------------------------------------------------

@@ -364,3 +364,26 @@ def test_aa_sample_rays_bit_exact_against_fp32_numpy(pkg, oracle, n_samples):
             o2, d2 = _sample_ray_f32(u25, w, h, n_samples, px, py, i)
             assert o.tobytes() == o2.tobytes(), (px, py, i, o, o2)
             assert d.tobytes() == d2.tobytes(), (px, py, i, d, d2)
+
+
+def test_random_unit_vector_hash_bits_and_sincos_accuracy(oracle):
+    """RandomUnitVector (compute:116-131), the source of the soft-shadow / glossy / motion-blur jitter.  z = 2 h.z - 1 must equal a
+    numpy FP32 restatement of Hash33 bit for bit; x, y use this build's fixed FP32 polynomial for cos / sin (shared by oracle and
+    kernels so that both agree exactly) and must stay within 5e-7 of r cos(a), r sin(a) evaluated in float64."""
+    rng = np.random.RandomState(3)
+    worst = 0.0
+    for _ in range(300):
+        seed = np.array([rng.randint(0, 4000) + rng.randint(0, 16) * 9.0, rng.randint(0, 3000) + rng.randint(0, 16) * 4.0, rng.randint(0, 40)], np.float32)
+        got = oracle.random_unit_vector(seed)
+        p = [_frac32(_f(seed[0]) * _f(.1031)), _frac32(_f(seed[1]) * _f(.1030)), _frac32(_f(seed[2]) * _f(.0973))]
+        k = _f(33.33)
+        d = _f(_f(_f(p[0] * _f(p[1] + k)) + _f(p[1] * _f(p[0] + k))) + _f(p[2] * _f(p[2] + k)))  # dot(p, p.yxz + 33.33)
+        p = [_f(p[0] + d), _f(p[1] + d), _f(p[2] + d)]
+        hx = _frac32(_f(_f(p[0] + p[1]) * p[2]))  # frac((p.xxy + p.yxx) * p.zyx)
+        hz = _frac32(_f(_f(p[1] + p[0]) * p[0]))
+        z = _f(_f(hz * _f(2.0)) - _f(1.0))
+        assert got[2].tobytes() == z.tobytes()
+        a = _f(hx * _f(6.2831853))
+        r = np.sqrt(_f(_f(1.0) - _f(z * z)), dtype=np.float32)
+        worst = max(worst, abs(float(got[0]) - float(r) * np.cos(float(a))), abs(float(got[1]) - float(r) * np.sin(float(a))))
+    assert worst <= 5e-7, worst
