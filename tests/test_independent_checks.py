@@ -195,9 +195,82 @@ def _closest64(o, d, v0, e1, e2):
     return best, np.where(np.isfinite(best), idx, -1), u[r, idx], v[r, idx]
 
 
-def _render64(tri18, mat_idx, materials, u25, w, h, max_depth):
+def _analytic64(kind, M, o, d):
+    """SphereInstance.Hit / BoxInstance.Hit (HittableObjects.cs:45-77, 149-174) in float64: ray to object space with the direction
+    re-normalised, unit sphere (quadratic, :82-107) or unit cube (slabs with face tracking, :180-223), world t = |pWS - origin|,
+    normal = normalize(worldToObject^T nOS).  Returns (tWS or inf, pWS, nWS)."""
+    W = np.linalg.inv(M)
+    oo = o @ W[:3, :3].T + W[:3, 3]
+    dd = _normalize64(d @ W[:3, :3].T)
+    n = len(o)
+    if kind == 1:
+        a = (dd * dd).sum(-1)
+        b = 2.0 * (oo * dd).sum(-1)
+        c = (oo * oo).sum(-1) - 1.0
+        disc = b * b - 4.0 * a * c
+        ok = disc >= 0
+        sq = np.sqrt(np.where(ok, disc, 0.0))
+        t0, t1 = (-b - sq) / (2.0 * a), (-b + sq) / (2.0 * a)
+        tos = np.where(t0 > 1e-3, t0, t1)
+        ok &= tos > 1e-3
+        pos_os = oo + tos[:, None] * dd
+        n_os = _normalize64(np.where(ok[:, None], pos_os, 1.0))
+    else:
+        tmin, tmax = np.full(n, -1e20), np.full(n, 1e20)
+        nmin, nmax = np.zeros((n, 3)), np.zeros((n, 3))
+        ok = np.ones(n, bool)
+        for ax in range(3):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                inv = np.where(np.abs(dd[:, ax]) > 1e-8, 1.0 / dd[:, ax], np.inf)
+                t1, t2 = (-0.5 - oo[:, ax]) * inv, (0.5 - oo[:, ax]) * inv
+            e1_, e2_ = np.zeros(3), np.zeros(3)
+            e1_[ax], e2_[ax] = -1.0, 1.0
+            swap = t1 > t2
+            ta, tb = np.where(swap, t2, t1), np.where(swap, t1, t2)
+            na = np.where(swap[:, None], e2_, e1_)
+            nb = np.where(swap[:, None], e1_, e2_)
+            up = ta > tmin
+            tmin, nmin = np.where(up, ta, tmin), np.where(up[:, None], na, nmin)
+            dn = tb < tmax
+            tmax, nmax = np.where(dn, tb, tmax), np.where(dn[:, None], nb, nmax)
+            ok &= ~(tmin > tmax) & ~(tmax < 1e-3)
+        tos = np.where(tmin >= 1e-3, tmin, tmax)
+        ok &= tos >= 1e-3
+        n_os = np.where((tos == tmin)[:, None], nmin, nmax)
+        pos_os = oo + tos[:, None] * dd
+    pos_ws = pos_os @ M[:3, :3].T + M[:3, 3]
+    tws = np.sqrt(((pos_ws - o) ** 2).sum(-1))
+    ok &= tws > 1e-4
+    n_ws = _normalize64(np.where(ok[:, None], n_os @ W[:3, :3], 1.0))  # W^T n
+    return np.where(ok, tws, np.inf), pos_ws, n_ws
+
+
+def _scene64(o, d, v0, e1, e2, n0, n1, n2, mat_idx, prims):
+    """Closest hit over triangles, then analytic primitives in emission order (strict "<": the first of equal t wins).
+    Returns (t or inf, position, shading normal, material index)."""
+    n = len(o)
+    if len(v0):
+        t, idx, bu, bv = _closest64(o, d, v0, e1, e2)
+        safe = np.maximum(idx, 0)
+        pos = o + np.where(np.isfinite(t), t, 0.0)[:, None] * d
+        nrm = _normalize64(np.where((idx >= 0)[:, None], (1 - bu - bv)[:, None] * n0[safe] + bu[:, None] * n1[safe] + bv[:, None] * n2[safe], 1.0))
+        mi = mat_idx[safe].copy()
+    else:
+        t, pos, nrm, mi = np.full(n, np.inf), np.zeros((n, 3)), np.ones((n, 3)), np.zeros(n, np.int64)
+    for kind, M, material in prims:
+        ta, pa, na = _analytic64(kind, M, o, d)
+        better = ta < t
+        t = np.where(better, ta, t)
+        pos, nrm = np.where(better[:, None], pa, pos), np.where(better[:, None], na, nrm)
+        mi = np.where(better, material, mi)
+    return t, pos, nrm, mi
+
+
+def _render64(tri18, mat_idx, materials, u25, w, h, max_depth, prims=()):
     """The per-pixel loop of CSMain (BVHRayTracing.compute:283-340 ray generation, :356-478 depth loop) in float64 numpy, written
-    from the shader text: one sample per pixel, perspective camera, all lighting toggles on, no distribution effects."""
+    from the shader text: one sample per pixel, perspective camera, all lighting toggles on, no distribution effects.
+    `prims`: analytic spheres / boxes (kind, objectToWorld 4x4, material) tested after the triangles, as the oracle's analytic mode
+    does with the semantics of HittableObjects.cs."""
     M = u25[:16].reshape(4, 4).astype(np.float64)
     cam_d, tan_half = float(u25[16]), float(u25[17])
     light, bg = u25[19:22].astype(np.float64), u25[22:25].astype(np.float64)
@@ -221,16 +294,14 @@ def _render64(tri18, mat_idx, materials, u25, w, h, max_depth):
     for _ in range(max_depth):
         if len(alive) == 0:
             break
-        t, idx, bu, bv = _closest64(o, d, v0, e1, e2)
-        miss = idx < 0
+        t, pos, nrm, mi = _scene64(o, d, v0, e1, e2, n0, n1, n2, mat_idx, prims)
+        miss = ~np.isfinite(t)
         color[alive[miss]] += att[miss] * bg
         keep = ~miss
-        alive, o, d, att, t, idx, bu, bv = alive[keep], o[keep], d[keep], att[keep], t[keep], idx[keep], bu[keep], bv[keep]
+        alive, o, d, att, t, pos, nrm, mi = alive[keep], o[keep], d[keep], att[keep], t[keep], pos[keep], nrm[keep], mi[keep]
         if len(alive) == 0:
             break
-        pos = o + t[:, None] * d
-        nrm = _normalize64((1 - bu - bv)[:, None] * n0[idx] + bu[:, None] * n1[idx] + bv[:, None] * n2[idx])
-        m = mats[mat_idx[idx]]
+        m = mats[mi]
         col, ka, kd, ks, kr, ior = m[:, :3], m[:, 3], m[:, 4], m[:, 5], m[:, 6], m[:, 7]
         local = col * ka[:, None]
         ldir = _normalize64(light - pos)
@@ -239,8 +310,8 @@ def _render64(tri18, mat_idx, materials, u25, w, h, max_depth):
         need = ndl > 0
         lit = np.zeros(len(alive), bool)
         if need.any():
-            st, sidx, _, _ = _closest64((pos + nrm * 1e-2)[need], ldir[need], v0, e1, e2)
-            lit[need] = (sidx < 0) | (st > dist[need])
+            st, _, _, _ = _scene64((pos + nrm * 1e-2)[need], ldir[need], v0, e1, e2, n0, n1, n2, mat_idx, prims)
+            lit[need] = ~np.isfinite(st) | (st > dist[need])
         half = _normalize64(ldir + _normalize64(-d))
         spec = np.maximum((nrm * half).sum(-1), 0.0) ** 32
         local = local + np.where(lit[:, None], col * (kd * ndl)[:, None] + np.where(ks > 0, ks * spec, 0.0)[:, None], 0.0)
@@ -387,3 +458,31 @@ def test_random_unit_vector_hash_bits_and_sincos_accuracy(oracle):
         r = np.sqrt(_f(_f(1.0) - _f(z * z)), dtype=np.float32)
         worst = max(worst, abs(float(got[0]) - float(r) * np.cos(float(a))), abs(float(got[1]) - float(r) * np.sin(float(a))))
     assert worst <= 5e-7, worst
+
+
+@pytest.mark.parametrize("w,h,depth", [(64, 48, 3), (96, 72, 6)])
+@pytest.mark.parametrize("name", synth.SAMPLE_SCENES)
+def test_analytic_mode_frame_against_float64_brute_force(pkg, oracle, name, w, h, depth):
+    """The oracle's ANALYTIC primitive mode (spheres / boxes with the semantics of the reference's dead SphereInstance / BoxInstance,
+    SURVEY A13) against the same float64 renderer with analytic primitives built from the scene description.  The product's analytic
+    kernels are checked against this oracle mode on the GPU; this pins the oracle mode itself."""
+    obj = synth.sample_scene(name)
+    osc, holder = oracle_scene(oracle, obj)
+    osc.set_primitive_mode(1)
+    p = params(w, h, depth)
+    ref = osc.render(p)["rgba8"][..., :3]
+    u25 = np.zeros(25, np.float32)
+    wh = (C.c_int32 * 2)()
+    assert abi.load().rtb_resolve_frame(holder.ptr(), C.byref(p), u25.ctypes.data_as(C.POINTER(C.c_float)), wh) == abi.RTB_OK
+    tri18, mat_idx, _ = osc.triangles()  # analytic mode: the mesh triangles only
+
+    def matrix(ti):
+        t = obj.Transformations[ti] if 0 <= ti < len(obj.Transformations) else None  # out of range -> identity, SceneGeometryConverter.cs:85
+        return _float64_matrix([(e.Type, *e.XYZ, e.AngleDeg) for e in t.Elements]) if t else np.eye(4)
+
+    prims = [(2, matrix(b.transformationIndex), b.materialIndex) for b in obj.Boxes] + [(1, matrix(sp.transformationIndex), sp.materialIndex) for sp in obj.Spheres]
+    assert len(prims) >= 2 and len(tri18) == sum(len(m.materials) for m in obj.TriangleMeshes)
+    got = _render64(tri18, mat_idx, obj.Materials, u25, w, h, depth, prims)
+    diff = np.abs(got.astype(np.int32) - ref.astype(np.int32)).max(-1)
+    within = float((diff <= 1).mean())
+    assert within >= 0.99, f"{name}: only {within * 100:.2f}% of pixels within 1/255 (worst {int(diff.max())})"
