@@ -486,3 +486,78 @@ def test_analytic_mode_frame_against_float64_brute_force(pkg, oracle, name, w, h
     diff = np.abs(got.astype(np.int32) - ref.astype(np.int32)).max(-1)
     within = float((diff <= 1).mean())
     assert within >= 0.99, f"{name}: only {within * 100:.2f}% of pixels within 1/255 (worst {int(diff.max())})"
+
+
+# ---- tessellation: AddCube / AddSphere / meshes in float64, written from SceneGeometryConverter.cs -----------------------------------
+def _tessellate64(obj):
+    """ExtractTriangles (SceneGeometryConverter.cs:18-51): meshes, then boxes (AddCube :120-155), then spheres (AddSphere :161-230,
+    AddSmoothTri :245-264) in float64.  Returns [n, 18] (v0 v1 v2 n0 n1 n2) and materials."""
+    def matrix(ti):
+        ok = 0 <= ti < len(obj.Transformations)
+        return _float64_matrix([(e.Type, *e.XYZ, e.AngleDeg) for e in obj.Transformations[ti].Elements]) if ok else np.eye(4)
+
+    def point(M, v):
+        return M[:3, :3] @ v + M[:3, 3]
+
+    rows, mats = [], []
+
+    def flat(a, b, c, m):
+        n = np.cross(b - a, c - a)
+        n = n / np.linalg.norm(n)
+        rows.append(np.concatenate([a, b, c, n, n, n])); mats.append(m)
+
+    for mesh in obj.TriangleMeshes:
+        M = matrix(mesh.transformationIndex)
+        for k in range(len(mesh.materials)):
+            a, b, c = (point(M, mesh.vertices[k, j].astype(np.float64)) for j in range(3))
+            flat(a, b, c, int(mesh.materials[k]))
+    corners = np.array([[-.5, -.5, -.5], [.5, -.5, -.5], [.5, .5, -.5], [-.5, .5, -.5], [-.5, -.5, .5], [.5, -.5, .5], [.5, .5, .5], [-.5, .5, .5]])
+    faces = [(0, 2, 1), (0, 3, 2), (5, 7, 6), (5, 4, 7), (3, 6, 2), (3, 7, 6), (4, 1, 5), (4, 0, 1), (4, 3, 7), (4, 0, 3), (1, 6, 2), (1, 5, 6)]
+    for box in obj.Boxes:
+        M = matrix(box.transformationIndex)
+        v = [point(M, c) for c in corners]
+        for i, j, k in faces:
+            flat(v[i], v[j], v[k], box.materialIndex)
+    nb_long, nb_lat = 24, 16
+    sv = np.zeros(((nb_long + 1) * nb_lat + 2, 3))
+    sv[0] = (0, 1, 0)
+    for lat in range(nb_lat):
+        a1 = np.pi * (lat + 1) / (nb_lat + 1)
+        for lon in range(nb_long + 1):
+            a2 = 2 * np.pi * (0 if lon == nb_long else lon) / nb_long
+            sv[lon + lat * (nb_long + 1) + 1] = (np.sin(a1) * np.cos(a2), np.cos(a1), np.sin(a1) * np.sin(a2))
+    sv[-1] = (0, -1, 0)
+    for sph in obj.Spheres:
+        M = matrix(sph.transformationIndex)
+        NM = np.linalg.inv(M).T
+
+        def smooth(a, b, c):
+            ns = [NM[:3, :3] @ (p / np.linalg.norm(p)) for p in (a, b, c)]
+            ns = [n / np.linalg.norm(n) for n in ns]
+            rows.append(np.concatenate([point(M, a), point(M, b), point(M, c), *ns])); mats.append(sph.materialIndex)
+
+        for lon in range(nb_long):
+            smooth(sv[0], sv[lon + 2], sv[lon + 1])
+        for lat in range(nb_lat - 1):
+            for lon in range(nb_long):
+                cur = lon + lat * (nb_long + 1) + 1
+                nxt, below = cur + 1, cur + nb_long + 1
+                smooth(sv[cur], sv[below], sv[nxt])
+                smooth(sv[nxt], sv[below], sv[below + 1])
+        last = len(sv) - 1
+        for lon in range(nb_long):
+            smooth(sv[last], sv[last - (nb_long + 1) + lon], sv[last - (nb_long + 1) + lon + 1])
+    return np.array(rows), np.array(mats, np.int32)
+
+
+@pytest.mark.parametrize("name", synth.SAMPLE_SCENES)
+def test_tessellation_against_float64(pkg, oracle, name):
+    """Emission order, winding, vertex positions and (flat / smooth, inverse-transpose) normals of every triangle the oracle
+    flattens, against the float64 restatement above: same count and materials, positions within 2e-5, normals within 2e-5."""
+    obj = synth.sample_scene(name)
+    osc, _ = oracle_scene(oracle, obj)
+    vn, mat, _ = osc.triangles()
+    want, wmat = _tessellate64(obj)
+    assert vn.shape == want.shape and (mat == wmat).all()
+    assert np.abs(vn[:, :9] - want[:, :9]).max() <= 2e-5
+    assert np.abs(vn[:, 9:] - want[:, 9:]).max() <= 2e-5
