@@ -103,6 +103,8 @@ struct rtb_context {
   int n_lanes = 4;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues
   uint64_t frame_id = 0;
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
+  int packet_closest = 0;     // RTB_PACKET_CLOSEST: closest-hit rays of depth <= this go through the packet kernels (-1: none, k_raygen + per-lane)
+  int packet_shadow = 0;      // RTB_PACKET_SHADOW: shadow rays emitted at depth <= this go through k_packet (-1: none)
   int32_t tail_max = 65536;   // queues smaller than this finish in k_tail (RTB_TAIL_MAX; 0 = pure wavefront); sweep: profiles/r1e_sweep_tail_max.log
   std::vector<void*> ipc_opened;
   static constexpr int kTickets = 16;  // frames in flight through rtb_render_begin
@@ -417,11 +419,30 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
         CK(ctx, cudaMemsetAsync(L.q.counters, 0, (size_t)L.q.depth_cap * RTB_CNT_BLOCKS * sizeof(int32_t), stream));
         // raygen fills the depth-0 queue; depth d: traverse (closest-hit rays of depth d + shadow rays emitted at depth d-1),
         // then shade (or, for short queues, k_tail).  One more traverse at the end serves the last depth's shadow rays.
-        timed(1, [&] { launch_raygen(bvh, f, sv, qv, c, shade_grid, stream); });
+        // Depth 0 is coherent (8x4-pixel tiles), and so are the shadow rays those pixels emit: they go through the packet kernels
+        // (k_primary = raygen + traversal fused; k_packet); deeper, incoherent rays through the per-lane persistent kernel.
+        const int pk_closest = ctx->packet_closest, pk_shadow = ctx->packet_shadow;
+        const int packet_grid = d.sm_count * 8;
+        if (pk_closest >= 0) {
+          const int tb = stream_block_threads();
+          const int primary_grid = (int)std::min<int64_t>(((int64_t)c.n_slots + tb - 1) / tb, (int64_t)1 << 20);
+          timed(0, [&] { launch_primary(bvh, f, sv, qv, c, std::max(primary_grid, 1), stream); });
+        } else {
+          timed(1, [&] { launch_raygen(bvh, f, sv, qv, c, shade_grid, stream); });
+        }
         for (int depth = 0; depth <= f.max_depth; depth++) {
           if (depth > 0 && ctx->cancel && *ctx->cancel) { device_sync(d); return fail(ctx, RTB_E_CANCELLED, "cancelled"); }
-          if (depth < f.max_depth || f.en_diffuse == 1)
-            timed(0, [&] { launch_traverse(bvh, sv, qv, depth, smem_bytes ? d.sm_count : d.grid_traverse[bvh], smem_bytes, stream); });
+          int mode = 0;
+          if (depth < f.max_depth && !(depth == 0 && pk_closest >= 0)) {
+            if (depth > 0 && depth <= pk_closest) timed(0, [&] { launch_packet(bvh, sv, qv, depth, 0, packet_grid, stream); });
+            else mode |= 1;
+          }
+          if (depth > 0 && f.en_diffuse == 1) {
+            if (depth - 1 <= pk_shadow) timed(0, [&] { launch_packet(bvh, sv, qv, depth - 1, 1, packet_grid, stream); });
+            else mode |= 2;
+          }
+          if (mode != 0)
+            timed(0, [&] { launch_traverse(bvh, sv, qv, depth, mode, smem_bytes ? d.sm_count : d.grid_traverse[bvh], smem_bytes, stream); });
           if (depth < f.max_depth) {
             timed(1, [&] { launch_shade(f, sv, qv, c, depth, ctx->tail_max, shade_grid, stream); });
             if (ctx->tail_max > 0) timed(0, [&] { launch_tail(bvh, f, sv, qv, c, depth, ctx->tail_max, d.sm_count * 4, stream); });
@@ -587,6 +608,8 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
   if (const char* env = std::getenv("RTB_LANES")) ctx->n_lanes = std::min((int)DeviceState::kMaxLanes, std::max(1, std::atoi(env)));
   if (const char* env = std::getenv("RTB_SMEM")) ctx->smem_mode = std::atoi(env);
   if (const char* env = std::getenv("RTB_SPLIT_BLOCKING")) ctx->split_blocking = std::atoi(env);
+  if (const char* env = std::getenv("RTB_PACKET_CLOSEST")) ctx->packet_closest = std::atoi(env);
+  if (const char* env = std::getenv("RTB_PACKET_SHADOW")) ctx->packet_shadow = std::atoi(env);
   if (const char* env = std::getenv("RTB_TAIL_MAX")) ctx->tail_max = (int32_t)std::max(0LL, std::atoll(env));
   ctx->devs.resize(ids.size());
   for (size_t k = 0; k < ids.size(); k++) {

@@ -35,7 +35,14 @@ void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const Queu
 // `grid` = number of persistent blocks (sm_count * traverse_blocks_per_sm).
 // smem_bytes > 0 selects the shared-memory staged variant (grid = sm_count blocks of 1024 threads); it must have been
 // enabled for that size with traverse_enable_smem and equal traverse_smem_bytes(bvh, s).
-void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int grid, size_t smem_bytes, cudaStream_t st);
+// mode: bit 0 = the closest-hit rays of `depth`, bit 1 = the shadow rays emitted at depth - 1.
+void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int mode, int grid, size_t smem_bytes, cudaStream_t st);
+// Packet kernels (one warp walks the BVH once for 32 neighbouring rays).  launch_primary: ray generation + depth-0 traversal
+// fused, fills the depth-0 ray queue with the hits only (grid blocks of stream_block_threads() threads, one slot per thread and
+// iteration).  launch_packet: kind 0 = closest-hit rays of `depth`, kind 1 = shadow rays emitted at `depth`.
+void launch_primary(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st);
+void launch_packet(int bvh, const SceneView& s, const QueueView& q, int depth, int kind, int grid, cudaStream_t st);
+int stream_block_threads();
 size_t traverse_smem_bytes(int bvh, const SceneView& s);
 cudaError_t traverse_enable_smem(int bvh, size_t bytes);
 // k_shade handles depth `depth` when its queue holds >= tail_max rays; otherwise k_tail runs the remaining paths to their

@@ -240,8 +240,9 @@ __device__ __forceinline__ void stage_scene(const SceneView& s, int node_f4, flo
   tris = sm + n_node;
 }
 
-// Triangle test shared by both flavours.  Returns true when a shadow ray found its occluder.
-template <bool SMEM, bool ANALYTIC>
+// Triangle test shared by both flavours.  Returns true when a shadow ray found its occluder.  TIE: see closer_hit (trace.cuh);
+// a shadow lane keeps tri = -1 until it is occluded, so for it the rule reduces to "t < bound".
+template <bool SMEM, bool ANALYTIC, bool TIE>
 __device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, const float4* tri_isect, int32_t tri) {
   float4 a, b;
 #if RTB_TRI_F4 == 4
@@ -257,7 +258,7 @@ __device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, 
     if (!intersect_analytic(&s.prims[6 * __float_as_int(a.x)], __float_as_int(c.w), L.o, L.d, t, u, face)) return false;
     v = (float)face;
   } else if (!moller_trumbore(r, mk3(a), mk3(b), mk3(c), t, u, v)) return false;
-  if (!(t < L.t)) return false;
+  if (!closer_hit<TIE>(t, tri, L.t, L.tri)) return false;
   if (L.shadow) { L.tri = 0; return true; }
   L.t = t; L.u = u; L.v = v; L.tri = tri;
   return false;
@@ -267,14 +268,16 @@ __device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, 
 // k_traverse, LBVH flavour: ordered traversal over 64-byte two-box nodes (see lbvh.cu for the layout).
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool SMEM, bool ANALYTIC>
-__global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB_TRAVERSE_MIN_BLOCKS) k_traverse_lbvh(const SceneView s, const QueueView q, const int depth) {
+__global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB_TRAVERSE_MIN_BLOCKS) k_traverse_lbvh(const SceneView s, const QueueView q, const int depth, const int mode) {
   extern __shared__ float4 sm_scene[];
   const float4* nodes = s.nodes;
   const float4* tri_isect = s.tri_isect;
   if (SMEM) stage_scene(s, lbvh_node_f4, sm_scene, nodes, tri_isect);
   const int lane = threadIdx.x & 31;
-  const int32_t n_closest = RTB_CNT_RAY(q, depth);
-  const int32_t n_shadow = depth == 0 ? 0 : RTB_CNT_SHADOW(q, depth - 1);
+  // mode: bit 0 = serve the closest-hit rays of this depth, bit 1 = the shadow rays emitted at depth - 1 (the packet
+  // kernels below may have taken either)
+  const int32_t n_closest = (mode & 1) ? RTB_CNT_RAY(q, depth) : 0;
+  const int32_t n_shadow = (depth == 0 || !(mode & 2)) ? 0 : RTB_CNT_SHADOW(q, depth - 1);
   const int32_t total = n_closest + n_shadow;
   const int in_q = depth & 1;
 #if RTB_MIN_BATCHES > 0
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
         while (sp > 0) {
           sp--;
           const float2 e = stack[sp];
-          if (!(e.x >= L.t)) { cur = __float_as_int(e.y); break; }
+          if (!(e.x > L.t)) { cur = __float_as_int(e.y); break; }
         }
       }
     }
@@ -359,13 +362,13 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
       const int32_t first = code >> 3, count = (code & 7) + 1;
       bool occluded = false;
       n_tris += count;
-      for (int32_t i = 0; i < count && !occluded; i++) occluded = lane_test_triangle<SMEM, ANALYTIC>(L, s, tri_isect, first + i);
+      for (int32_t i = 0; i < count && !occluded; i++) occluded = lane_test_triangle<SMEM, ANALYTIC, true>(L, s, tri_isect, first + i);
       cur = RTB_REF_DONE;
       if (!occluded)
         while (sp > 0) {
           sp--;
           const float2 e = stack[sp];
-          if (!(e.x >= L.t)) { cur = __float_as_int(e.y); break; }
+          if (!(e.x > L.t)) { cur = __float_as_int(e.y); break; }
         }
     }
     if (cur == RTB_REF_DONE && L.item >= 0) { sp = 0; L.done = true; }
@@ -392,14 +395,16 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
 // culled when its own slab entry >= best t; leaves of any size.  Same results as the reference for every ray.
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool SMEM, bool ANALYTIC>
-__global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB_TRAVERSE_MIN_BLOCKS) k_traverse_ref(const SceneView s, const QueueView q, const int depth) {
+__global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB_TRAVERSE_MIN_BLOCKS) k_traverse_ref(const SceneView s, const QueueView q, const int depth, const int mode) {
   extern __shared__ float4 sm_scene[];
   const float4* nodes = s.nodes;
   const float4* tri_isect = s.tri_isect;
   if (SMEM) stage_scene(s, 2, sm_scene, nodes, tri_isect);
   const int lane = threadIdx.x & 31;
-  const int32_t n_closest = RTB_CNT_RAY(q, depth);
-  const int32_t n_shadow = depth == 0 ? 0 : RTB_CNT_SHADOW(q, depth - 1);
+  // mode: bit 0 = serve the closest-hit rays of this depth, bit 1 = the shadow rays emitted at depth - 1 (the packet
+  // kernels below may have taken either)
+  const int32_t n_closest = (mode & 1) ? RTB_CNT_RAY(q, depth) : 0;
+  const int32_t n_shadow = (depth == 0 || !(mode & 2)) ? 0 : RTB_CNT_SHADOW(q, depth - 1);
   const int32_t total = n_closest + n_shadow;
   const int in_q = depth & 1;
 #if RTB_MIN_BATCHES > 0
@@ -454,7 +459,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
     if (leaf_count > 0) {
       bool occluded = false;
       n_tris += leaf_count;
-      for (int32_t i = 0; i < leaf_count && !occluded; i++) occluded = lane_test_triangle<SMEM, ANALYTIC>(L, s, tri_isect, leaf_first + i);
+      for (int32_t i = 0; i < leaf_count && !occluded; i++) occluded = lane_test_triangle<SMEM, ANALYTIC, false>(L, s, tri_isect, leaf_first + i);
       leaf_count = 0;
       if (occluded) sp = 0;
     }
@@ -471,6 +476,244 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
     if (n_nodes) atomicAdd(&q.totals[5], (unsigned long long)n_nodes);
     if (n_tris) atomicAdd(&q.totals[6], (unsigned long long)n_tris);
   }
+}
+
+
+// =====================================================================================================================
+// Packet traversal: a warp walks the BVH ONCE for its 32 rays.  Rays that are neighbours on the screen (primary rays of an
+// 8x4 tile, the shadow rays those pixels emit towards the one light) visit nearly the same nodes, so the per-lane kernels
+// above fetch every node record 32 times from 32 divergent addresses (one L1 wavefront each) and idle through each other's
+// steps (13 of 32 lanes live, profiles/r1e_ncu_full_k_traverse_c4.csv).  Here the node / triangle address is warp-uniform
+// (one broadcast wavefront per load), the stack is one per warp in shared memory, and every lane tests its own ray against
+// the shared record with the same box / triangle arithmetic as the per-lane kernels, so per-ray results are the same:
+//   reference flavour: TraverseBVH's order (compute:235-264) does not depend on the ray, so the packet follows it exactly and
+//     each lane sees its own subsequence of it (a lane skips a node when ITS slab test culls it, :245-246) — same tie winners;
+//   LBVH flavour: near child first by majority vote; the closest hit is order-independent by closer_hit<true>.
+// =====================================================================================================================
+#define RTB_PSTACK 96
+struct PacketStack {  // one per warp, shared memory
+  int32_t ref[RTB_PSTACK];
+  unsigned mask[RTB_PSTACK];   // LBVH: lanes whose ray entered the deferred child's box
+  float nearest[RTB_PSTACK];   // LBVH: smallest entry distance among them
+};
+
+// L: o, d, t = bound (closest: Infinity; shadow: nextafter(distToLight)), tri = -1, shadow set.  `valid` = the lane holds a ray.
+// On return L.t/u/v/tri hold the closest hit, or for a shadow ray L.tri = 0 iff an occluder was found.
+template <bool ANALYTIC>
+__device__ __forceinline__ void packet_traverse_lbvh(const SceneView& s, Lane& L, const bool valid, PacketStack& st, unsigned& overflow, unsigned& n_nodes,
+                                                     unsigned& n_tris, unsigned& w_nodes, unsigned& w_tris) {
+  const int lane = threadIdx.x & 31;
+  if (s.n_tris == 0) return;
+  const f3 inv = safe_inverse(L.d);
+  const f3 ood = L.o * inv;
+  const float t_saved = L.t;
+  if (!valid) L.t = -1.0f;  // every box test fails (exit <= bound < 0 <= entry)
+  int sp = 0;
+  int32_t cur = s.root;
+  bool act = valid;
+  for (;;) {
+    if (cur >= 0) {
+      float4 n0, n1, n2, n3;  // warp-uniform address: broadcast
+      ld8<false>(&s.nodes[4 * (size_t)cur], n0, n1);
+      ld8<false>(&s.nodes[4 * (size_t)cur + 2], n2, n3);
+      float dl, dr;
+      const bool hl = act && slab_hit_fma(inv, ood, mk3(n0), mk3(n1), L.t, dl);
+      const bool hr = act && slab_hit_fma(inv, ood, mk3(n2), mk3(n3), L.t, dr);
+      const unsigned ml = __ballot_sync(kFull, hl), mr = __ballot_sync(kFull, hr);
+      n_nodes += act ? 1u : 0u;
+      w_nodes += lane == 0 ? 1u : 0u;
+      const int32_t lref = __float_as_int(n0.w), rref = __float_as_int(n1.w);
+      if (ml != 0 && mr != 0) {
+        const int votes_l = __popc(__ballot_sync(kFull, hl && (!hr || !(dr < dl))));
+        const int votes_r = __popc(__ballot_sync(kFull, hr && (!hl || dr < dl)));
+        const bool left_first = votes_l >= votes_r;
+        const float d_far = left_first ? (hr ? dr : INFINITY) : (hl ? dl : INFINITY);
+        const float far_min = __uint_as_float(__reduce_min_sync(kFull, __float_as_uint(d_far)));  // entries are >= 0: they order like their bits
+        if (sp < RTB_PSTACK) {
+          if (lane == 0) { st.ref[sp] = left_first ? rref : lref; st.mask[sp] = left_first ? mr : ml; st.nearest[sp] = far_min; }
+          sp++;
+          __syncwarp();
+        } else if (lane == 0) overflow++;
+        cur = left_first ? lref : rref;
+        act = left_first ? hl : hr;
+        continue;
+      }
+      if (ml != 0) { cur = lref; act = hl; continue; }
+      if (mr != 0) { cur = rref; act = hr; continue; }
+    } else {
+      const int32_t code = ~cur;
+      const int32_t first = code >> 3, count = (code & 7) + 1;
+      w_tris += lane == 0 ? (unsigned)count : 0u;
+      n_tris += act ? (unsigned)count : 0u;
+      for (int32_t i = 0; i < count; i++)
+        if (act && lane_test_triangle<false, ANALYTIC, true>(L, s, s.tri_isect, first + i)) { L.t = -1.0f; act = false; }  // shadow ray occluded: drops out
+    }
+    // next deferred child some lane still needs
+    cur = RTB_REF_DONE;
+    while (sp > 0) {
+      sp--;
+      const bool want = ((st.mask[sp] >> lane) & 1u) != 0u && !(st.nearest[sp] > L.t);
+      if (__any_sync(kFull, want)) { cur = st.ref[sp]; act = want; break; }
+    }
+    if (cur == RTB_REF_DONE) break;
+  }
+  if (!valid) L.t = t_saved;
+}
+
+template <bool ANALYTIC>
+__device__ __forceinline__ void packet_traverse_ref(const SceneView& s, Lane& L, const bool valid, PacketStack& st, unsigned& overflow, unsigned& n_nodes,
+                                                    unsigned& n_tris, unsigned& w_nodes, unsigned& w_tris) {
+  const int lane = threadIdx.x & 31;
+  if (s.n_nodes == 0) return;
+  Ray r; r.o = L.o; r.d = L.d; r.inv = mk3(1.0f / L.d.x, 1.0f / L.d.y, 1.0f / L.d.z);  // CreateRay :142
+  int sp = 0;
+  if (lane == 0) st.ref[0] = 0;
+  sp = 1;
+  __syncwarp();
+  bool live = valid;  // a shadow ray that found its occluder stops (the per-lane kernel empties its stack)
+  while (sp > 0) {
+    const int32_t ni = st.ref[--sp];
+    float4 lo, hi;
+    ld8<false>(&s.nodes[2 * (size_t)ni], lo, hi);
+    const float dst = slab_entry(r, mk3(lo), mk3(hi));
+    const bool want = live && !(dst >= L.t);  // compute:246
+    w_nodes += lane == 0 ? 1u : 0u;
+    if (!__any_sync(kFull, want)) continue;
+    n_nodes += want ? 1u : 0u;
+    const int32_t count = __float_as_int(hi.w), left_or_first = __float_as_int(lo.w);
+    if (count > 0) {
+      w_tris += lane == 0 ? (unsigned)count : 0u;
+      n_tris += want ? (unsigned)count : 0u;
+      for (int32_t i = 0; i < count; i++)
+        if (want && live && lane_test_triangle<false, ANALYTIC, false>(L, s, s.tri_isect, left_or_first + i)) live = false;
+    } else if (sp + 2 <= RTB_PSTACK) {
+      __syncwarp();  // every lane has read the entry this push may overwrite
+      if (lane == 0) { st.ref[sp] = left_or_first + 1; st.ref[sp + 1] = left_or_first; }
+      sp += 2;
+      __syncwarp();
+    } else if (lane == 0) overflow++;
+  }
+}
+
+template <int BVH, bool ANALYTIC>
+__device__ __forceinline__ void packet_traverse(const SceneView& s, Lane& L, const bool valid, PacketStack& st, unsigned& overflow, unsigned& n_nodes,
+                                                unsigned& n_tris, unsigned& w_nodes, unsigned& w_tris) {
+  if (BVH == RTB_BVH_REFERENCE) packet_traverse_ref<ANALYTIC>(s, L, valid, st, overflow, n_nodes, n_tris, w_nodes, w_tris);
+  else packet_traverse_lbvh<ANALYTIC>(s, L, valid, st, overflow, n_nodes, n_tris, w_nodes, w_tris);
+}
+
+__device__ __forceinline__ void packet_counters(const QueueView& q, unsigned overflow, unsigned n_nodes, unsigned n_tris, unsigned w_nodes, unsigned w_tris) {
+  for (int o = 16; o > 0; o >>= 1) {
+    n_nodes += __shfl_xor_sync(kFull, n_nodes, o);
+    n_tris += __shfl_xor_sync(kFull, n_tris, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (overflow) atomicAdd(&q.totals[4], (unsigned long long)overflow);
+    if (n_nodes) atomicAdd(&q.totals[5], (unsigned long long)n_nodes);
+    if (n_tris) atomicAdd(&q.totals[6], (unsigned long long)n_tris);
+    if (w_nodes) atomicAdd(&q.totals[RTB_TOT_PACKET_NODES], (unsigned long long)w_nodes);
+    if (w_tris) atomicAdd(&q.totals[RTB_TOT_PACKET_TRIS], (unsigned long long)w_tris);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_primary (K3 + K4 fused): primary rays of the chunk (CSMain compute:283-349) traced as packets, one warp per 8x4 pixel
+// tile and sample.  A ray that hits nothing takes the background at once (:364-368: sampleColor = 0 + attenuation * bg with
+// attenuation (1,1,1)); the hits are compacted into the depth-0 ray queue together with their hit records, so k_shade(0)
+// only sees paths it has to shade.  Replaces k_raygen + k_traverse(depth 0); no ray makes a round trip through HBM before
+// its first traversal.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int BVH, bool ANALYTIC>
+__global__ void __launch_bounds__(kStreamBlock) k_primary(const FrameParams f, const SceneView s, const QueueView q, const ChunkView c) {
+  __shared__ PacketStack stacks[kStreamBlock / 32];
+  __shared__ BlockReserve<1> reserve;
+  const int lane = threadIdx.x & 31;
+  const unsigned below = (1u << lane) - 1u;
+  unsigned n_valid = 0, overflow = 0, n_nodes = 0, n_tris = 0, w_nodes = 0, w_tris = 0;
+  int it = 0;
+  for (int32_t base = blockIdx.x * kStreamBlock; base < c.n_slots; base += gridDim.x * kStreamBlock, it++) {  // block-uniform trip count
+    const int32_t slot = base + threadIdx.x;
+    Ray ray;
+    int px, py, sample;
+    const bool valid = primary_ray_of_slot(f, c, slot, ray, px, py, sample);
+    Lane L;
+    L.item = slot; L.shadow = false; L.done = false; L.t = RTB_INFINITY; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
+    L.o = valid ? ray.o : mk3(0.0f, 0.0f, 0.0f);
+    L.d = valid ? ray.d : mk3(0.0f, 0.0f, 1.0f);
+    L.inv = mk3(0.0f, 0.0f, 0.0f);
+    if (__any_sync(kFull, valid)) packet_traverse<BVH, ANALYTIC>(s, L, valid, stacks[threadIdx.x >> 5], overflow, n_nodes, n_tris, w_nodes, w_tris);
+    const bool found = valid && L.tri >= 0;
+    if (valid) {
+      n_valid++;
+      const f3 bg = mk3(1.0f, 1.0f, 1.0f) * mk3(f.bg[0], f.bg[1], f.bg[2]);
+      const f3 first = found ? mk3(0.0f, 0.0f, 0.0f) : mk3(0.0f, 0.0f, 0.0f) + bg;
+      q.accum[slot] = make_float4(first.x, first.y, first.z, 0.0f);
+    }
+    const unsigned m[1] = {__ballot_sync(kFull, found)};
+    int32_t* const counters[1] = {&RTB_CNT_RAY(q, 0)};
+    int32_t first_at[1];
+    block_reserve<1>(reserve, it, m, counters, first_at);
+    if (found) {
+      const int32_t at = first_at[0] + __popc(m[0] & below);
+      __stcs(&q.ray_o[0][at], make_float4(ray.o.x, ray.o.y, ray.o.z, __int_as_float(slot)));
+      __stcs(&q.ray_d[0][at], make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f));
+      __stcs(&q.ray_att[0][at], make_float4(1.0f, 1.0f, 1.0f, 0.0f));
+      __stcs(&q.hits[at], make_float4(L.t, L.u, L.v, __int_as_float(L.tri)));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) n_valid += __shfl_xor_sync(kFull, n_valid, o);
+  if (lane == 0 && n_valid) atomicAdd(&q.totals[0], (unsigned long long)n_valid);
+  packet_counters(q, overflow, n_nodes, n_tris, w_nodes, w_tris);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_packet: 32 consecutive entries of a queue as one packet — the closest-hit rays of `depth` (kind 0: writes their hit
+// records) or the shadow rays emitted at `depth` (kind 1: adds the lit or unlit increment of :418, like lane_finish).
+// Queue order follows screen order (k_primary / k_shade compact in runs of 256), so neighbours in the queue are neighbours
+// on the screen as long as the surfaces they left are; api.cu uses this for the depths given by RTB_PACKET_CLOSEST /
+// RTB_PACKET_SHADOW and the per-lane kernels beyond.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int BVH, bool ANALYTIC>
+__global__ void __launch_bounds__(kStreamBlock) k_packet(const SceneView s, const QueueView q, const int depth, const int kind) {
+  __shared__ PacketStack stacks[kStreamBlock / 32];
+  const int lane = threadIdx.x & 31;
+  const int32_t n = kind == 0 ? RTB_CNT_RAY(q, depth) : RTB_CNT_SHADOW(q, depth);
+  const int in_q = depth & 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) {
+    if (kind == 0) { if (depth > 0) atomicAdd(&q.totals[1], (unsigned long long)n); }
+    else atomicAdd(&q.totals[2], (unsigned long long)n);
+  }
+  unsigned overflow = 0, n_nodes = 0, n_tris = 0, w_nodes = 0, w_tris = 0;
+  const int32_t warps = (int32_t)((gridDim.x * blockDim.x) >> 5);
+  for (int32_t base = ((int32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * 32; base < n; base += warps * 32) {
+    const int32_t idx = base + lane;
+    const bool valid = idx < n;
+    Lane L;
+    L.item = idx; L.shadow = kind != 0; L.done = false; L.t = RTB_INFINITY; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
+    L.o = mk3(0.0f, 0.0f, 0.0f); L.d = mk3(0.0f, 0.0f, 1.0f); L.inv = mk3(0.0f, 0.0f, 0.0f);
+    int32_t slot = 0;
+    if (valid) {
+      if (kind == 0) {
+        const float4 o = __ldcs(&q.ray_o[in_q][idx]), d = __ldcs(&q.ray_d[in_q][idx]);
+        L.o = mk3(o); L.d = mk3(d);
+      } else {
+        const float4 o = __ldcs(&q.sh_o[idx]), d = __ldcs(&q.sh_d[idx]);
+        L.o = mk3(o); L.d = mk3(d);
+        L.t = nextafterf(o.w, INFINITY);  // see lane_load
+        slot = __float_as_int(d.w);
+      }
+    }
+    packet_traverse<BVH, ANALYTIC>(s, L, valid, stacks[threadIdx.x >> 5], overflow, n_nodes, n_tris, w_nodes, w_tris);
+    if (valid) {
+      if (kind == 0) __stcs(&q.hits[idx], make_float4(L.t, L.u, L.v, __int_as_float(L.tri)));
+      else {
+        const float4 inc = (L.tri == 0) ? __ldcs(&q.sh_unlit[idx]) : __ldcs(&q.sh_lit[idx]);
+        const float4 prev = q.accum[slot];
+        q.accum[slot] = make_float4(prev.x + inc.x, prev.y + inc.y, prev.z + inc.z, 0.0f);
+      }
+    }
+  }
+  packet_counters(q, overflow, n_nodes, n_tris, w_nodes, w_tris);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -858,19 +1101,43 @@ cudaError_t traverse_enable_smem(int bvh, size_t bytes) {
 
 // Scenes with analytic primitives (s.n_prims > 0) run the ANALYTIC instantiations; everything else keeps the leaner
 // triangle-only code.  The shared-memory variant exists for triangle-only scenes.
-void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int grid, size_t smem_bytes, cudaStream_t st) {
+void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int mode, int grid, size_t smem_bytes, cudaStream_t st) {
   const bool ref = bvh == RTB_BVH_REFERENCE;
   if (s.n_prims > 0) {
-    if (ref) k_traverse_ref<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth);
-    else k_traverse_lbvh<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth);
+    if (ref) k_traverse_ref<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode);
+    else k_traverse_lbvh<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode);
   } else if (smem_bytes > 0) {  // small scene: one 1024-thread block per SM works out of its shared-memory copy
-    if (ref) k_traverse_ref<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
-    else k_traverse_lbvh<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth);
+    if (ref) k_traverse_ref<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth, mode);
+    else k_traverse_lbvh<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth, mode);
   } else {
-    if (ref) k_traverse_ref<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth);
-    else k_traverse_lbvh<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth);
+    if (ref) k_traverse_ref<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode);
+    else k_traverse_lbvh<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode);
   }
 }
+
+void launch_primary(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st) {
+  const bool ref = bvh == RTB_BVH_REFERENCE;
+  if (s.n_prims > 0) {
+    if (ref) k_primary<RTB_BVH_REFERENCE, true><<<grid, kStreamBlock, 0, st>>>(f, s, q, c);
+    else k_primary<RTB_BVH_LBVH, true><<<grid, kStreamBlock, 0, st>>>(f, s, q, c);
+  } else {
+    if (ref) k_primary<RTB_BVH_REFERENCE, false><<<grid, kStreamBlock, 0, st>>>(f, s, q, c);
+    else k_primary<RTB_BVH_LBVH, false><<<grid, kStreamBlock, 0, st>>>(f, s, q, c);
+  }
+}
+
+void launch_packet(int bvh, const SceneView& s, const QueueView& q, int depth, int kind, int grid, cudaStream_t st) {
+  const bool ref = bvh == RTB_BVH_REFERENCE;
+  if (s.n_prims > 0) {
+    if (ref) k_packet<RTB_BVH_REFERENCE, true><<<grid, kStreamBlock, 0, st>>>(s, q, depth, kind);
+    else k_packet<RTB_BVH_LBVH, true><<<grid, kStreamBlock, 0, st>>>(s, q, depth, kind);
+  } else {
+    if (ref) k_packet<RTB_BVH_REFERENCE, false><<<grid, kStreamBlock, 0, st>>>(s, q, depth, kind);
+    else k_packet<RTB_BVH_LBVH, false><<<grid, kStreamBlock, 0, st>>>(s, q, depth, kind);
+  }
+}
+
+int stream_block_threads() { return kStreamBlock; }
 
 void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,
                   cudaStream_t st) {

@@ -230,19 +230,28 @@ __device__ __forceinline__ bool moller_trumbore(const Ray& r, f3 v0, f3 e1, f3 e
   return t > RTB_EPSILON;
 }
 
+// Which of two hits a closest-hit query keeps.  Reference flavour (TIE = false): compute:179, strictly closer, so the first
+// triangle tested wins among equal t — the reference's traversal order decides.  LBVH flavour (TIE = true): among equal t the
+// smaller leaf-order index wins, which makes the result independent of the order triangles are tested in: the per-lane
+// ordered traversal, the per-thread one and the packet traversal (trace.cu) all return the same (t, triangle).
+template <bool TIE>
+__device__ __forceinline__ bool closer_hit(float t, int32_t tri, float best_t, int32_t best_tri) {
+  return t < best_t || (TIE && t == best_t && tri < best_tri);
+}
+
 // For an analytic primitive the hit record holds (t_world, t_object, face code) in (t, u, v).
-template <bool ANALYTIC>
+template <bool ANALYTIC, bool TIE>
 __device__ __forceinline__ void test_triangle_closest(const SceneView& s, const Ray& r, int32_t tri, Hit& best) {
   const float4 a = __ldg(&s.tri_isect[RTB_TRI_F4 * tri]), b = __ldg(&s.tri_isect[RTB_TRI_F4 * tri + 1]), c = __ldg(&s.tri_isect[RTB_TRI_F4 * tri + 2]);
   float t, u, v;
   if (ANALYTIC && __float_as_int(c.w) != 0) {
     int face;
-    if (intersect_analytic(&s.prims[6 * __float_as_int(a.x)], __float_as_int(c.w), r.o, r.d, t, u, face) && t < best.t) {
+    if (intersect_analytic(&s.prims[6 * __float_as_int(a.x)], __float_as_int(c.w), r.o, r.d, t, u, face) && closer_hit<TIE>(t, tri, best.t, best.tri)) {
       best.t = t; best.u = u; best.v = (float)face; best.tri = tri;
     }
     return;
   }
-  if (moller_trumbore(r, mk3(a), mk3(b), mk3(c), t, u, v) && t < best.t) { best.t = t; best.u = u; best.v = v; best.tri = tri; }
+  if (moller_trumbore(r, mk3(a), mk3(b), mk3(c), t, u, v) && closer_hit<TIE>(t, tri, best.t, best.tri)) { best.t = t; best.u = u; best.v = v; best.tri = tri; }
 }
 template <bool ANALYTIC>
 __device__ __forceinline__ bool test_triangle_any(const SceneView& s, const Ray& r, int32_t tri, float t_limit) {
@@ -276,7 +285,7 @@ __device__ __forceinline__ bool traverse_reference(const SceneView& s, const Ray
     if (count > 0) {
       for (int32_t i = 0; i < count; i++) {
         if (ANY) { if (test_triangle_any<ANALYTIC>(s, r, left_or_first + i, t_limit)) return true; }
-        else test_triangle_closest<ANALYTIC>(s, r, left_or_first + i, best);
+        else test_triangle_closest<ANALYTIC, false>(s, r, left_or_first + i, best);
       }
     } else if (sp + 2 <= RTB_STACK_REF) {
       stack[sp++] = left_or_first + 1;
@@ -395,7 +404,7 @@ __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, 
       const int32_t first = code >> 3, count = (code & 7) + 1;
       for (int32_t i = 0; i < count; i++) {
         if (ANY) { if (test_triangle_any<ANALYTIC>(s, r, first + i, t_limit)) return true; }
-        else test_triangle_closest<ANALYTIC>(s, r, first + i, best);
+        else test_triangle_closest<ANALYTIC, true>(s, r, first + i, best);
       }
     }
     // pop the next deferred child that can still matter
@@ -403,7 +412,7 @@ __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, 
       if (sp == 0) return best.tri >= 0;
       sp--;
       const float2 e = stack[sp];
-      if (ANY ? !(e.x > t_limit) : !(e.x >= best.t)) { cur = __float_as_int(e.y); break; }
+      if (ANY ? !(e.x > t_limit) : !(e.x > best.t)) { cur = __float_as_int(e.y); break; }  // '>': a triangle tying with the best hit may sit exactly at the entry
     }
   }
 }
