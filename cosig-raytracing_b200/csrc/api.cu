@@ -31,6 +31,7 @@ struct DeviceScene {
   int32_t* perm = nullptr;
   int32_t n_tris = 0, n_nodes = 0, n_mats = 0, root = 0;
   int bvh_mode = RTB_BVH_REFERENCE;
+  int flavour = RTB_BVH_REFERENCE;  // what the kernels dispatch on: RTB_BVH_REFERENCE, RTB_BVH_LBVH (binary records) or RTB_BVH_WIDE
   int node_floats = 8;
 };
 
@@ -80,7 +81,7 @@ struct DeviceState {
   int32_t *aux_prim = nullptr, *aux_mat = nullptr;
   float* aux_t = nullptr;
   size_t aux_px = 0;
-  int grid_traverse[2] = {0, 0};
+  int grid_traverse[3] = {0, 0, 0};
   size_t smem_limit = 0;       // opt-in dynamic shared memory per block
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_trace, prof_shadow, prof_resolve;
   size_t prof_used[3] = {0, 0, 0};
@@ -103,8 +104,9 @@ struct rtb_context {
   int n_lanes = 4;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues
   uint64_t frame_id = 0;
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
-  int packet_closest = 0;     // RTB_PACKET_CLOSEST: closest-hit rays of depth <= this go through the packet kernels (-1: none, k_raygen + per-lane)
-  int packet_shadow = 0;      // RTB_PACKET_SHADOW: shadow rays emitted at depth <= this go through k_packet (-1: none)
+  int wide = 1;               // RTB_WIDE: RTB_BVH_LBVH scenes are stored as 8-wide quantised records (0: binary two-box records)
+  int packet_closest = -1;     // RTB_PACKET_CLOSEST: closest-hit rays of depth <= this go through the packet kernels (-1: none, k_raygen + per-lane)
+  int packet_shadow = -1;     // RTB_PACKET_SHADOW: shadow rays emitted at depth <= this go through k_packet (-1: none)
   int32_t tail_max = 65536;   // queues smaller than this finish in k_tail (RTB_TAIL_MAX; 0 = pure wavefront); sweep: profiles/r1e_sweep_tail_max.log
   std::vector<void*> ipc_opened;
   static constexpr int kTickets = 16;  // frames in flight through rtb_render_begin
@@ -250,11 +252,13 @@ void prof_pair(DeviceState& d, int family, cudaEvent_t& a, cudaEvent_t& b) {
 // ---------------------------------------------------------------------------------------------------------------------
 int upload_on_device(rtb_context* ctx, DeviceState& d, const rtb_scene_desc& desc, const std::vector<FlattenObject>& objs, int32_t n_out,
                      const std::vector<float>& mats, const std::vector<float>& prims, int bvh_mode, float& ms_build) {
+  const bool wide = bvh_mode == RTB_BVH_LBVH && ctx->wide != 0;
   CK(ctx, cudaSetDevice(d.device));
   device_sync(d);
   free_scene(d);
   DeviceScene& s = d.scene;
   s.bvh_mode = bvh_mode;
+  s.flavour = wide ? RTB_BVH_WIDE : bvh_mode;
   s.n_tris = n_out;
   s.n_mats = (int32_t)(mats.size() / 8);
   CK(ctx, cudaMalloc(&s.materials, mats.size() * sizeof(float)));
@@ -305,9 +309,10 @@ int upload_on_device(rtb_context* ctx, DeviceState& d, const rtb_scene_desc& des
     CK(ctx, cudaStreamSynchronize(d.stream));  // bvh vectors go out of scope
   } else {
     const int32_t max_nodes = n_out > 1 ? n_out - 1 : 1;
-    s.node_floats = 4 * lbvh_node_f4;
+    const int rec_f4 = node_record_f4(s.flavour);
+    s.node_floats = 4 * rec_f4;
     float4* big = nullptr;  // worst-case sized; the records actually written are copied into an exact allocation below
-    CK(ctx, cudaMalloc(&big, (size_t)max_nodes * lbvh_node_f4 * sizeof(float4)));
+    CK(ctx, cudaMalloc(&big, (size_t)max_nodes * rec_f4 * sizeof(float4)));
     LbvhBuffers b;
     b.nodes = big;
     b.perm = s.perm;
@@ -319,15 +324,15 @@ int upload_on_device(rtb_context* ctx, DeviceState& d, const rtb_scene_desc& des
     if (cudaMalloc(&root_dev, 2 * sizeof(int32_t)) != cudaSuccess) { cudaFree(ws); cudaFree(big); return fail(ctx, RTB_E_CUDA, "cudaMalloc(root) failed"); }
     b.workspace = ws;
     b.root_out = root_dev;
-    cudaError_t e = lbvh_build(s.raw, n_out, b, d.stream);
+    cudaError_t e = lbvh_build(s.raw, n_out, b, d.stream, wide);
     if (e == cudaSuccess) { launch_pack(s.raw, s.nrm, s.perm, n_out, s.isect, s.shade, d.stream); e = cudaGetLastError(); }
     if (e == cudaSuccess) e = cudaMemcpyAsync(root_host, root_dev, sizeof root_host, cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
     if (e == cudaSuccess) {
       s.root = root_host[0];
       s.n_nodes = std::max(1, std::min(root_host[1], max_nodes));
-      e = cudaMalloc(&s.nodes, (size_t)s.n_nodes * lbvh_node_f4 * sizeof(float4));
-      if (e == cudaSuccess) e = cudaMemcpyAsync(s.nodes, big, (size_t)s.n_nodes * lbvh_node_f4 * sizeof(float4), cudaMemcpyDeviceToDevice, d.stream);
+      e = cudaMalloc(&s.nodes, (size_t)s.n_nodes * rec_f4 * sizeof(float4));
+      if (e == cudaSuccess) e = cudaMemcpyAsync(s.nodes, big, (size_t)s.n_nodes * rec_f4 * sizeof(float4), cudaMemcpyDeviceToDevice, d.stream);
     }
     if (e == cudaSuccess) e = cudaEventRecord(d.ev_end, d.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
@@ -346,7 +351,7 @@ int upload_on_device(rtb_context* ctx, DeviceState& d, const rtb_scene_desc& des
 // ---------------------------------------------------------------------------------------------------------------------
 int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, void* dst, int& launches, int& chunks) {
   CK(ctx, cudaSetDevice(d.device));
-  const int bvh = d.scene.bvh_mode;
+  const int bvh = d.scene.flavour;
   const SceneView sv = scene_view(d.scene);
   const int32_t local_rows = band_local_rows(f.height, f.band_rank, f.band_world, f.band_rows);
   const int32_t tiles_x = (f.width + 7) / 8;
@@ -419,9 +424,12 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
         CK(ctx, cudaMemsetAsync(L.q.counters, 0, (size_t)L.q.depth_cap * RTB_CNT_BLOCKS * sizeof(int32_t), stream));
         // raygen fills the depth-0 queue; depth d: traverse (closest-hit rays of depth d + shadow rays emitted at depth d-1),
         // then shade (or, for short queues, k_tail).  One more traverse at the end serves the last depth's shadow rays.
-        // Depth 0 is coherent (8x4-pixel tiles), and so are the shadow rays those pixels emit: they go through the packet kernels
-        // (k_primary = raygen + traversal fused; k_packet); deeper, incoherent rays through the per-lane persistent kernel.
-        const int pk_closest = ctx->packet_closest, pk_shadow = ctx->packet_shadow;
+        // Optional packet kernels (RTB_PACKET_CLOSEST / RTB_PACKET_SHADOW >= 0; off by default): depth 0 is coherent (8x4-pixel tiles),
+        // and so are the shadow rays those pixels emit; k_primary = raygen + traversal fused, k_packet = 32 queue entries per walk.
+        // Measured (profiles/r2_sweep_packet.log): at 4K over 1 M triangles a tile's rays share the top of the tree only — its union
+        // of nodes is ~3x one ray's path — so packets lose 8-60 % there; they remain for scenes of few large triangles.
+        const bool packets = bvh != RTB_BVH_WIDE;  // the packet kernels walk the reference tree and the binary LBVH records
+        const int pk_closest = packets ? ctx->packet_closest : -1, pk_shadow = packets ? ctx->packet_shadow : -1;
         const int packet_grid = d.sm_count * 8;
         if (pk_closest >= 0) {
           const int tb = stream_block_threads();
@@ -608,6 +616,7 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
   if (const char* env = std::getenv("RTB_LANES")) ctx->n_lanes = std::min((int)DeviceState::kMaxLanes, std::max(1, std::atoi(env)));
   if (const char* env = std::getenv("RTB_SMEM")) ctx->smem_mode = std::atoi(env);
   if (const char* env = std::getenv("RTB_SPLIT_BLOCKING")) ctx->split_blocking = std::atoi(env);
+  if (const char* env = std::getenv("RTB_WIDE")) ctx->wide = std::atoi(env);
   if (const char* env = std::getenv("RTB_PACKET_CLOSEST")) ctx->packet_closest = std::atoi(env);
   if (const char* env = std::getenv("RTB_PACKET_SHADOW")) ctx->packet_shadow = std::atoi(env);
   if (const char* env = std::getenv("RTB_TAIL_MAX")) ctx->tail_max = (int32_t)std::max(0LL, std::atoll(env));
@@ -899,7 +908,7 @@ int rtb_render_aux(rtb_context* ctx, const rtb_render_params* p, int32_t* prim_i
     d.aux_px = n_px;
   }
   device_sync(d);
-  launch_aux(d.scene.bvh_mode, f, scene_view(d.scene), d.aux_prim, d.aux_t, d.aux_mat, d.sm_count * 8, d.stream);
+  launch_aux(d.scene.flavour, f, scene_view(d.scene), d.aux_prim, d.aux_t, d.aux_mat, d.sm_count * 8, d.stream);
   CK(ctx, cudaGetLastError());
   if (prim_id) CK(ctx, cudaMemcpyAsync(prim_id, d.aux_prim, n_px * 4, cudaMemcpyDeviceToHost, d.stream));
   if (t) CK(ctx, cudaMemcpyAsync(t, d.aux_t, n_px * 4, cudaMemcpyDeviceToHost, d.stream));
@@ -951,6 +960,11 @@ int rtb_get_bvh(rtb_context* ctx, void* nodes, int64_t nodes_capacity_bytes, int
     CK(ctx, cudaMemcpy(perm, d.scene.perm, (size_t)d.scene.n_tris * 4, cudaMemcpyDeviceToHost));
   }
   return RTB_OK;
+}
+
+int32_t rtb_get_bvh_node_words(rtb_context* ctx) {
+  if (!ctx || !ctx->has_scene) return 0;
+  return ctx->devs[0].scene.node_floats;
 }
 
 int rtb_get_stats(rtb_context* ctx, rtb_stats* out) {

@@ -19,7 +19,7 @@ void launch_pack(const float4* raw, const float4* nrm, const int32_t* perm, int3
 
 // ---- lbvh.cu (K2: Morton-code LBVH built on the GPU) -------------------------------------------------------------------
 struct LbvhBuffers {            // all device memory, sized by lbvh_workspace_bytes / allocated by the caller
-  float4* nodes;                // (4 or 8, see lbvh_node_f4) * max(1, n-1): worst case; root_out[1] tells how many records were written
+  float4* nodes;                // (4 or 8, see lbvh_node_f4; wide: 6) * max(1, n-1): worst case; root_out[1] tells how many records were written
   int32_t* perm;                // n
   void* workspace;              // lbvh_workspace_bytes(n)
   size_t workspace_bytes;
@@ -28,7 +28,10 @@ struct LbvhBuffers {            // all device memory, sized by lbvh_workspace_by
 size_t lbvh_workspace_bytes(int32_t n);
 constexpr int lbvh_node_f4 = RTB_LBVH_WIDTH == 4 ? 8 : 4;  // float4 per node record
 // Returns cudaSuccess or the failing call's error.  Asynchronous on `st`.
-cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaStream_t st);
+// wide: emit 8-wide quantised records (RTB_WIDE_F4 float4 each, trace.cuh) instead of the binary two-box records; the wide build
+// synchronises `st` (it reads its work-list size back between batches of tree levels).
+cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaStream_t st, bool wide);
+int node_record_f4(int bvh);  // float4 per node record of a kernel-side flavour (RTB_BVH_REFERENCE / RTB_BVH_LBVH / RTB_BVH_WIDE)
 
 // ---- trace.cu (K3-K8: the per-pixel wavefront) --------------------------------------------------------------------------
 void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st);

@@ -38,6 +38,8 @@ struct Workspace {
   int32_t* flag;             // n-1
   float4* box;               // 2*(2n-1): min,max of internal nodes then leaves
   int32_t* idx4;             // n-1: compact index of each emitted 4-wide node (exclusive scan of the emit flags)
+  void* wide_queue[2];       // n-1 WideItem each: work lists of the wide collapse (one tree level per launch, ping-pong)
+  int32_t* wide_counters;    // 4
   void* cub_temp;
   size_t cub_bytes;
 };
@@ -67,6 +69,9 @@ Workspace carve(void* base, int32_t n) {
   w.flag = (int32_t*)take(ni * 4);
   w.box = (float4*)take(na * 2 * sizeof(float4));
   w.idx4 = (int32_t*)take(ni * 4);
+  w.wide_queue[0] = take(ni * 8);
+  w.wide_queue[1] = take(ni * 8);
+  w.wide_counters = (int32_t*)take(16);
   w.cub_bytes = cub_temp_bytes(n);
   w.cub_temp = take(w.cub_bytes);
   return w;
@@ -304,6 +309,148 @@ __global__ void __launch_bounds__(kBlock) k_emit4(int32_t n, const int2* __restr
 
 #endif
 
+
+// ---- 8-wide quantised records (RTB_BVH_WIDE; layout and arithmetic: trace.cuh) ----------------------------------------------------
+// The binary radix tree is collapsed top-down, one tree level of WIDE nodes per launch: a wide node starts from the two
+// children of its binary node and keeps replacing the child with the largest surface area by that child's two children until it
+// has eight (children whose range holds <= RTB_LEAF_MAX triangles are leaves and stay).  The children that remain inner nodes
+// get consecutive record indices (one atomicAdd) and form the next level's work list.  Children go to the slot whose octant
+// best matches their position relative to the node's centre (greedy assignment), which is what lets the traversal order them
+// by (slot XOR ray octant).  Triangles keep the Morton order (leaf references address `perm` positions), so the record order
+// may vary from run to run but nothing a ray returns does.
+struct WideItem { int32_t bnode, wnode; };
+
+__device__ __forceinline__ float half_area(const float4 mn, const float4 mx) {
+  const float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z;
+  return dx * dy + dy * dz + dz * dx;
+}
+
+// Quantisation grid of one axis: the biased exponent byte of S = 2^15 * cell, cell = the smallest power of two with 255 cells >= extent.
+__device__ __forceinline__ unsigned grid_exponent(float extent, float& inv_cell) {
+  int e = -100;
+  if (extent > 0.0f) e = ilogbf(extent / 255.0f) + 1;
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  while (e < 100 && ldexpf(255.0f, e) < extent) e++;
+  inv_cell = ldexpf(1.0f, -e);
+  return (unsigned)(e + 15 + 127);
+}
+
+__global__ void __launch_bounds__(128) k_wide_level(int32_t n, const int2* __restrict__ child, const int2* __restrict__ range, const float4* __restrict__ box,
+                                                    const WideItem* __restrict__ in, const int32_t* __restrict__ n_in, WideItem* __restrict__ out,
+                                                    int32_t* n_out, int32_t* n_nodes, float4* __restrict__ nodes, int32_t capacity, int32_t* error) {
+  const int32_t n_int = n - 1;
+  const int32_t count_in = *n_in;
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count_in; i += gridDim.x * blockDim.x) {
+    const WideItem it = in[i];
+    int32_t ref[8];  // Karras references: >= 0 inner node, < 0 ~leaf
+    int ns = 2;
+    { const int2 ch = child[it.bnode]; ref[0] = ch.x; ref[1] = ch.y; }
+    auto big = [&](int32_t r) { if (r < 0) return false; const int2 rg = range[r]; return rg.y - rg.x + 1 > RTB_LEAF_MAX; };
+    auto box_at = [&](int32_t r) { return r >= 0 ? (size_t)r : (size_t)(n_int + ~r); };
+    while (ns < 8) {
+      int best = -1;
+      float best_area = -1.0f;
+      for (int k = 0; k < ns; k++)
+        if (big(ref[k])) {
+          const size_t b = box_at(ref[k]);
+          const float a = half_area(box[2 * b], box[2 * b + 1]);
+          if (a > best_area) { best_area = a; best = k; }
+        }
+      if (best < 0) break;
+      const int2 ch = child[ref[best]];
+      ref[best] = ch.x;
+      ref[ns++] = ch.y;
+    }
+    int n_inner = 0;
+    for (int k = 0; k < ns; k++) n_inner += big(ref[k]) ? 1 : 0;
+    int32_t wbase = 0, qbase = 0;
+    if (n_inner > 0) {
+      wbase = atomicAdd(n_nodes, n_inner);
+      qbase = atomicAdd(n_out, n_inner);
+      if (wbase + n_inner > capacity) { atomicExch(error, 1); n_inner = 0; }
+    }
+    // slot assignment: cost[s][k] = sigma(s) . (centre_k - centre_node), take the largest remaining pair each round
+    const float4 nmn = box[2 * (size_t)it.bnode], nmx = box[2 * (size_t)it.bnode + 1];
+    const float ccx = 0.5f * (nmn.x + nmx.x), ccy = 0.5f * (nmn.y + nmx.y), ccz = 0.5f * (nmn.z + nmx.z);
+    float vx[8], vy[8], vz[8];
+    for (int k = 0; k < ns; k++) {
+      const size_t b = box_at(ref[k]);
+      const float4 mn = box[2 * b], mx = box[2 * b + 1];
+      vx[k] = 0.5f * (mn.x + mx.x) - ccx; vy[k] = 0.5f * (mn.y + mx.y) - ccy; vz[k] = 0.5f * (mn.z + mx.z) - ccz;
+    }
+    int child_of_slot[8];
+    for (int sidx = 0; sidx < 8; sidx++) child_of_slot[sidx] = -1;
+    unsigned child_done = 0u;
+    for (int round = 0; round < ns; round++) {
+      int bs = -1, bk = -1;
+      float bc = -INFINITY;
+      for (int sidx = 0; sidx < 8; sidx++) {
+        if (child_of_slot[sidx] >= 0) continue;
+        for (int k = 0; k < ns; k++) {
+          if (child_done & (1u << k)) continue;
+          const float c = ((sidx & 4) ? vx[k] : -vx[k]) + ((sidx & 2) ? vy[k] : -vy[k]) + ((sidx & 1) ? vz[k] : -vz[k]);
+          if (c > bc) { bc = c; bs = sidx; bk = k; }
+        }
+      }
+      child_of_slot[bs] = bk;
+      child_done |= 1u << bk;
+    }
+    // quantise and write the record
+    float icx, icy, icz;
+    const unsigned esx = grid_exponent(nmx.x - nmn.x, icx), esy = grid_exponent(nmx.y - nmn.y, icy), esz = grid_exponent(nmx.z - nmn.z, icz);
+    unsigned q[6][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}, {0u, 0u}, {0u, 0u}, {0u, 0u}};  // lo.x lo.y lo.z hi.x hi.y hi.z, 8 bytes each
+    int32_t out_ref[8];
+    unsigned valid = 0u;
+    int inner_seen = 0;
+    for (int sidx = 0; sidx < 8; sidx++) {
+      const int k = child_of_slot[sidx];
+      unsigned lo[3] = {255u, 255u, 255u}, hi[3] = {0u, 0u, 0u};  // empty slot: inverted box
+      out_ref[sidx] = RTB_REF_DONE;
+      if (k >= 0) {
+        valid |= 1u << sidx;
+        const size_t b = box_at(ref[k]);
+        const float4 mn = box[2 * b], mx = box[2 * b + 1];
+        const float l[3] = {floorf((mn.x - nmn.x) * icx), floorf((mn.y - nmn.y) * icy), floorf((mn.z - nmn.z) * icz)};
+        const float h[3] = {ceilf((mx.x - nmn.x) * icx), ceilf((mx.y - nmn.y) * icy), ceilf((mx.z - nmn.z) * icz)};
+        for (int a = 0; a < 3; a++) {
+          lo[a] = (unsigned)fminf(fmaxf(l[a], 0.0f), 255.0f);
+          hi[a] = (unsigned)fminf(fmaxf(h[a], 0.0f), 255.0f);
+        }
+        if (ref[k] < 0) out_ref[sidx] = lbvh_leaf_ref(~ref[k], 1);
+        else if (!big(ref[k])) { const int2 rg = range[ref[k]]; out_ref[sidx] = lbvh_leaf_ref(rg.x, rg.y - rg.x + 1); }
+        else if (inner_seen < n_inner) {
+          out_ref[sidx] = wbase + inner_seen;
+          out[qbase + inner_seen] = WideItem{ref[k], wbase + inner_seen};
+          inner_seen++;
+        }
+      }
+      for (int a = 0; a < 3; a++) {
+        q[a][sidx >> 2] |= lo[a] << (8 * (sidx & 3));
+        q[3 + a][sidx >> 2] |= hi[a] << (8 * (sidx & 3));
+      }
+    }
+    float4* rec = nodes + RTB_WIDE_F4 * (size_t)it.wnode;
+    rec[0] = make_float4(nmn.x, nmn.y, nmn.z, __uint_as_float(esx | (esy << 8) | (esz << 16) | (valid << 24)));
+    rec[1] = make_float4(__int_as_float(out_ref[0]), __int_as_float(out_ref[1]), __int_as_float(out_ref[2]), __int_as_float(out_ref[3]));
+    rec[2] = make_float4(__uint_as_float(q[0][0]), __uint_as_float(q[0][1]), __uint_as_float(q[1][0]), __uint_as_float(q[1][1]));
+    rec[3] = make_float4(__uint_as_float(q[2][0]), __uint_as_float(q[2][1]), __uint_as_float(q[3][0]), __uint_as_float(q[3][1]));
+    rec[4] = make_float4(__uint_as_float(q[4][0]), __uint_as_float(q[4][1]), __uint_as_float(q[5][0]), __uint_as_float(q[5][1]));
+    rec[5] = make_float4(__int_as_float(out_ref[4]), __int_as_float(out_ref[5]), __int_as_float(out_ref[6]), __int_as_float(out_ref[7]));
+  }
+}
+
+__global__ void k_wide_init(int32_t n, WideItem* queue, int32_t* counters, int32_t* root_out) {
+  // counters: [0] items in queue A, [1] items in queue B, [2] records allocated, [3] error flag
+  const bool has_root = n > RTB_LEAF_MAX;
+  queue[0] = WideItem{0, 0};
+  counters[0] = has_root ? 1 : 0;
+  counters[1] = 0;
+  counters[2] = has_root ? 1 : 0;
+  counters[3] = 0;
+  root_out[0] = has_root ? 0 : lbvh_leaf_ref(0, n);
+  root_out[1] = 0;
+}
+
 inline int grid_for(int64_t n) {
   const int64_t g = (n + kBlock - 1) / kBlock;
   return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -315,10 +462,10 @@ size_t lbvh_workspace_bytes(int32_t n) {
   if (n <= 0) return 256;
   const size_t ni = (size_t)(n > 1 ? n - 1 : 1), nt = (size_t)n, na = 2 * nt;
   return align_up(24) + 2 * align_up(nt * 8) + align_up(nt * 4) + 2 * align_up(ni * 8) + align_up(na * 4) + align_up(ni * 4) +
-         align_up(na * 2 * sizeof(float4)) + align_up(ni * 4) + align_up(cub_temp_bytes(n)) + 256;
+         align_up(na * 2 * sizeof(float4)) + align_up(ni * 4) + 2 * align_up(ni * 8) + align_up(16) + align_up(cub_temp_bytes(n)) + 256;
 }
 
-cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaStream_t st) {
+cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaStream_t st, bool wide) {
   if (n <= 0) return cudaSuccess;
   Workspace w = carve(b.workspace, n);
   k_init_bounds<<<1, 32, 0, st>>>(w.bounds);
@@ -334,6 +481,35 @@ cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaS
     k_hierarchy<<<grid_for(n - 1), kBlock, 0, st>>>(w.keys_sorted, n, w.child, w.range, w.parent);
   }
   k_refit<<<grid_for(n), kBlock, 0, st>>>(raw, b.perm, n, w.child, w.parent, w.flag, w.box);
+  if (wide) {
+    // Collapse into 8-wide records, one level per launch.  The number of levels is not known on the host: launch them in batches
+    // and read the work-list size back after each batch (typically one round trip: 12 levels reach 8^12 leaves).
+    WideItem* qa = (WideItem*)w.wide_queue[0];
+    WideItem* qb = (WideItem*)w.wide_queue[1];
+    int32_t* cnt = w.wide_counters;
+    k_wide_init<<<1, 1, 0, st>>>(n, qa, cnt, b.root_out);
+    const int32_t capacity = n > 1 ? n - 1 : 1;
+    int side = 0;
+    for (int batch = 0; batch < 16; batch++) {
+      for (int level = 0; level < 12; level++) {
+        cudaError_t e2 = cudaMemsetAsync(cnt + (side ^ 1), 0, sizeof(int32_t), st);
+        if (e2 != cudaSuccess) return e2;
+        k_wide_level<<<148 * 4, 128, 0, st>>>(n, w.child, w.range, w.box, side ? qb : qa, cnt + side, side ? qa : qb, cnt + (side ^ 1), cnt + 2,
+                                               b.nodes, capacity, cnt + 3);
+        side ^= 1;
+      }
+      int32_t host[4] = {0, 0, 0, 0};
+      cudaError_t e2 = cudaMemcpyAsync(host, cnt, sizeof host, cudaMemcpyDeviceToHost, st);
+      if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+      if (e2 != cudaSuccess) return e2;
+      if (host[3] != 0) return cudaErrorMemoryAllocation;
+      if (host[side] == 0) {
+        e2 = cudaMemcpyAsync(b.root_out + 1, cnt + 2, sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+        return e2 != cudaSuccess ? e2 : cudaGetLastError();
+      }
+    }
+    return cudaErrorUnknown;  // deeper than 192 wide levels: not a tree this builder produces
+  }
 #if RTB_LBVH_WIDTH == 4
   if (n > 1) {
     k_mark4<<<grid_for(n - 1), kBlock, 0, st>>>(n, w.range, w.parent, w.flag);

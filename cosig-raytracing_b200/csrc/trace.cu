@@ -479,6 +479,86 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_traverse, wide flavour: the same persistent per-lane loop over the 8-wide quantised records (trace.cuh: wide_visit).
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef RTB_WIDE_MIN_BLOCKS
+#define RTB_WIDE_MIN_BLOCKS 8
+#endif
+template <bool SMEM, bool ANALYTIC>
+__global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB_WIDE_MIN_BLOCKS) k_traverse_wide(const SceneView s, const QueueView q, const int depth, const int mode) {
+  extern __shared__ float4 sm_scene[];
+  const float4* nodes = s.nodes;
+  const float4* tri_isect = s.tri_isect;
+  if (SMEM) stage_scene(s, RTB_WIDE_F4, sm_scene, nodes, tri_isect);
+  const int lane = threadIdx.x & 31;
+  const int32_t n_closest = (mode & 1) ? RTB_CNT_RAY(q, depth) : 0;
+  const int32_t n_shadow = (depth == 0 || !(mode & 2)) ? 0 : RTB_CNT_SHADOW(q, depth - 1);
+  const int32_t total = n_closest + n_shadow;
+  const int in_q = depth & 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (depth > 0 && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
+    if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
+  }
+  uint2 stack[RTB_STACK_WIDE];  // deferred sibling groups: (node, octant-ordered hit mask)
+  int sp = 0;
+  int32_t cur = RTB_REF_DONE;
+  unsigned neg = 0u;
+  Lane L;
+  L.item = -1; L.shadow = false; L.done = false; L.t = 0.0f; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
+  L.o = L.d = L.inv = mk3(0.0f, 0.0f, 0.0f);
+  WorkPool pool;
+  unsigned overflow = 0, n_nodes = 0, n_tris = 0;
+
+  for (;;) {
+    const int n_out = __popc(__ballot_sync(kFull, L.item < 0 || L.done));
+    if (n_out >= RefillMin<SMEM>::value) {
+      if (L.item >= 0 && L.done) lane_finish(L, q, n_closest);
+      const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, L.item < 0, lane);
+      if (item >= 0) {
+        lane_load(L, q, item, n_closest, in_q);
+        sp = 0;
+        cur = s.n_tris > 0 ? s.root : RTB_REF_DONE;
+        L.done = cur == RTB_REF_DONE;
+        L.inv = safe_inverse(L.d);
+        neg = octant_of(L.d);
+      }
+      if (__ballot_sync(kFull, L.item >= 0 && !L.done) == 0) {
+        if (__ballot_sync(kFull, L.item >= 0) == 0 && pool.exhausted) break;
+        continue;
+      }
+    }
+
+    // ---- inner nodes: descend until this lane holds a leaf (or runs out of work) ----
+    while (cur >= 0) {
+      n_nodes++;
+      cur = wide_visit<SMEM>(nodes, cur, L.o, L.inv, neg, L.t, stack, sp, overflow);
+    }
+
+    // ---- leaf ----
+    if (cur != RTB_REF_DONE) {
+      const int32_t code = ~cur;
+      const int32_t first = code >> 3, count = (code & 7) + 1;
+      bool occluded = false;
+      n_tris += count;
+      for (int32_t i = 0; i < count && !occluded; i++) occluded = lane_test_triangle<SMEM, ANALYTIC, true>(L, s, tri_isect, first + i);
+      cur = occluded ? RTB_REF_DONE : wide_pop<SMEM>(nodes, neg, stack, sp);
+    }
+    if (cur == RTB_REF_DONE && L.item >= 0) { sp = 0; L.done = true; }
+  }
+
+  for (int o = 16; o > 0; o >>= 1) {
+    overflow += __shfl_xor_sync(kFull, overflow, o);
+    n_nodes += __shfl_xor_sync(kFull, n_nodes, o);
+    n_tris += __shfl_xor_sync(kFull, n_tris, o);
+  }
+  if (lane == 0) {
+    if (overflow) atomicAdd(&q.totals[4], (unsigned long long)overflow);
+    if (n_nodes) atomicAdd(&q.totals[5], (unsigned long long)n_nodes);
+    if (n_tris) atomicAdd(&q.totals[6], (unsigned long long)n_tris);
+  }
+}
+
 // =====================================================================================================================
 // Packet traversal: a warp walks the BVH ONCE for its 32 rays.  Rays that are neighbours on the screen (primary rays of an
 // 8x4 tile, the shadow rays those pixels emit towards the one light) visit nearly the same nodes, so the per-lane kernels
@@ -730,6 +810,15 @@ __global__ void __launch_bounds__(kStreamBlock) k_raygen(const FrameParams f, co
   bool have_box = false;
   if (BVH == RTB_BVH_REFERENCE) {
     if (s.n_nodes > 0) { rmn = mk3(__ldg(&s.nodes[0])); rmx = mk3(__ldg(&s.nodes[1])); have_box = true; }
+  } else if (BVH == RTB_BVH_WIDE) {
+    if (s.n_tris > 0 && s.root >= 0) {  // the root record's grid: p .. p + 256 cells (a superset of the scene's box)
+      const float4 h = __ldg(&s.nodes[RTB_WIDE_F4 * (size_t)s.root]);
+      const unsigned hdr = __float_as_uint(h.w);
+      const float cx = __uint_as_float((hdr & 0xffu) << 23) * 0.0078125f, cy = __uint_as_float((hdr & 0xff00u) << 15) * 0.0078125f, cz = __uint_as_float((hdr & 0xff0000u) << 7) * 0.0078125f;  // 256 cells = S * 2^-7
+      rmn = mk3(h.x - cx * 0.00390625f, h.y - cy * 0.00390625f, h.z - cz * 0.00390625f);  // one cell of slack on either side
+      rmx = mk3(h.x + cx * 1.00390625f, h.y + cy * 1.00390625f, h.z + cz * 1.00390625f);
+      have_box = true;
+    }
   } else if (s.n_tris > 0 && s.root >= 0) {
 #if RTB_LBVH_WIDTH == 4
     const float4* rec = s.nodes + 8 * (size_t)s.root;  // unused slots repeat slot 0's box, so the union may include them
@@ -760,6 +849,10 @@ __global__ void __launch_bounds__(kStreamBlock) k_raygen(const FrameParams f, co
         const f3 inv = safe_inverse(ray.d);
         float entry;
         survives = slab_hit_fma(inv, ray.o * inv, rmn, rmx, RTB_INFINITY, entry);
+        if (BVH == RTB_BVH_WIDE && !survives) {  // the FMA form rounds by ~1e-7 |origin / d|: decide near misses with the exact form over the slack box
+          Ray exact = ray;
+          survives = !(slab_entry(exact, rmn, rmx) >= RTB_INFINITY);
+        }
       }
     }
     if (valid) {
@@ -1082,20 +1175,25 @@ int blocks_per_sm(K kernel) {
 }  // namespace
 
 int traverse_blocks_per_sm(int bvh) {
+  if (bvh == RTB_BVH_WIDE) return blocks_per_sm(k_traverse_wide<false, false>);
   return bvh == RTB_BVH_REFERENCE ? blocks_per_sm(k_traverse_ref<false, false>) : blocks_per_sm(k_traverse_lbvh<false, false>);
 }
 
 void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st) {
   if (bvh == RTB_BVH_REFERENCE) k_raygen<RTB_BVH_REFERENCE><<<grid * kBlock / kStreamBlock, kStreamBlock, 0, st>>>(f, s, q, c);
+  else if (bvh == RTB_BVH_WIDE) k_raygen<RTB_BVH_WIDE><<<grid * kBlock / kStreamBlock, kStreamBlock, 0, st>>>(f, s, q, c);
   else k_raygen<RTB_BVH_LBVH><<<grid * kBlock / kStreamBlock, kStreamBlock, 0, st>>>(f, s, q, c);
 }
 
+int node_record_f4(int bvh) { return bvh == RTB_BVH_REFERENCE ? 2 : (bvh == RTB_BVH_WIDE ? RTB_WIDE_F4 : lbvh_node_f4); }
+
 size_t traverse_smem_bytes(int bvh, const SceneView& s) {
-  return ((size_t)s.n_nodes * (bvh == RTB_BVH_REFERENCE ? 2 : lbvh_node_f4) + (size_t)s.n_tris * RTB_TRI_F4) * sizeof(float4);
+  return ((size_t)s.n_nodes * node_record_f4(bvh) + (size_t)s.n_tris * RTB_TRI_F4) * sizeof(float4);
 }
 
 cudaError_t traverse_enable_smem(int bvh, size_t bytes) {
   if (bvh == RTB_BVH_REFERENCE) return cudaFuncSetAttribute(k_traverse_ref<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (bvh == RTB_BVH_WIDE) return cudaFuncSetAttribute(k_traverse_wide<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   return cudaFuncSetAttribute(k_traverse_lbvh<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
@@ -1103,6 +1201,12 @@ cudaError_t traverse_enable_smem(int bvh, size_t bytes) {
 // triangle-only code.  The shared-memory variant exists for triangle-only scenes.
 void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int mode, int grid, size_t smem_bytes, cudaStream_t st) {
   const bool ref = bvh == RTB_BVH_REFERENCE;
+  if (bvh == RTB_BVH_WIDE) {
+    if (s.n_prims > 0) k_traverse_wide<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode);
+    else if (smem_bytes > 0) k_traverse_wide<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth, mode);
+    else k_traverse_wide<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode);
+    return;
+  }
   if (s.n_prims > 0) {
     if (ref) k_traverse_ref<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode);
     else k_traverse_lbvh<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode);
@@ -1147,12 +1251,13 @@ void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, 
 
 void launch_tail(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,
                  cudaStream_t st) {
-  const bool ref = bvh == RTB_BVH_REFERENCE;
   if (s.n_prims > 0) {
-    if (ref) k_tail<RTB_BVH_REFERENCE, true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+    if (bvh == RTB_BVH_REFERENCE) k_tail<RTB_BVH_REFERENCE, true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+    else if (bvh == RTB_BVH_WIDE) k_tail<RTB_BVH_WIDE, true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
     else k_tail<RTB_BVH_LBVH, true><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
   } else {
-    if (ref) k_tail<RTB_BVH_REFERENCE, false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+    if (bvh == RTB_BVH_REFERENCE) k_tail<RTB_BVH_REFERENCE, false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
+    else if (bvh == RTB_BVH_WIDE) k_tail<RTB_BVH_WIDE, false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
     else k_tail<RTB_BVH_LBVH, false><<<grid, kBlock, 0, st>>>(f, s, q, c, depth, tail_max);
   }
 }
@@ -1162,23 +1267,25 @@ void launch_resolve(const FrameParams& f, const QueueView& q, const ChunkView& c
 }
 
 void launch_debug(int bvh, const FrameParams& f, const SceneView& s, const ChunkView& c, void* dst, int grid, cudaStream_t st) {
-  const bool ref = bvh == RTB_BVH_REFERENCE;
   if (s.n_prims > 0) {
-    if (ref) k_debug<RTB_BVH_REFERENCE, true><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
+    if (bvh == RTB_BVH_REFERENCE) k_debug<RTB_BVH_REFERENCE, true><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
+    else if (bvh == RTB_BVH_WIDE) k_debug<RTB_BVH_WIDE, true><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
     else k_debug<RTB_BVH_LBVH, true><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
   } else {
-    if (ref) k_debug<RTB_BVH_REFERENCE, false><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
+    if (bvh == RTB_BVH_REFERENCE) k_debug<RTB_BVH_REFERENCE, false><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
+    else if (bvh == RTB_BVH_WIDE) k_debug<RTB_BVH_WIDE, false><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
     else k_debug<RTB_BVH_LBVH, false><<<grid, kBlock, 0, st>>>(f, s, c, (uchar4*)dst);
   }
 }
 
 void launch_aux(int bvh, const FrameParams& f, const SceneView& s, int32_t* prim, float* t, int32_t* mat, int grid, cudaStream_t st) {
-  const bool ref = bvh == RTB_BVH_REFERENCE;
   if (s.n_prims > 0) {
-    if (ref) k_aux<RTB_BVH_REFERENCE, true><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
+    if (bvh == RTB_BVH_REFERENCE) k_aux<RTB_BVH_REFERENCE, true><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
+    else if (bvh == RTB_BVH_WIDE) k_aux<RTB_BVH_WIDE, true><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
     else k_aux<RTB_BVH_LBVH, true><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
   } else {
-    if (ref) k_aux<RTB_BVH_REFERENCE, false><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
+    if (bvh == RTB_BVH_REFERENCE) k_aux<RTB_BVH_REFERENCE, false><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
+    else if (bvh == RTB_BVH_WIDE) k_aux<RTB_BVH_WIDE, false><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
     else k_aux<RTB_BVH_LBVH, false><<<grid, kBlock, 0, st>>>(f, s, prim, t, mat);
   }
 }

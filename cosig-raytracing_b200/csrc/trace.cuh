@@ -417,9 +417,136 @@ __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 8-wide quantised LBVH (RTB_BVH_WIDE, the default form of RTB_BVH_LBVH; lbvh.cu: k_wide_level builds it from the binary radix
+// tree).  One 96-byte record = three 32-byte sectors = three 256-bit loads decides eight children, so a ray makes about a
+// third of the dependent node fetches of the two-box binary records and half the L1 wavefronts.  Record (24 words):
+//   w0-2  p = min corner of the node's box          w3  bytes: ESx, ESy, ESz (biased exponents of S = 2^15 * cell), valid mask
+//   w4-7  child references of slots 0-3             w8-15  lo.x[8] lo.y[8] lo.z[8] hi.x[8]   (one byte per slot)
+//   w16-19 hi.y[8] hi.z[8]                          w20-23 child references of slots 4-7
+// A child box is p + q * cell per axis with q rounded outward to 8 bits.  The byte goes into mantissa bits 8-15 of 1.0f by ONE
+// byte-permute (f = 1 + q * 2^-15, no integer->float conversion), and a slab plane is t = f * A + B with A = S / d and
+// B = (p - o) / d - A.  The rounding of that form is at most 2^-22 (|(p - o) / d| + |A|); the near planes are moved earlier and
+// the far planes later by 2^-20 of the same sum (1/32 of a cell), so every box the exact test would enter is entered whatever
+// the distance between camera and scene (no build-time padding, nothing to assume about the camera).  The boxes decide only
+// which nodes are opened; t, u, v and ids come from the unchanged triangle test.
+// Slot s sits on the + side of x / y / z where bit 2 / 1 / 0 of s is set (greedy assignment at build time), so visiting the hit
+// slots in increasing order of (s XOR the ray's negative-direction bits) goes roughly front to back without any distances.
+// ---------------------------------------------------------------------------------------------------------------------
+#define RTB_STACK_WIDE 48  /* deferred sibling groups: at most one per level of the wide tree */
+
+__device__ __forceinline__ unsigned octant_of(f3 d) { return (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u); }
+// m'[k] = m[k ^ neg] for an 8-bit mask
+__device__ __forceinline__ unsigned octant_permute(unsigned m, unsigned neg) {
+  if (neg & 1u) m = ((m & 0x55u) << 1) | ((m >> 1) & 0x55u);
+  if (neg & 2u) m = ((m & 0x33u) << 2) | ((m >> 2) & 0x33u);
+  if (neg & 4u) m = ((m & 0x0fu) << 4) | (m >> 4);
+  return m;
+}
+__device__ __forceinline__ float quant_to_float(unsigned word, unsigned selector) { return __uint_as_float(__byte_perm(word, 0x3F800000u, selector)); }
+
+// Tests the eight child boxes of the record at `rec` against the ray; returns the hit mask over slots and the slots' references.
+template <bool SMEM>
+__device__ __forceinline__ unsigned wide_test(const float4* rec, f3 o, f3 inv, unsigned neg, float bound, int32_t (&refs)[8]) {
+  float4 a0, a1, b0, b1, c0, c1;
+  ld8<SMEM>(rec, a0, a1);
+  ld8<SMEM>(rec + 2, b0, b1);
+  ld8<SMEM>(rec + 4, c0, c1);
+  refs[0] = __float_as_int(a1.x); refs[1] = __float_as_int(a1.y); refs[2] = __float_as_int(a1.z); refs[3] = __float_as_int(a1.w);
+  refs[4] = __float_as_int(c1.x); refs[5] = __float_as_int(c1.y); refs[6] = __float_as_int(c1.z); refs[7] = __float_as_int(c1.w);
+  const unsigned hdr = __float_as_uint(a0.w);
+  const float ax = inv.x * __uint_as_float((hdr & 0xffu) << 23), ay = inv.y * __uint_as_float((hdr & 0xff00u) << 15), az = inv.z * __uint_as_float((hdr & 0xff0000u) << 7);
+  const float ox = (a0.x - o.x) * inv.x, oy = (a0.y - o.y) * inv.y, oz = (a0.z - o.z) * inv.z;
+  const float ex = (fabsf(ox) + fabsf(ax)) * 9.5367431640625e-7f, ey = (fabsf(oy) + fabsf(ay)) * 9.5367431640625e-7f, ez = (fabsf(oz) + fabsf(az)) * 9.5367431640625e-7f;
+  const float bx = ox - ax, by = oy - ay, bz = oz - az;
+  const float bnx = bx - ex, bny = by - ey, bnz = bz - ez, bfx = bx + ex, bfy = by + ey, bfz = bz + ez;
+  // per axis: the planes a ray moving in + direction meets first are the lo planes
+  const bool px = (neg & 4u) == 0u, py = (neg & 2u) == 0u, pz = (neg & 1u) == 0u;
+  const unsigned lox[2] = {__float_as_uint(b0.x), __float_as_uint(b0.y)}, loy[2] = {__float_as_uint(b0.z), __float_as_uint(b0.w)};
+  const unsigned loz[2] = {__float_as_uint(b1.x), __float_as_uint(b1.y)}, hix[2] = {__float_as_uint(b1.z), __float_as_uint(b1.w)};
+  const unsigned hiy[2] = {__float_as_uint(c0.x), __float_as_uint(c0.y)}, hiz[2] = {__float_as_uint(c0.z), __float_as_uint(c0.w)};
+  const unsigned nx[2] = {px ? lox[0] : hix[0], px ? lox[1] : hix[1]}, fx[2] = {px ? hix[0] : lox[0], px ? hix[1] : lox[1]};
+  const unsigned ny[2] = {py ? loy[0] : hiy[0], py ? loy[1] : hiy[1]}, fy[2] = {py ? hiy[0] : loy[0], py ? hiy[1] : loy[1]};
+  const unsigned nz[2] = {pz ? loz[0] : hiz[0], pz ? loz[1] : hiz[1]}, fz[2] = {pz ? hiz[0] : loz[0], pz ? hiz[1] : loz[1]};
+  unsigned mask = 0u;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const int w = c >> 2;
+    const unsigned sel = 0x7604u | ((unsigned)(c & 3) << 4);
+    const float tnx = __fmaf_rn(quant_to_float(nx[w], sel), ax, bnx), tny = __fmaf_rn(quant_to_float(ny[w], sel), ay, bny), tnz = __fmaf_rn(quant_to_float(nz[w], sel), az, bnz);
+    const float tfx = __fmaf_rn(quant_to_float(fx[w], sel), ax, bfx), tfy = __fmaf_rn(quant_to_float(fy[w], sel), ay, bfy), tfz = __fmaf_rn(quant_to_float(fz[w], sel), az, bfz);
+    const float entry = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+    const float exit = fminf(fminf(tfx, tfy), fminf(tfz, bound));
+    if (entry <= exit) mask |= 1u << c;
+  }
+  return mask & (hdr >> 24);
+}
+
+__device__ __forceinline__ int32_t select_ref(const int32_t (&refs)[8], unsigned slot) {
+  const int32_t a = (slot & 1u) ? refs[1] : refs[0], b = (slot & 1u) ? refs[3] : refs[2], c = (slot & 1u) ? refs[5] : refs[4], d = (slot & 1u) ? refs[7] : refs[6];
+  const int32_t ab = (slot & 2u) ? b : a, cd = (slot & 2u) ? d : c;
+  return (slot & 4u) ? cd : ab;
+}
+template <bool SMEM>
+__device__ __forceinline__ int32_t load_ref(const float4* nodes, int32_t node, unsigned slot) {
+  const int32_t* w = (const int32_t*)(nodes + RTB_WIDE_F4 * (size_t)node);
+  const int32_t* p = &w[(slot < 4u ? 4 : 16) + (int)slot];
+  return SMEM ? *p : __ldg(p);
+}
+
+// One step of the wide traversal: visits node `cur`, returns the nearest child still to be looked at (a node >= 0 or a leaf
+// reference < 0) and defers its hit siblings as ONE stack entry (node, octant-ordered mask); RTB_REF_DONE when the ray is done.
+template <bool SMEM>
+__device__ __forceinline__ int32_t wide_pop(const float4* nodes, unsigned neg, uint2* stack, int& sp) {
+  if (sp == 0) return RTB_REF_DONE;
+  const uint2 e = stack[sp - 1];
+  const unsigned k = (unsigned)__ffs((int)e.y) - 1u, rest = e.y & (e.y - 1u);
+  if (rest) stack[sp - 1].y = rest; else sp--;
+  return load_ref<SMEM>(nodes, (int32_t)e.x, k ^ neg);
+}
+template <bool SMEM>
+__device__ __forceinline__ int32_t wide_visit(const float4* nodes, int32_t cur, f3 o, f3 inv, unsigned neg, float bound, uint2* stack, int& sp, unsigned& overflow) {
+  int32_t refs[8];
+  unsigned m = octant_permute(wide_test<SMEM>(nodes + RTB_WIDE_F4 * (size_t)cur, o, inv, neg, bound, refs), neg);
+  if (m == 0u) return wide_pop<SMEM>(nodes, neg, stack, sp);
+  const unsigned k = (unsigned)__ffs((int)m) - 1u;
+  m &= m - 1u;
+  if (m) {
+    if (sp < RTB_STACK_WIDE) { stack[sp] = make_uint2((unsigned)cur, m); sp++; }
+    else overflow++;
+  }
+  return select_ref(refs, k ^ neg);
+}
+
+// Per-thread closest-hit / any-hit query over the wide tree (k_tail, k_aux, k_debug; the wavefront uses the persistent form).
+template <bool ANY, bool ANALYTIC>
+__device__ __forceinline__ bool traverse_wide(const SceneView& s, const Ray& r, float t_limit, Hit& best, unsigned& overflow) {
+  best.t = RTB_INFINITY; best.u = 0.0f; best.v = 0.0f; best.tri = -1;
+  if (s.n_tris == 0) return false;
+  uint2 stack[RTB_STACK_WIDE];
+  int sp = 0;
+  int32_t cur = s.root;
+  const f3 inv = safe_inverse(r.d);
+  const unsigned neg = octant_of(r.d);
+  const float any_bound = nextafterf(t_limit, INFINITY);
+  while (cur != RTB_REF_DONE) {
+    if (cur >= 0) { cur = wide_visit<false>(s.nodes, cur, r.o, inv, neg, ANY ? any_bound : best.t, stack, sp, overflow); continue; }
+    const int32_t code = ~cur;
+    const int32_t first = code >> 3, count = (code & 7) + 1;
+    for (int32_t i = 0; i < count; i++) {
+      if (ANY) { if (test_triangle_any<ANALYTIC>(s, r, first + i, t_limit)) return true; }
+      else test_triangle_closest<ANALYTIC, true>(s, r, first + i, best);
+    }
+    cur = wide_pop<false>(s.nodes, neg, stack, sp);
+  }
+  return best.tri >= 0;
+}
+
 template <int BVH, bool ANY, bool ANALYTIC>
 __device__ __forceinline__ bool traverse(const SceneView& s, const Ray& r, float t_limit, Hit& best, unsigned& overflow) {
   if (BVH == RTB_BVH_REFERENCE) return traverse_reference<ANY, ANALYTIC>(s, r, t_limit, best, overflow);
+  if (BVH == RTB_BVH_WIDE) return traverse_wide<ANY, ANALYTIC>(s, r, t_limit, best, overflow);
   return traverse_lbvh<ANY, ANALYTIC>(s, r, t_limit, best, overflow);
 }
 

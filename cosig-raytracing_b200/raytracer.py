@@ -250,9 +250,7 @@ class RayTracer:
     def bvh(self):
         nn = C.c_int64()
         self._check(self._lib.rtb_get_bvh(self._ctx, None, 0, C.byref(nn), None, 0))
-        sizes = (C.c_int32 * 9)()
-        self._lib.rtb_abi_sizes(sizes, 9)
-        words = 8 if self.bvh_mode == abi.RTB_BVH_REFERENCE else sizes[8]
+        words = self._lib.rtb_get_bvh_node_words(self._ctx)
         nodes = np.zeros((nn.value, words), np.float32)
         st = self.stats()
         perm = np.zeros(st.n_triangles, np.int32)

@@ -536,7 +536,62 @@ struct Scene {
   std::vector<GpuNode> nodes;
   std::vector<rtb_material> mats;   // SetupMaterialBuffer, RayTracer.cs:455-499
   int max_leaf = 0;
+  // Checker-only (see LeafAccel below): big leaves get a private sub-tree; node index -> entry of leaf_accel, or -1
+  std::vector<int> accel_of_node;
+  std::vector<struct LeafAccel> leaf_accel;
 };
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CHECKER-ONLY ACCELERATOR — not part of the reference and not a change of its semantics.  BVHBuilder.cs makes a leaf of ANY
+// size when its partition fails (:142-145: eval_scene has a 578-triangle leaf, the C3 sphere grid two leaves of 98 310), and
+// TraverseBVH tests every triangle of a leaf in order (:251-256), which makes the restatement too slow to check full C3
+// frames.  A leaf with more than g_leaf_accel_min triangles therefore gets a private balanced sub-tree over ITS triangles,
+// and "test all of the leaf's triangles in order, keep the first of the closest" (the strict '<' of :179) is evaluated as
+// "closest t below the incoming bound; among equal t the smallest leaf position" — the same triangle, the same t/u/v bits,
+// because every (ray, triangle) test is the unchanged IntersectTriangle.  The sub-tree's boxes are padded far beyond any
+// rounding of its slab test (1e-3 + 1e-5 |coordinate|), so it never skips a triangle IntersectTriangle would accept; the
+// reference tree above the leaf, its node order and its culling are untouched.  Counters report the leaf's full triangle
+// count, as the linear scan would.  tests/test_host_cpu.py compares accelerated and plain renders bit for bit.
+// ---------------------------------------------------------------------------------------------------------------------
+static int g_leaf_accel_min = 32;  // 0 = never accelerate
+struct SubNode { V3 mn, mx; int left = -1, right = -1, first = 0, count = 0; };
+struct LeafAccel {
+  std::vector<SubNode> nodes;
+  std::vector<int> order;  // leaf-order triangle indices, grouped by sub-tree leaf
+};
+
+static int build_sub(LeafAccel& a, const std::vector<Tri>& tris, int first, int count) {
+  const int me = (int)a.nodes.size();
+  a.nodes.emplace_back();
+  V3 mn = v3(INFINITY, INFINITY, INFINITY), mx = v3(-INFINITY, -INFINITY, -INFINITY), cmn = mn, cmx = mx;
+  for (int k = 0; k < count; k++) {
+    const Tri& t = tris[a.order[first + k]];
+    const V3 p[3] = {t.v0, t.v1, t.v2};
+    for (auto& v : p) {
+      mn = v3(std::min(mn.x, v.x), std::min(mn.y, v.y), std::min(mn.z, v.z));
+      mx = v3(std::max(mx.x, v.x), std::max(mx.y, v.y), std::max(mx.z, v.z));
+    }
+    cmn = v3(std::min(cmn.x, t.center.x), std::min(cmn.y, t.center.y), std::min(cmn.z, t.center.z));
+    cmx = v3(std::max(cmx.x, t.center.x), std::max(cmx.y, t.center.y), std::max(cmx.z, t.center.z));
+  }
+  auto pad = [](float v) { return 1e-3f + 1e-5f * fabsf(v); };
+  a.nodes[me].mn = v3(mn.x - pad(mn.x), mn.y - pad(mn.y), mn.z - pad(mn.z));
+  a.nodes[me].mx = v3(mx.x + pad(mx.x), mx.y + pad(mx.y), mx.z + pad(mx.z));
+  a.nodes[me].first = first; a.nodes[me].count = count;
+  if (count <= 4) return me;
+  const V3 ext = cmx - cmn;
+  int axis = 0;
+  if (ext.y > ext.x) axis = 1;
+  if (ext.z > (axis == 0 ? ext.x : ext.y)) axis = 2;
+  auto key = [&](int i) { const V3& c = tris[i].center; return axis == 0 ? c.x : (axis == 1 ? c.y : c.z); };
+  const int half = count / 2;  // object median: always balanced, whatever the geometry
+  std::nth_element(a.order.begin() + first, a.order.begin() + first + half, a.order.begin() + first + count,
+                   [&](int x, int y) { const float kx = key(x), ky = key(y); return kx < ky || (kx == ky && x < y); });
+  const int l = build_sub(a, tris, first, half);
+  const int r = build_sub(a, tris, first + half, count - half);
+  a.nodes[me].left = l; a.nodes[me].right = r; a.nodes[me].count = 0;
+  return me;
+}
 
 static void build_scene(Scene& sc) {
   const rtb_scene_desc& d = sc.owned.d;
@@ -573,6 +628,19 @@ static void build_scene(Scene& sc) {
       sc.nodes[at] = g;
     }
   }
+  sc.accel_of_node.assign(sc.nodes.size(), -1);
+  sc.leaf_accel.clear();
+  if (g_leaf_accel_min > 0)
+    for (size_t ni = 0; ni < sc.nodes.size(); ni++) {
+      const GpuNode& n = sc.nodes[ni];
+      if (n.count <= g_leaf_accel_min) continue;
+      sc.accel_of_node[ni] = (int)sc.leaf_accel.size();
+      sc.leaf_accel.emplace_back();
+      LeafAccel& a = sc.leaf_accel.back();
+      a.order.resize((size_t)n.count);
+      for (int k = 0; k < n.count; k++) a.order[(size_t)k] = n.leftOrFirst + k;
+      build_sub(a, sc.tris, 0, n.count);
+    }
   sc.mats.clear();
   if (d.n_materials == 0) sc.mats.push_back(rtb_material{1, 1, 1, 0.1f, 0.7f, 0, 0, 1.0f});
   else sc.mats.assign(d.materials, d.materials + d.n_materials);
@@ -619,6 +687,32 @@ static inline void IntersectTriangle(const Ray& r, const Tri& tri, int index, Hi
   float t = dot(e2, qvec) * invDet;
   if (t > kEpsilon && t < best.t) { best.hit = true; best.t = t; best.tri = index; best.u = u; best.v = v; }
 }
+// Checker-only: the leaf loop of :251-256 over a big leaf, through its sub-tree (see LeafAccel).  Same result as
+// `for (i = first; i < first + count; i++) IntersectTriangle(r, tris[i], i, hit)`.
+static void IntersectLeafAccelerated(const Scene& sc, const LeafAccel& a, const Ray& r, Hit& hit) {
+  bool from_leaf = false;  // the current best came from this leaf (only then does the leaf position break ties)
+  int stack[128];
+  int sp = 0;
+  stack[sp++] = 0;
+  while (sp > 0) {
+    const SubNode& n = a.nodes[(size_t)stack[--sp]];
+    const float dst = IntersectAABB(r, n.mn, n.mx);
+    if (dst >= kInfinity || dst > hit.t) continue;  // '>' : a triangle tying with the best may sit exactly at the entry
+    if (n.count > 0) {
+      for (int k = 0; k < n.count; k++) {
+        const int idx = a.order[(size_t)(n.first + k)];
+        Hit h{false, kInfinity, -1, 0, 0};
+        IntersectTriangle(r, sc.tris[(size_t)idx], idx, h);
+        if (h.hit && (h.t < hit.t || (h.t == hit.t && from_leaf && idx < hit.tri))) { hit = h; from_leaf = true; }
+      }
+    } else {
+      if (sp + 2 > 128) abort();
+      stack[sp++] = n.right;
+      stack[sp++] = n.left;
+    }
+  }
+}
+
 // TraverseBVH :225-267
 static Hit TraverseBVH(const Scene& sc, const Ray& r, Counters& c) {
   Hit hit{false, kInfinity, -1, 0, 0};
@@ -633,7 +727,9 @@ static Hit TraverseBVH(const Scene& sc, const Ray& r, Counters& c) {
     float dst = IntersectAABB(r, n.mn, n.mx);
     if (dst >= hit.t) continue;
     if (n.count > 0) {
-      for (int i = 0; i < n.count; i++) { c.tris_tested++; IntersectTriangle(r, sc.tris[n.leftOrFirst + i], n.leftOrFirst + i, hit); }
+      const int accel = sc.accel_of_node[(size_t)ni];
+      if (accel >= 0) { c.tris_tested += n.count; IntersectLeafAccelerated(sc, sc.leaf_accel[(size_t)accel], r, hit); }
+      else for (int i = 0; i < n.count; i++) { c.tris_tested++; IntersectTriangle(r, sc.tris[n.leftOrFirst + i], n.leftOrFirst + i, hit); }
     } else {
       stack[sp++] = n.leftOrFirst + 1;
       stack[sp++] = n.leftOrFirst;
@@ -1110,6 +1206,11 @@ int32_t orc_brute_closest(const orc_scene* s, const float* o3, const float* d3, 
   return n;
 }
 
-int orc_version(void) { return 1; }
+// Checker-only leaf accelerator (LeafAccel): leaves with more than `min_count` triangles get a sub-tree; 0 = plain linear scan.
+// Applies to scenes built afterwards.  Returns the previous value.
+int orc_set_leaf_accel(int32_t min_count) { const int prev = g_leaf_accel_min; g_leaf_accel_min = min_count < 0 ? 0 : min_count; return prev; }
+int32_t orc_n_accelerated_leaves(const orc_scene* s) { return (int32_t)s->s.leaf_accel.size(); }
+
+int orc_version(void) { return 2; }
 
 }  // extern "C"

@@ -68,6 +68,8 @@ def lib():
         L.orc_brute_closest.argtypes = [VP, VP, VP, VP, VP, C.c_int32]
         L.orc_random_unit_vector.argtypes = [VP, VP]
         L.orc_sample_ray.argtypes = [VP, C.POINTER(_abi.RenderParams), C.c_int32, C.c_int32, C.c_int32, VP, VP]
+        L.orc_set_leaf_accel.argtypes = [C.c_int32]
+        L.orc_n_accelerated_leaves.argtypes = [VP]
         L.orc_gif_color_table.argtypes = [VP]
         L.orc_gif_convert_to_indexed.argtypes = [VP, C.c_int32, C.c_int32, VP]
         L.orc_gif_lzw.argtypes = [VP, C.c_int64, VP, C.c_int64]
@@ -134,6 +136,10 @@ class OracleScene:
     def max_leaf(self) -> int:
         return lib().orc_max_leaf(self.h)
 
+    @property
+    def n_accelerated_leaves(self) -> int:
+        return lib().orc_n_accelerated_leaves(self.h)
+
     def triangles(self):
         n = self.n_triangles
         vn = np.zeros((n, 18), np.float32)
@@ -193,6 +199,13 @@ class OracleScene:
         ids = np.zeros(cap, np.int32)
         n = lib().orc_brute_closest(self.h, o.ctypes.data, d.ctypes.data, C.byref(t), ids.ctypes.data, cap)
         return t.value, ids[:min(n, cap)].copy(), n
+
+
+def set_leaf_accel(min_count: int) -> int:
+    """Checker-only: leaves of the reference-shape BVH with more than `min_count` triangles are searched through a private
+    sub-tree instead of linearly (same results, see oracle.cpp: LeafAccel); 0 = never.  Applies to scenes built afterwards;
+    returns the previous setting."""
+    return lib().orc_set_leaf_accel(min_count)
 
 
 def random_unit_vector(seed) -> np.ndarray:
