@@ -139,7 +139,7 @@ SYMBOLS = {
     "rtb_abi_sizes": (None, [C.POINTER(C.c_int32), C.c_int32]),
     "rtb_resolve_frame": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(RenderParams), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "rtb_get_bvh": (C.c_int, [_VP, _VP, C.c_int64, C.POINTER(C.c_int64), _VP, C.c_int64]),
-    "rtb_get_bvh_node_words": (C.c_int32, [_VP]),
+    "rtb_get_bvh_node_words": (C.c_int, [_VP]),
     "rtb_frame_read": (C.c_int, [_VP, _VP, C.c_size_t]),
     "rtb_build_reference_bvh": (C.c_int, [_VP, C.c_int32, _VP, C.c_int64, C.POINTER(C.c_int64), _VP]),
     # GIF sweep (GifGenerator.cs)

@@ -962,7 +962,7 @@ int rtb_get_bvh(rtb_context* ctx, void* nodes, int64_t nodes_capacity_bytes, int
   return RTB_OK;
 }
 
-int32_t rtb_get_bvh_node_words(rtb_context* ctx) {
+int rtb_get_bvh_node_words(rtb_context* ctx) {
   if (!ctx || !ctx->has_scene) return 0;
   return ctx->devs[0].scene.node_floats;
 }

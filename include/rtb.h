@@ -202,7 +202,7 @@ int rtb_frame_read(rtb_context* ctx, uint8_t* rgba8, size_t bytes);
 int rtb_get_bvh(rtb_context* ctx, void* nodes, int64_t nodes_capacity_bytes, int64_t* n_nodes, int32_t* perm, int64_t perm_capacity);
 /* 32-bit words per node record of the uploaded scene as rtb_get_bvh returns them: 8 (reference mode), 24 (LBVH mode: 8-wide
  * quantised records) or 16 (LBVH mode with RTB_WIDE=0: binary two-box records); 0 without a scene. */
-int32_t rtb_get_bvh_node_words(rtb_context* ctx);
+int rtb_get_bvh_node_words(rtb_context* ctx);
 
 /* Host-only helpers (no CUDA device needed; used by the CPU test-suite and by hosts that want the uniforms).
  * rtb_resolve_frame: what RayTracer.cs:221-355 resolves from (scene, settings): out25 = cameraToObject (row-major 4x4),
