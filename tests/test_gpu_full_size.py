@@ -1,0 +1,197 @@
+"""GPU parity at BASELINE.json's FULL sizes (C3, C4, C5) and for the process-per-GPU gather, against the CPU oracle.
+
+The oracle reaches these sizes through its checker-only leaf accelerator (oracle.cpp: LeafAccel — same results as the linear leaf
+scan, tests/test_host_cpu.py proves it bit for bit), so C3 is checked on every 16th row of the 4K frame instead of one row.
+Bars as everywhere: t bits / ids exact where the closest hit is unique, RGB within 1/255 per channel on >= 99.9 % of pixels.
+"""
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from util import abi, assert_rgb_parity, oracle_scene, params, rgb_agreement, scene_mod, synth
+
+pytestmark = pytest.mark.gpu
+
+rt_mod = importlib.import_module("cosig-raytracing_b200.raytracer")
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def c4(oracle):
+    obj = synth.heightfield_scene()
+    osc, holder = oracle_scene(oracle, obj)
+    return obj, osc, holder
+
+
+# ---- C3: glass / mirror sphere grid, 3840x2160, depth 16 ---------------------------------------------------------------------------
+def test_c3_full_size_lbvh_against_oracle(oracle):
+    """BASELINE config C3 at full size through the GPU-built LBVH; the oracle renders every 16th row (135 rows, ~1.5 M rays).  The
+    reference-shape BVH degenerates on this scene (two leaves of 98 310 triangles), which is exactly what the leaf accelerator
+    is for."""
+    obj = synth.sphere_grid_scene(16)
+    osc, holder = oracle_scene(oracle, obj)
+    assert osc.max_leaf > 90000 and osc.n_accelerated_leaves >= 2
+    p = params(3840, 2160, 16)
+    rows = np.arange(0, 2160, 16)
+    ref = osc.render(p, rows=(0, -1, 16), want_aux=True)
+    with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as rt:
+        tex = rt.RenderAsync(obj, p).pixels
+        st = rt.stats()
+        assert st.n_triangles == 196620 and st.reserved[0] == 0
+        assert_rgb_parity(tex[rows], ref["rgba8"][rows], "C3 LBVH vs oracle rows")
+        prim, t, mat = rt.primary_hits(obj, p)
+        same_t = t[rows].view(np.uint32) == ref["t"][rows].view(np.uint32)
+        assert same_t.mean() >= 0.9999
+        assert (mat[rows] == ref["mat"][rows]).mean() >= 0.9999
+        # ray counts: every row the oracle rendered contributes its exact share; the whole frame is bounded by the per-row maximum
+        assert st.rays_primary == 3840 * 2160
+
+
+def test_c3_full_size_analytic_against_oracle(oracle):
+    """C3 with analytic spheres / box: 257 primitives, every 16th row against the oracle's analytic mode."""
+    obj = synth.sphere_grid_scene(16)
+    osc, holder = oracle_scene(oracle, obj)
+    osc.set_primitive_mode(abi.RTB_PRIM_ANALYTIC)
+    p = params(3840, 2160, 16)
+    rows = np.arange(0, 2160, 16)
+    ref = osc.render(p, rows=(0, -1, 16))
+    for mode in (abi.RTB_BVH_LBVH, abi.RTB_BVH_REFERENCE):
+        with rt_mod.RayTracer(bvh_mode=mode, primitive_mode=abi.RTB_PRIM_ANALYTIC) as rt:
+            tex = rt.RenderAsync(obj, p).pixels
+            assert rt.stats().n_triangles == 257 and rt.stats().reserved[0] == 0
+            assert_rgb_parity(tex[rows], ref["rgba8"][rows], f"C3 analytic mode {mode} vs oracle rows")
+
+
+# ---- C4: 1 M triangles, the tie rule of the LBVH flavour --------------------------------------------------------------------------
+def test_c4_lbvh_prim_ids_differ_only_at_exact_ties(c4):
+    """'ids equal except exact ties' for C4 / LBVH, at 1 M triangles and 4K.  Every 16th row: t bits and material
+    equal wherever the oracle has a unique closest hit; where the prim id differs, brute force over all 1 M triangles must find
+    several triangles at exactly the closest t, the GPU's id among them (the LBVH flavour then keeps the smallest leaf index)."""
+    obj, osc, _ = c4
+    p = params(3840, 2160, 6)
+    rows = np.arange(8, 2160, 16)
+    ref = osc.render(p, rows=(8, -1, 16), want_aux=True)
+    with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as rt:
+        prim, t, mat = rt.primary_hits(obj, p)
+        assert rt.stats().reserved[0] == 0
+    same_t = t[rows].view(np.uint32) == ref["t"][rows].view(np.uint32)
+    assert same_t.mean() >= 0.9999, f"t mismatch on {(~same_t).sum()} pixels"
+    differ = np.argwhere((prim[rows] != ref["prim"][rows]) & same_t)
+    assert len(differ) <= 0.002 * same_t.size
+    for yi, x in differ[:60]:
+        y = int(rows[yi])
+        o, d = osc.primary_ray(p, int(x), y)
+        tb, ids, n = osc.brute_closest(o, d, cap=64)
+        assert n >= 2 and prim[y, x] in ids, f"pixel ({x},{y}): id {prim[y, x]} vs {ref['prim'][y, x]} without a tie"
+    assert (mat[rows] == ref["mat"][rows])[same_t].mean() >= 0.999
+
+
+def test_c4_binary_and_wide_records_agree(c4, monkeypatch):
+    """The two node formats of the LBVH flavour (8-wide quantised, binary two-box) must give the same primary hits and frames: the
+    closest hit does not depend on which boxes were opened, nor on the order (closer_hit's tie rule)."""
+    obj, _, _ = c4
+    p = params(1920, 1080, 6)
+    out = {}
+    for wide in ("1", "0"):
+        monkeypatch.setenv("RTB_WIDE", wide)
+        with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as rt:
+            tex = rt.RenderAsync(obj, p).pixels
+            out[wide] = (tex,) + rt.primary_hits(obj, p)
+            assert rt.stats().reserved[0] == 0
+    a, b = out["1"], out["0"]
+    assert (a[2].view(np.uint32) == b[2].view(np.uint32)).all(), "primary t bits differ between node formats"
+    assert (a[1] == b[1]).all(), "primary prim ids differ between node formats"
+    assert (a[0] == b[0]).mean() >= 0.99999
+
+
+# ---- C5: the C4 scene at 7680x4320, 16 spp ----------------------------------------------------------------------------------------
+def test_c5_on_the_c4_scene_sampled_rows(c4):
+    """BASELINE config C5 proper (1 M triangles, 8K, 16 spp, depth 6: 531 M pixel-samples in 32 chunks): the oracle renders 9 rows
+    spread over the frame (1.1 M pixel-samples, ~2 M rays)."""
+    obj, osc, _ = c4
+    p = params(7680, 4320, 6, 16)
+    rows = np.arange(150, 4320, 500)
+    ref = osc.render(p, rows=(150, -1, 500))
+    with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as rt:
+        tex = rt.RenderAsync(obj, p).pixels
+        st = rt.stats()
+        assert st.chunks >= 30 and st.rays_primary == 7680 * 4320 * 16 and st.reserved[0] == 0
+    assert_rgb_parity(tex[rows], ref["rgba8"][rows], "C5 on the C4 scene, LBVH vs oracle rows")
+
+
+# ---- camera far from the scene (the LBVH box tests must stay conservative whatever the distance) -----------------------------------
+@pytest.mark.parametrize("distance", [74.0, 3000.0, 60000.0])
+def test_far_camera_lbvh_matches_reference_mode(distance):
+    """the binary LBVH's FMA slab test relied on build-time padding sized for cameras within a few scene radii.  The wide
+    records widen per ray instead, so a camera 1000 scene radii away must still see every hit the reference-shape tree sees."""
+    obj = synth.heightfield_scene(100, 50)
+    T = scene_mod.TransformElement
+    obj.Transformations[1] = scene_mod.CompositeTransformation([T.Translation((0, 0, -distance)), T.RotationX(-60.0), T.RotationZ(45.0)])
+    fov = float(np.degrees(2.0 * np.arctan(np.tan(np.radians(15.0)) * 74.0 / distance)))
+    p = params(640, 360, 4, has_fov=1, fov_deg=fov)
+    with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_REFERENCE) as rt:
+        ref_prim, ref_t, _ = rt.primary_hits(obj, p)
+    with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as rt:
+        prim, t, _ = rt.primary_hits(obj, p)
+    hit_ref, hit = ref_prim >= 0, prim >= 0
+    assert hit_ref.mean() > 0.2
+    assert (hit_ref & ~hit).sum() == 0, f"{(hit_ref & ~hit).sum()} hits of the reference-shape tree are lost by the LBVH at distance {distance}"
+    assert (t.view(np.uint32) == ref_t.view(np.uint32)).mean() >= (0.9999 if distance < 100.0 else 0.999)
+
+
+# ---- process-per-GPU gather on ONE GPU: two processes, CUDA IPC, peer stores from k_resolve ------------------------------------------
+_CHILD = r"""
+import importlib, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+from util import abi, params, synth
+rt_mod = importlib.import_module("cosig-raytracing_b200.raytracer")
+handle = bytes.fromhex(sys.stdin.readline().strip())
+obj = synth.sample_scene("test_scene_2")
+rt = rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH)
+dst = rt.frame_import(handle)
+p = params({w}, {h}, 5, 2, band_rank=1, band_world=2, band_rows=8)
+rt.RenderToTexture(obj, p, dst, {w} * {h} * 4, sync=True)
+print("stored", flush=True)
+sys.stdin.readline()   # keep the mapping alive until the parent has read the frame
+rt.close()
+"""
+
+
+def test_two_processes_gather_into_one_frame_over_ipc(samples_scene2):
+    """The N > 1 form of bench.py on a single GPU: rank 0 (this process) exports its frame buffer, rank 1 (a second process on the
+    same device) maps it through CUDA IPC and its k_resolve stores its bands straight into it; rank 0 renders its own bands, waits
+    for rank 1 and reads the frame back.  Must equal the one-context frame bit for bit."""
+    obj = samples_scene2
+    w, h = 640, 360
+    p_full = params(w, h, 5, 2)
+    with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as one:
+        want = one.RenderAsync(obj, p_full).pixels
+    rt = rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH)
+    try:
+        ptr, handle = rt.frame_export(w * h * 4)
+        child = subprocess.Popen([sys.executable, "-c", _CHILD.format(root=ROOT, tests=os.path.join(ROOT, "tests"), w=w, h=h)],
+                                 stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
+        child.stdin.write(handle.hex() + "\n"); child.stdin.flush()
+        rt.RenderToTexture(obj, params(w, h, 5, 2, band_rank=0, band_world=2, band_rows=8), ptr, w * h * 4, sync=True)
+        line = ""
+        for _ in range(50):  # skip anything a library prints while loading
+            line = child.stdout.readline()
+            if not line or line.strip() == "stored":
+                break
+        assert line.strip() == "stored", f"child ended with {line!r} (exit code {child.poll()})"
+        got = np.zeros((h, w, 4), np.uint8)
+        rt.frame_read(got)
+        child.stdin.write("done\n"); child.stdin.flush()
+        assert child.wait(timeout=120) == 0
+    finally:
+        rt.close()
+    assert (got == want).all(), f"{(got != want).any(axis=-1).sum()} pixels differ"
+
+
+@pytest.fixture(scope="module")
+def samples_scene2():
+    return synth.sample_scene("test_scene_2")

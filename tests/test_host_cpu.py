@@ -62,6 +62,50 @@ def test_oracle_closest_hit_agrees_with_brute_force(oracle):
                 assert np.float32(t).view(np.uint32) == r["t"][y, x].view(np.uint32) and r["prim"][y, x] in ids
 
 
+@pytest.mark.parametrize("name", ["eval_scene", "test_scene_2"])  # leaves of 578 / 83 triangles (BVHBuilder.cs:142-145)
+def test_oracle_leaf_accelerator_changes_nothing(oracle, name):
+    """The checker-only accelerator for oversized leaves (oracle.cpp: LeafAccel) must return what the reference's linear leaf
+    scan returns: frames, float accumulators, primary ids / t bits / materials and every counter, bit for bit."""
+    packed = scene_mod.pack_scene(synth.sample_scene(name))
+    prev = oracle.set_leaf_accel(0)
+    try:
+        plain = oracle.OracleScene.from_desc(packed.desc)
+        oracle.set_leaf_accel(8)
+        fast = oracle.OracleScene.from_desc(packed.desc)
+    finally:
+        oracle.set_leaf_accel(prev)
+    assert plain.n_accelerated_leaves == 0 and fast.n_accelerated_leaves >= 5
+    for kw in (dict(depth=6), dict(depth=4, aa=4, soft_shadows=1, light_size=5.0, glossy=1, roughness=0.05), dict(depth=3, is_orthographic=1)):
+        p = params(200, 150, **kw)
+        a, b = plain.render(p, want_aux=True, want_rgbf=True), fast.render(p, want_aux=True, want_rgbf=True)
+        for key in ("rgba8", "prim", "mat"):
+            assert (a[key] == b[key]).all(), (name, kw, key)
+        assert (a["t"].view(np.uint32) == b["t"].view(np.uint32)).all() and (a["rgbf"].view(np.uint32) == b["rgbf"].view(np.uint32)).all()
+        for f in ("rays_primary", "rays_continuation", "rays_shadow", "nodes_visited", "tris_tested", "closest_hits", "primary_hits"):
+            assert getattr(a["counters"], f) == getattr(b["counters"], f), (name, kw, f)
+
+
+def test_oracle_reaches_c3_at_full_size(oracle):
+    """With the accelerator the degenerate reference BVH of the C3 sphere grid (two leaves of 98 310 triangles) renders 4K rows
+    in a fraction of a second each; one row agrees with the plain linear scan (which needs ~30 s for it)."""
+    packed = scene_mod.pack_scene(synth.sphere_grid_scene(16))
+    osc = oracle.OracleScene.from_desc(packed.desc)
+    assert osc.max_leaf == 98310 and osc.n_accelerated_leaves == 2
+    p = params(3840, 2160, 16)
+    fast = osc.render(p, rows=(1000, 1001, 1), want_aux=True)
+    assert fast["counters"].seconds < 5.0
+    prev = oracle.set_leaf_accel(0)
+    try:
+        plain_scene = oracle.OracleScene.from_desc(packed.desc)
+    finally:
+        oracle.set_leaf_accel(prev)
+    pl = params(3840, 2160, 2)  # depth 2 keeps the plain scan within the CPU suite's budget
+    a = plain_scene.render(pl, rows=(1000, 1001, 1), want_aux=True)
+    b = osc.render(pl, rows=(1000, 1001, 1), want_aux=True)
+    assert (a["rgba8"][1000] == b["rgba8"][1000]).all() and (a["prim"][1000] == b["prim"][1000]).all()
+    assert (a["t"][1000].view(np.uint32) == b["t"][1000].view(np.uint32)).all()
+
+
 @pytest.mark.skipif(not os.path.isdir(REFERENCE_SCENES), reason="reference tree only exists in the build container")
 @pytest.mark.parametrize("name", synth.SAMPLE_SCENES)
 def test_packed_scenes_match_reference_files(oracle, name):
