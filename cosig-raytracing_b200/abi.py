@@ -21,6 +21,7 @@ RTB_XF_T, RTB_XF_RX, RTB_XF_RY, RTB_XF_RZ, RTB_XF_S = 0, 1, 2, 3, 4
 RTB_PRIM_TESSELLATED, RTB_PRIM_ANALYTIC = 0, 1
 RTB_BVH_REFERENCE, RTB_BVH_LBVH = 0, 1
 RTB_OUT_FRAME, RTB_OUT_COMPACT = 0, 1
+RTB_EXT_OPAQUE_FD, RTB_EXT_OPAQUE_WIN32, RTB_EXT_D3D12_HEAP, RTB_EXT_D3D12_RESOURCE = 1, 2, 4, 5
 
 
 class XformElem(C.Structure):
@@ -140,6 +141,12 @@ SYMBOLS = {
     "rtb_resolve_frame": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(RenderParams), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "rtb_get_bvh": (C.c_int, [_VP, _VP, C.c_int64, C.POINTER(C.c_int64), _VP, C.c_int64]),
     "rtb_get_bvh_node_words": (C.c_int, [_VP]),
+    "rtb_group_create": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_size_t, C.c_int32, _VP]),
+    "rtb_group_render_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, C.c_size_t, C.POINTER(C.c_int32)]),
+    "rtb_group_render_end": (C.c_int, [_VP, C.c_int32]),
+    "rtb_group_destroy": (C.c_int, [_VP]),
+    "rtb_external_import": (C.c_int, [_VP, C.c_int32, _VP, C.c_size_t, C.c_int32, C.POINTER(_VP)]),
+    "rtb_external_release": (C.c_int, [_VP, _VP]),
     "rtb_frame_read": (C.c_int, [_VP, _VP, C.c_size_t]),
     "rtb_build_reference_bvh": (C.c_int, [_VP, C.c_int32, _VP, C.c_int64, C.POINTER(C.c_int64), _VP]),
     # GIF sweep (GifGenerator.cs)

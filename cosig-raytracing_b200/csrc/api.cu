@@ -104,11 +104,28 @@ struct rtb_context {
   int n_lanes = 4;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues
   uint64_t frame_id = 0;
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
-  int wide = 1;               // RTB_WIDE: RTB_BVH_LBVH scenes are stored as 8-wide quantised records (0: binary two-box records)
+  int wide = 0;               // RTB_WIDE=1: RTB_BVH_LBVH scenes are stored as 8-wide quantised records instead of binary two-box records (measured slower: profiles/r2_sweep_wide.log)
   int packet_closest = -1;     // RTB_PACKET_CLOSEST: closest-hit rays of depth <= this go through the packet kernels (-1: none, k_raygen + per-lane)
   int packet_shadow = -1;     // RTB_PACKET_SHADOW: shadow rays emitted at depth <= this go through k_packet (-1: none)
   int32_t tail_max = 65536;   // queues smaller than this finish in k_tail (RTB_TAIL_MAX; 0 = pure wavefront); sweep: profiles/r1e_sweep_tail_max.log
   std::vector<void*> ipc_opened;
+  // Process-per-GPU frame ring (rtb_group_*): n_buf frame buffers + sequence flags in rank 0's memory, mapped by every rank.
+  struct Group {
+    bool active = false, owner = false;
+    int rank = 0, world = 1, n_buf = 0;
+    size_t frame_bytes = 0, stride = 0;
+    uint8_t* base = nullptr;      // rank 0: own allocation; other ranks: CUDA-IPC mapping of it
+    uint32_t* flags = nullptr;    // behind the frames: stored[world][n_buf], then read_done[n_buf]
+    uint32_t* error = nullptr;    // own device word, set by a wait that timed out
+    uint64_t seq = 0;             // frames begun
+    cudaStream_t gate = nullptr;  // the "buffer is free again" waits run here
+    cudaEvent_t gate_done = nullptr;
+    static constexpr int kTickets = 16;
+    cudaEvent_t ticket[kTickets] = {};
+    unsigned long long timeout_ns = 10000000000ull;
+  } group;
+  struct External { cudaExternalMemory_t mem; void* ptr; size_t bytes; };
+  std::vector<External> externals;  // rtb_external_import: graphics-API allocations mapped into device 0's address space
   static constexpr int kTickets = 16;  // frames in flight through rtb_render_begin
   cudaEvent_t ticket_event[kTickets] = {};   // frame complete in its host buffer
   cudaEvent_t frame_ready[kTickets] = {};    // frame complete in its device buffer (the copy stream waits for it)
@@ -571,6 +588,21 @@ int collect_stats(rtb_context* ctx) {
 
 }  // namespace
 
+namespace {
+void group_release(rtb_context* ctx) {
+  rtb_context::Group& g = ctx->group;
+  if (!g.active) return;
+  cudaSetDevice(ctx->devs[0].device);
+  for (auto& d : ctx->devs) device_sync(d);
+  if (g.gate) { cudaStreamSynchronize(g.gate); cudaStreamDestroy(g.gate); }
+  if (g.gate_done) cudaEventDestroy(g.gate_done);
+  for (auto& e : g.ticket) if (e) cudaEventDestroy(e);
+  if (g.base) { if (g.owner) cudaFree(g.base); else cudaIpcCloseMemHandle(g.base); }
+  if (g.error) cudaFree(g.error);
+  g = rtb_context::Group();
+}
+}  // namespace
+
 // =====================================================================================================================
 // C ABI
 // =====================================================================================================================
@@ -667,9 +699,16 @@ void rtb_destroy(rtb_context* ctx) {
     if (e) { cudaSetDevice(ctx->devs[0].device); cudaEventDestroy(e); }
   for (auto& e : ctx->frame_ready)
     if (e) { cudaSetDevice(ctx->devs[0].device); cudaEventDestroy(e); }
+  group_release(ctx);
+  for (auto& d : ctx->devs) device_sync(d);
   for (void* p : ctx->ipc_opened) {
     cudaSetDevice(ctx->devs[0].device);
     cudaIpcCloseMemHandle(p);
+  }
+  for (auto& x : ctx->externals) {
+    cudaSetDevice(ctx->devs[0].device);
+    cudaFree(x.ptr);
+    cudaDestroyExternalMemory(x.mem);
   }
   for (auto& d : ctx->devs) {
     device_sync(d);
@@ -1038,6 +1077,173 @@ int rtb_frame_import(rtb_context* ctx, const uint8_t handle64[64], void** dev_pt
   ctx->ipc_opened.push_back(p);
   *dev_ptr = p;
   return RTB_OK;
+}
+
+// ---- process-per-GPU frame ring ------------------------------------------------------------------------------------------------
+// One frame split over the ranks of a job by row bands, gathered on rank 0 by the resolve kernels' peer stores, read
+// back by rank 0, pipelined over n_buffers frames — all inside the library: every rank only enqueues (group.cu has the
+// hand-shake), so frame k+1 .. k+n_buffers-1 render on all ranks while rank 0 copies frame k out.
+
+int rtb_group_create(rtb_context* ctx, int32_t rank, int32_t world, size_t frame_bytes, int32_t n_buffers, uint8_t handle64[64]) {
+  if (!ctx || !handle64) return fail(ctx, RTB_E_ARG, "null argument");
+  if (world < 1 || world > 32 || rank < 0 || rank >= world || n_buffers < 1 || n_buffers > 8 || frame_bytes == 0) return fail(ctx, RTB_E_ARG, "bad group shape");
+  if (ctx->devs.size() != 1) return fail(ctx, RTB_E_ARG, "a group member is a single-device context");
+  group_release(ctx);
+  rtb_context::Group& g = ctx->group;
+  CK(ctx, cudaSetDevice(ctx->devs[0].device));
+  g.rank = rank; g.world = world; g.n_buf = n_buffers; g.frame_bytes = frame_bytes;
+  g.stride = (frame_bytes + 255) & ~(size_t)255;
+  const size_t flag_bytes = 4096;
+  const size_t total = g.stride * (size_t)n_buffers + flag_bytes;
+  if (rank == 0) {
+    CK(ctx, cudaMalloc(&g.base, total));
+    g.owner = true;
+    CK(ctx, cudaMemset(g.base + g.stride * (size_t)n_buffers, 0, flag_bytes));
+    cudaIpcMemHandle_t h;
+    CK(ctx, cudaIpcGetMemHandle(&h, g.base));
+    std::memcpy(handle64, &h, 64);
+  } else {
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CK(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    g.base = (uint8_t*)p;
+  }
+  g.flags = (uint32_t*)(g.base + g.stride * (size_t)n_buffers);
+  CK(ctx, cudaMalloc(&g.error, sizeof(uint32_t)));
+  CK(ctx, cudaMemset(g.error, 0, sizeof(uint32_t)));
+  CK(ctx, cudaStreamCreateWithFlags(&g.gate, cudaStreamNonBlocking));
+  CK(ctx, cudaEventCreateWithFlags(&g.gate_done, cudaEventDisableTiming));
+  if (const char* env = std::getenv("RTB_GROUP_TIMEOUT_MS")) g.timeout_ns = (unsigned long long)std::max(1LL, std::atoll(env)) * 1000000ull;
+  g.seq = 0;
+  g.active = true;
+  return RTB_OK;
+}
+
+int rtb_group_destroy(rtb_context* ctx) {
+  if (!ctx) return RTB_E_ARG;
+  group_release(ctx);
+  return RTB_OK;
+}
+
+int rtb_group_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* ticket) {
+  if (!ctx || !p || !ticket) return fail(ctx, RTB_E_ARG, "null argument");
+  rtb_context::Group& g = ctx->group;
+  if (!g.active) return fail(ctx, RTB_E_ARG, "no group (rtb_group_create)");
+  if (!ctx->has_scene) return fail(ctx, RTB_E_NOSCENE, "no scene uploaded (rtb_upload_scene)");
+  rtb_render_params pp = *p;
+  pp.band_rank = g.rank; pp.band_world = g.world; pp.out_layout = RTB_OUT_FRAME;
+  if (pp.band_rows <= 0) pp.band_rows = 8;
+  FrameParams f;
+  std::string why;
+  if (!resolve_frame(ctx->host.d, pp, f, why)) return fail(ctx, RTB_E_ARG, why);
+  const size_t need = (size_t)f.width * f.height * 4;
+  if (need > g.frame_bytes) return fail(ctx, RTB_E_SIZE, "frame larger than the group's buffers");
+  if (g.rank == 0 && (!rgba8 || bytes < need)) return fail(ctx, RTB_E_SIZE, "rgba8 buffer too small for the resolved resolution");
+  DeviceState& d = ctx->devs[0];
+  CK(ctx, cudaSetDevice(d.device));
+  const uint64_t k = g.seq;
+  const int j = (int)(k % (uint64_t)g.n_buf), slot = (int)(k % rtb_context::Group::kTickets);
+  uint32_t* stored = g.flags;                                   // [world][n_buf]
+  uint32_t* read_done = g.flags + (size_t)g.world * g.n_buf;    // [n_buf]
+  if (!g.ticket[slot]) CK(ctx, cudaEventCreateWithFlags(&g.ticket[slot], cudaEventDisableTiming));
+  else CK(ctx, cudaEventSynchronize(g.ticket[slot]));  // the ring of tickets is full: wait for the frame begun kTickets calls ago
+  // the buffer still holds frame k - n_buf until rank 0 has copied it out
+  if (k >= (uint64_t)g.n_buf) {
+    launch_group_wait(read_done + j, 1, 1, (uint32_t)(k - (uint64_t)g.n_buf + 1), g.error, g.timeout_ns, g.gate);
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaEventRecord(g.gate_done, g.gate));
+    for (int l = 0; l < ctx->n_lanes; l++) CK(ctx, cudaStreamWaitEvent(d.lane[l].stream, g.gate_done, 0));
+  }
+  uint8_t* dst = g.base + (size_t)j * g.stride;
+  FrameParams f2;
+  const int rc = render_frame(ctx, &pp, dst, g.stride, /*to_internal_frame=*/false, /*sync=*/false, f2);
+  if (rc != RTB_OK) return rc;
+  LaneState& last = d.lane[d.last_lane];
+  for (int l = 0; l < DeviceState::kMaxLanes; l++)  // multi-chunk frame: every lane that carried one of its chunks
+    if (l != d.last_lane && d.lane[l].stream && d.lane[l].frame_id == ctx->frame_id) CK(ctx, cudaStreamWaitEvent(last.stream, d.lane[l].ev_done, 0));
+  launch_group_post(stored + (size_t)g.rank * g.n_buf + j, (uint32_t)(k + 1), last.stream);
+  CK(ctx, cudaGetLastError());
+  CK(ctx, cudaEventRecord(last.ev_done, last.stream));
+  last.used = true;
+  if (g.rank == 0) {
+    launch_group_wait(stored + j, g.world, g.n_buf, (uint32_t)(k + 1), g.error, g.timeout_ns, d.copy_stream);
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpyAsync(rgba8, dst, need, cudaMemcpyDeviceToHost, d.copy_stream));  // ReadPixels, RayTracer.cs:371-375
+    launch_group_post(read_done + j, (uint32_t)(k + 1), d.copy_stream);
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaEventRecord(g.ticket[slot], d.copy_stream));
+    d.copy_pending = true;
+    ctx->stats.d2h_bytes = (int64_t)need;
+  } else {
+    CK(ctx, cudaEventRecord(g.ticket[slot], last.stream));
+  }
+  ctx->stats.kernel_launches += g.rank == 0 ? 3 : 1;
+  *ticket = (int32_t)(k & 0x7fffffff);
+  g.seq++;
+  return RTB_OK;
+}
+
+int rtb_group_render_end(rtb_context* ctx, int32_t ticket) {
+  if (!ctx) return RTB_E_ARG;
+  rtb_context::Group& g = ctx->group;
+  if (!g.active) return fail(ctx, RTB_E_ARG, "no group (rtb_group_create)");
+  if (ticket < 0 || (uint64_t)ticket >= g.seq) return fail(ctx, RTB_E_ARG, "unknown ticket");
+  CK(ctx, cudaSetDevice(ctx->devs[0].device));
+  if (g.seq - (uint64_t)ticket <= (uint64_t)rtb_context::Group::kTickets) CK(ctx, cudaEventSynchronize(g.ticket[(uint64_t)ticket % rtb_context::Group::kTickets]));
+  uint32_t err = 0;
+  CK(ctx, cudaMemcpy(&err, g.error, sizeof err, cudaMemcpyDeviceToHost));
+  if (err) return fail(ctx, RTB_E_CUDA, "a rank of the group did not arrive in time (RTB_GROUP_TIMEOUT_MS)");
+  CK(ctx, cudaGetLastError());
+  return RTB_OK;
+}
+
+// Zero-copy realtime path (RayTracer.RenderToTexture, RayTracer.cs:82-202, hands Unity a GPU texture it never reads back,
+// SceneBuilder.cs:836-852): map a graphics-API allocation and let rtb_render_device's resolve kernel store into it.
+int rtb_external_import(rtb_context* ctx, int32_t handle_type, void* handle, size_t bytes, int32_t dedicated, void** dev_ptr) {
+  if (!ctx || !dev_ptr || bytes == 0) return fail(ctx, RTB_E_ARG, "null argument");
+  *dev_ptr = nullptr;
+  cudaExternalMemoryHandleDesc hd;
+  std::memset(&hd, 0, sizeof hd);
+  switch (handle_type) {
+    case RTB_EXT_OPAQUE_FD: hd.type = cudaExternalMemoryHandleTypeOpaqueFd; hd.handle.fd = (int)(intptr_t)handle; break;
+    case RTB_EXT_OPAQUE_WIN32: hd.type = cudaExternalMemoryHandleTypeOpaqueWin32; hd.handle.win32.handle = handle; break;
+    case RTB_EXT_D3D12_HEAP: hd.type = cudaExternalMemoryHandleTypeD3D12Heap; hd.handle.win32.handle = handle; break;
+    case RTB_EXT_D3D12_RESOURCE: hd.type = cudaExternalMemoryHandleTypeD3D12Resource; hd.handle.win32.handle = handle; break;
+    default: return fail(ctx, RTB_E_ARG, "unknown external handle type");
+  }
+  hd.size = bytes;
+  hd.flags = dedicated ? cudaExternalMemoryDedicated : 0;
+  CK(ctx, cudaSetDevice(ctx->devs[0].device));
+  cudaExternalMemory_t mem = nullptr;
+  CK(ctx, cudaImportExternalMemory(&mem, &hd));
+  cudaExternalMemoryBufferDesc bd;
+  std::memset(&bd, 0, sizeof bd);
+  bd.offset = 0;
+  bd.size = bytes;
+  void* p = nullptr;
+  cudaError_t e = cudaExternalMemoryGetMappedBuffer(&p, mem, &bd);
+  if (e != cudaSuccess) {
+    cudaDestroyExternalMemory(mem);
+    return fail(ctx, RTB_E_CUDA, std::string("cudaExternalMemoryGetMappedBuffer failed: ") + cudaGetErrorString(e));
+  }
+  ctx->externals.push_back({mem, p, bytes});
+  *dev_ptr = p;
+  return RTB_OK;
+}
+
+int rtb_external_release(rtb_context* ctx, void* dev_ptr) {
+  if (!ctx || !dev_ptr) return fail(ctx, RTB_E_ARG, "null argument");
+  for (size_t i = 0; i < ctx->externals.size(); i++)
+    if (ctx->externals[i].ptr == dev_ptr) {
+      for (auto& d : ctx->devs) device_sync(d);  // no kernel may still be storing into the mapping
+      CK(ctx, cudaSetDevice(ctx->devs[0].device));
+      cudaFree(ctx->externals[i].ptr);
+      cudaDestroyExternalMemory(ctx->externals[i].mem);
+      ctx->externals.erase(ctx->externals.begin() + (long)i);
+      return RTB_OK;
+    }
+  return fail(ctx, RTB_E_ARG, "not a pointer returned by rtb_external_import");
 }
 
 // Copies device 0's internal frame (the buffer rtb_frame_export shares) to the host: the readback step after a

@@ -57,6 +57,11 @@ void launch_tail(int bvh, const FrameParams& f, const SceneView& s, const QueueV
 void launch_resolve(const FrameParams& f, const QueueView& q, const ChunkView& c, void* dst, int grid, cudaStream_t st);
 void launch_debug(int bvh, const FrameParams& f, const SceneView& s, const ChunkView& c, void* dst, int grid, cudaStream_t st);
 void launch_aux(int bvh, const FrameParams& f, const SceneView& s, int32_t* prim, float* t, int32_t* mat, int grid, cudaStream_t st);
+// ---- group.cu (hand-shake of the process-per-GPU frame ring) ---------------------------------------------------------------
+void launch_group_post(uint32_t* flag, uint32_t value, cudaStream_t st);
+// waits until flags[i * stride] >= target for i < n (n <= 32); sets *error after timeout_ns
+void launch_group_wait(const uint32_t* flags, int n, int stride, uint32_t target, uint32_t* error, unsigned long long timeout_ns, cudaStream_t st);
+
 // Resident blocks per SM of the persistent traversal kernel (occupancy query), by variant.
 int traverse_blocks_per_sm(int bvh);
 

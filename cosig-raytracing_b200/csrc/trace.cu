@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
   bool saw_exhausted = false;
   if (lane == 0 && total > 0) atomicMax(&tl[0], ~global_ns());
 #endif
-  f3 ood = mk3(0.0f, 0.0f, 0.0f);
+  SlabRay sr;
+  sr.inv = sr.ood_mn = sr.ood_mx = mk3(0.0f, 0.0f, 0.0f);
   Lane L;
   L.item = -1; L.shadow = false; L.done = false; L.t = 0.0f; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
   L.o = L.d = L.inv = mk3(0.0f, 0.0f, 0.0f);
@@ -328,8 +329,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
         sp = 0;
         cur = s.n_tris > 0 ? s.root : RTB_REF_DONE;
         L.done = cur == RTB_REF_DONE;
-        L.inv = safe_inverse(L.d);
-        ood = L.o * L.inv;
+        sr = make_slab_ray(L.o, L.d);
       }
       if (__ballot_sync(kFull, L.item >= 0 && !L.done) == 0) {
         if (__ballot_sync(kFull, L.item >= 0) == 0 && pool.exhausted) break;
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
       ray_steps++;
 #endif
       // closest: a box is skipped when entry >= best t (compute:246); shadow rays carry nextafter(distToLight) as bound
-      const int32_t next = lbvh_visit<SMEM>(nodes, cur, L.inv, ood, L.t, stack, sp, overflow);
+      const int32_t next = lbvh_visit<SMEM>(nodes, cur, sr, L.t, stack, sp, overflow);
       if (next != RTB_REF_MISS) cur = next;
       else {
         cur = RTB_REF_DONE;
@@ -584,8 +584,7 @@ __device__ __forceinline__ void packet_traverse_lbvh(const SceneView& s, Lane& L
                                                      unsigned& n_tris, unsigned& w_nodes, unsigned& w_tris) {
   const int lane = threadIdx.x & 31;
   if (s.n_tris == 0) return;
-  const f3 inv = safe_inverse(L.d);
-  const f3 ood = L.o * inv;
+  const SlabRay sr = make_slab_ray(L.o, L.d);
   const float t_saved = L.t;
   if (!valid) L.t = -1.0f;  // every box test fails (exit <= bound < 0 <= entry)
   int sp = 0;
@@ -597,8 +596,8 @@ __device__ __forceinline__ void packet_traverse_lbvh(const SceneView& s, Lane& L
       ld8<false>(&s.nodes[4 * (size_t)cur], n0, n1);
       ld8<false>(&s.nodes[4 * (size_t)cur + 2], n2, n3);
       float dl, dr;
-      const bool hl = act && slab_hit_fma(inv, ood, mk3(n0), mk3(n1), L.t, dl);
-      const bool hr = act && slab_hit_fma(inv, ood, mk3(n2), mk3(n3), L.t, dr);
+      const bool hl = act && slab_hit(sr, mk3(n0), mk3(n1), L.t, dl);
+      const bool hr = act && slab_hit(sr, mk3(n2), mk3(n3), L.t, dr);
       const unsigned ml = __ballot_sync(kFull, hl), mr = __ballot_sync(kFull, hr);
       n_nodes += act ? 1u : 0u;
       w_nodes += lane == 0 ? 1u : 0u;
@@ -846,9 +845,9 @@ __global__ void __launch_bounds__(kStreamBlock) k_raygen(const FrameParams f, co
     if (survives && have_box) {
       if (BVH == RTB_BVH_REFERENCE) survives = !(slab_entry(ray, rmn, rmx) >= RTB_INFINITY);
       else {
-        const f3 inv = safe_inverse(ray.d);
+        const SlabRay sr = make_slab_ray(ray.o, ray.d);
         float entry;
-        survives = slab_hit_fma(inv, ray.o * inv, rmn, rmx, RTB_INFINITY, entry);
+        survives = slab_hit(sr, rmn, rmx, RTB_INFINITY, entry);
         if (BVH == RTB_BVH_WIDE && !survives) {  // the FMA form rounds by ~1e-7 |origin / d|: decide near misses with the exact form over the slack box
           Ray exact = ray;
           survives = !(slab_entry(exact, rmn, rmx) >= RTB_INFINITY);

@@ -141,6 +141,33 @@ __device__ __forceinline__ bool slab_hit_fma(f3 inv, f3 ood, f3 mn, f3 mx, float
 __device__ __forceinline__ float safe_rcp(float d) { return fabsf(d) > 1e-18f ? 1.0f / d : copysignf(1e18f, d); }
 __device__ __forceinline__ f3 safe_inverse(f3 d) { return mk3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)); }
 
+// The ray constants of the LBVH box test.  fma(bound, 1/d, -o/d) differs from the reference's (bound - o) * (1/d) by the rounding
+// of o/d — about 2^-24 |o| in space — and the triangle test itself places hits with an uncertainty of that order (o - v0 is
+// rounded), so whether a hit survives the box tests must not depend on it.  The build pads boxes for the scene's own scale
+// (lbvh.cu: k_emit); what grows with the CAMERA's distance is handled here, per ray and at no cost per node: the min planes and
+// the max planes get their own o/d, shifted by e = 2^-21 max|o| |1/d| towards "enters earlier, leaves later" (for d > 0 the min
+// plane is the near one; for d < 0 the max plane).
+struct SlabRay { f3 inv, ood_mn, ood_mx; };
+__device__ __forceinline__ SlabRay make_slab_ray(f3 o, f3 d) {
+  SlabRay r;
+  r.inv = safe_inverse(d);
+  const f3 ood = o * r.inv;
+  const float reach = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) * 4.76837158203125e-7f;  // 2^-21 max|o|
+  const f3 e = mk3(reach * r.inv.x, reach * r.inv.y, reach * r.inv.z);  // signed like 1/d
+  r.ood_mn = ood + e;
+  r.ood_mx = ood - e;
+  return r;
+}
+__device__ __forceinline__ bool slab_hit(const SlabRay& r, f3 mn, f3 mx, float bound, float& entry) {
+  const float t0x = __fmaf_rn(mn.x, r.inv.x, -r.ood_mn.x), t1x = __fmaf_rn(mx.x, r.inv.x, -r.ood_mx.x);
+  const float t0y = __fmaf_rn(mn.y, r.inv.y, -r.ood_mn.y), t1y = __fmaf_rn(mx.y, r.inv.y, -r.ood_mx.y);
+  const float t0z = __fmaf_rn(mn.z, r.inv.z, -r.ood_mn.z), t1z = __fmaf_rn(mx.z, r.inv.z, -r.ood_mx.z);
+  entry = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+  const float exit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), bound));
+  return entry <= exit;
+}
+
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Analytic primitives (RTB_PRIM_ANALYTIC): the reference's SphereInstance / BoxInstance, Assets/Services/BVH/HittableObjects.cs
 // (never instantiated there; semantics taken from it): the ray goes to object space with its direction re-normalised
@@ -326,17 +353,17 @@ __device__ __forceinline__ void ld8(const float4* p, float4& a, float4& b) {
 // ---------------------------------------------------------------------------------------------------------------------
 #if RTB_LBVH_WIDTH == 4
 template <bool SMEM>
-__device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, f3 inv, f3 ood, float bound, float2* stack,
+__device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, const SlabRay& sr, float bound, float2* stack,
                                               int& sp, unsigned& overflow) {
   const float4* rec = nodes + 8 * (size_t)cur;
   const float4 mnx = ld4<SMEM>(rec), mny = ld4<SMEM>(rec + 1), mnz = ld4<SMEM>(rec + 2);
   const float4 mxx = ld4<SMEM>(rec + 3), mxy = ld4<SMEM>(rec + 4), mxz = ld4<SMEM>(rec + 5);
   const float4 rf = ld4<SMEM>(rec + 6);
   float e0, e1, e2, e3;
-  const bool h0 = slab_hit_fma(inv, ood, mk3(mnx.x, mny.x, mnz.x), mk3(mxx.x, mxy.x, mxz.x), bound, e0);
-  const bool h1 = slab_hit_fma(inv, ood, mk3(mnx.y, mny.y, mnz.y), mk3(mxx.y, mxy.y, mxz.y), bound, e1);
-  const bool h2 = slab_hit_fma(inv, ood, mk3(mnx.z, mny.z, mnz.z), mk3(mxx.z, mxy.z, mxz.z), bound, e2);
-  const bool h3 = slab_hit_fma(inv, ood, mk3(mnx.w, mny.w, mnz.w), mk3(mxx.w, mxy.w, mxz.w), bound, e3);
+  const bool h0 = slab_hit(sr, mk3(mnx.x, mny.x, mnz.x), mk3(mxx.x, mxy.x, mxz.x), bound, e0);
+  const bool h1 = slab_hit(sr, mk3(mnx.y, mny.y, mnz.y), mk3(mxx.y, mxy.y, mxz.y), bound, e1);
+  const bool h2 = slab_hit(sr, mk3(mnx.z, mny.z, mnz.z), mk3(mxx.z, mxy.z, mxz.z), bound, e2);
+  const bool h3 = slab_hit(sr, mk3(mnx.w, mny.w, mnz.w), mk3(mxx.w, mxy.w, mxz.w), bound, e3);
   int32_t r0 = __float_as_int(rf.x), r1 = __float_as_int(rf.y), r2 = __float_as_int(rf.z), r3 = __float_as_int(rf.w);
   // misses (and unused slots) sort to the end
   if (!h0) e0 = INFINITY;
@@ -356,14 +383,14 @@ __device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, 
 }
 #else
 template <bool SMEM>
-__device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, f3 inv, f3 ood, float bound, float2* stack,
+__device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, const SlabRay& sr, float bound, float2* stack,
                                               int& sp, unsigned& overflow) {
   float4 n0, n1, n2, n3;
   ld8<SMEM>(&nodes[4 * cur], n0, n1);
   ld8<SMEM>(&nodes[4 * cur + 2], n2, n3);
   float dl, dr;
-  const bool hl = slab_hit_fma(inv, ood, mk3(n0), mk3(n1), bound, dl);
-  const bool hr = slab_hit_fma(inv, ood, mk3(n2), mk3(n3), bound, dr);
+  const bool hl = slab_hit(sr, mk3(n0), mk3(n1), bound, dl);
+  const bool hr = slab_hit(sr, mk3(n2), mk3(n3), bound, dr);
   const int32_t lref = __float_as_int(n0.w), rref = __float_as_int(n1.w);
   if (hl && hr) {
     const bool left_first = !(dr < dl);
@@ -391,13 +418,12 @@ __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, 
   float2 stack[RTB_STACK_LBVH];  // deferred children: (entry distance, node / leaf reference) in one 8-byte local-memory access
   int sp = 0;
   int32_t cur = s.root;
-  const f3 inv = safe_inverse(r.d);
-  const f3 ood = r.o * inv;
+  const SlabRay sr = make_slab_ray(r.o, r.d);
   for (;;) {
     if (cur >= 0) {
       // same box test, bound and child order as k_traverse_lbvh
       const float bound = ANY ? nextafterf(t_limit, INFINITY) : best.t;
-      const int32_t next = lbvh_visit<false>(s.nodes, cur, inv, ood, bound, stack, sp, overflow);
+      const int32_t next = lbvh_visit<false>(s.nodes, cur, sr, bound, stack, sp, overflow);
       if (next != RTB_REF_MISS) { cur = next; continue; }
     } else {
       const int32_t code = ~cur;
@@ -419,7 +445,7 @@ __device__ __forceinline__ bool traverse_lbvh(const SceneView& s, const Ray& r, 
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// 8-wide quantised LBVH (RTB_BVH_WIDE, the default form of RTB_BVH_LBVH; lbvh.cu: k_wide_level builds it from the binary radix
+// 8-wide quantised LBVH (RTB_BVH_WIDE: RTB_BVH_LBVH scenes when RTB_WIDE=1; lbvh.cu: k_wide_level builds it from the binary radix
 // tree).  One 96-byte record = three 32-byte sectors = three 256-bit loads decides eight children, so a ray makes about a
 // third of the dependent node fetches of the two-box binary records and half the L1 wavefronts.  Record (24 words):
 //   w0-2  p = min corner of the node's box          w3  bytes: ESx, ESy, ESz (biased exponents of S = 2^15 * cell), valid mask

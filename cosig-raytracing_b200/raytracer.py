@@ -288,6 +288,39 @@ class RayTracer:
         self._check(self._lib.rtb_frame_import(self._ctx, h, C.byref(ptr)))
         return ptr.value
 
+    # ---- process-per-GPU frame ring (rtb_group_*) ------------------------------------------------------------------------------
+    def group_create(self, rank: int, world: int, frame_bytes: int, n_buffers: int = 4, handle: Optional[bytes] = None) -> bytes:
+        """Rank 0 returns the 64-byte handle the other ranks must pass in (send it over torch.distributed, MPI, a pipe ...)."""
+        h = (C.c_uint8 * 64)(*(handle or bytes(64)))
+        self._check(self._lib.rtb_group_create(self._ctx, rank, world, frame_bytes, n_buffers, h))
+        return bytes(h)
+
+    def GroupRenderBegin(self, scene, settings, out: Optional[np.ndarray] = None) -> int:
+        """Enqueue this rank's bands of the next frame; on rank 0 `out` (pinned uint8 [h, w, 4]) receives the whole frame."""
+        if not self._ensure_scene(scene):
+            raise RtbError(abi.RTB_E_NOSCENE, "no scene")
+        p = self._params(settings)
+        ticket = C.c_int32()
+        ptr, n = (out.ctypes.data, out.nbytes) if out is not None else (None, 0)
+        self._check(self._lib.rtb_group_render_begin(self._ctx, C.byref(p), ptr, n, C.byref(ticket)))
+        return ticket.value
+
+    def GroupRenderEnd(self, ticket: int) -> None:
+        self._check(self._lib.rtb_group_render_end(self._ctx, ticket))
+
+    def group_destroy(self):
+        self._check(self._lib.rtb_group_destroy(self._ctx))
+
+    def external_import(self, handle_type: int, handle: int, nbytes: int, dedicated: bool = False) -> int:
+        """Maps a graphics-API allocation (POSIX fd / NT handle) into the device's address space; returns a device pointer usable
+        as RenderToTexture's dst_ptr (the zero-copy realtime path)."""
+        ptr = C.c_void_p()
+        self._check(self._lib.rtb_external_import(self._ctx, handle_type, C.c_void_p(handle), nbytes, 1 if dedicated else 0, C.byref(ptr)))
+        return ptr.value
+
+    def external_release(self, ptr: int):
+        self._check(self._lib.rtb_external_release(self._ctx, C.c_void_p(ptr)))
+
     def frame_read(self, out: np.ndarray):
         self._check(self._lib.rtb_frame_read(self._ctx, out.ctypes.data, out.nbytes))
 

@@ -191,9 +191,38 @@ void rtb_free_pinned(void* p);
  * `dst_device`.  Opened pointers are closed by rtb_destroy. */
 int rtb_frame_export(rtb_context* ctx, size_t bytes, void** dev_ptr, uint8_t handle64[64]);
 int rtb_frame_import(rtb_context* ctx, const uint8_t handle64[64], void** dev_ptr);
+/* Process-per-GPU rendering of ONE frame stream by `world` ranks (one process and one single-device context each): the
+ * frame is split into bands of params.band_rows rows (default 8), band b is rendered by rank b % world, every rank's resolve kernel
+ * stores its bands straight into a frame buffer of rank 0 over NVLink, and rank 0 reads whole frames back — pipelined over
+ * `n_buffers` (1..8) frame buffers with device-side sequence flags, so no rank ever blocks on another from the host.
+ * rtb_group_create: rank 0 allocates the ring (n_buffers frames of frame_bytes + flags) and FILLS handle64; every other rank
+ * receives those 64 bytes from the host's own channel (MPI, torch.distributed, a pipe) and PASSES them in.  All ranks then call
+ * rtb_group_render_begin for the same sequence of frames (band_rank / band_world / out_layout of `p` are set by the library);
+ * `rgba8` (pinned host memory, width*height*4 bytes) is used on rank 0 only.  rtb_group_render_end: rank 0 — the frame is in
+ * its host buffer; other ranks — their bands are stored.  Up to 16 frames may be begun before the oldest is ended.  A rank that
+ * does not arrive within RTB_GROUP_TIMEOUT_MS (default 10000) turns into RTB_E_CUDA on the waiting ranks, never a hang.
+ * Destroy the group (or the contexts) on every rank before rank 0's context goes away. */
+int rtb_group_create(rtb_context* ctx, int32_t rank, int32_t world, size_t frame_bytes, int32_t n_buffers, uint8_t handle64[64]);
+int rtb_group_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* ticket);
+int rtb_group_render_end(rtb_context* ctx, int32_t ticket);
+int rtb_group_destroy(rtb_context* ctx);
+
 /* ReadPixels (RayTracer.cs:371-375) of the context's own frame buffer — the one rtb_frame_export shares — after the
  * peers have stored their bands into it. */
 int rtb_frame_read(rtb_context* ctx, uint8_t* rgba8, size_t bytes);
+
+/* Zero-copy display: the reference's realtime mode never reads the frame back — RenderToTexture returns the GPU
+ * RenderTexture (RayTracer.cs:82-202) and UI Toolkit shows it (SceneBuilder.cs:836-852).  The counterpart here: the host's graphics
+ * API allocates the buffer its texture is fed from, exports it (Vulkan vkGetMemoryFdKHR / vkGetMemoryWin32HandleKHR, D3D12
+ * CreateSharedHandle), and rtb_external_import maps it into device_ids[0]'s address space (cudaImportExternalMemory); the
+ * returned pointer is then a valid `dst_device` of rtb_render_device, whose resolve kernel stores the RGBA8 pixels straight into
+ * it.  `handle`: the file descriptor cast to a pointer (RTB_EXT_OPAQUE_FD; owned by CUDA after a successful import — do not
+ * close it) or the NT handle.  `dedicated` != 0 for D3D12 committed resources / Vulkan dedicated allocations.  Synchronise with
+ * the graphics queue by `sync` = 1 (or rtb_synchronize) before the graphics API samples the buffer.  rtb_external_release (or
+ * rtb_destroy) unmaps. */
+enum { RTB_EXT_OPAQUE_FD = 1, RTB_EXT_OPAQUE_WIN32 = 2, RTB_EXT_D3D12_HEAP = 4, RTB_EXT_D3D12_RESOURCE = 5 };
+int rtb_external_import(rtb_context* ctx, int32_t handle_type, void* handle, size_t bytes, int32_t dedicated, void** dev_ptr);
+int rtb_external_release(rtb_context* ctx, void* dev_ptr);
 
 /* Parity/debug access to the acceleration structure of the uploaded scene: nodes as stored on the device (reference
  * mode: 8 words per node = GPUBVHNode, BVHBuilder.cs:27-34; LBVH mode: 16 words per node) and the

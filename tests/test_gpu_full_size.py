@@ -124,10 +124,14 @@ def test_c5_on_the_c4_scene_sampled_rows(c4):
 
 
 # ---- camera far from the scene (the LBVH box tests must stay conservative whatever the distance) -----------------------------------
+@pytest.mark.parametrize("wide", ["0", "1"])
 @pytest.mark.parametrize("distance", [74.0, 3000.0, 60000.0])
-def test_far_camera_lbvh_matches_reference_mode(distance):
-    """the binary LBVH's FMA slab test relied on build-time padding sized for cameras within a few scene radii.  The wide
-    records widen per ray instead, so a camera 1000 scene radii away must still see every hit the reference-shape tree sees."""
+def test_far_camera_lbvh_matches_reference_mode(distance, wide, monkeypatch):
+    """the LBVH box tests are evaluated as fma(bound, 1/d, -origin/d), which rounds by ~1e-7 |origin / d|: build-time
+    padding alone only covered cameras within a few scene radii.  Both node formats now widen per ray (the binary records by
+    2^-21 |origin / d| per axis, the wide records by 2^-20 of their plane terms), so a camera 1000 scene radii away must still see
+    every hit the reference-shape tree sees."""
+    monkeypatch.setenv("RTB_WIDE", wide)
     obj = synth.heightfield_scene(100, 50)
     T = scene_mod.TransformElement
     obj.Transformations[1] = scene_mod.CompositeTransformation([T.Translation((0, 0, -distance)), T.RotationX(-60.0), T.RotationZ(45.0)])
@@ -195,3 +199,151 @@ def test_two_processes_gather_into_one_frame_over_ipc(samples_scene2):
 @pytest.fixture(scope="module")
 def samples_scene2():
     return synth.sample_scene("test_scene_2")
+
+
+# ---- zero-copy display path: render into memory owned by another API ---------------------------------------------------
+def test_render_into_imported_external_memory(samples_scene2):
+    """RenderToTexture without readback (RayTracer.cs:82-202): the frame lands in an allocation the library did not make.  A CUDA
+    virtual-memory allocation exported as a POSIX file descriptor stands in for the Vulkan / D3D12 buffer Unity would export
+    (vkGetMemoryFdKHR): rtb_external_import maps it (cudaImportExternalMemory), rtb_render_device's resolve kernel stores into it,
+    and the 'graphics side' reads the pixels through its own mapping of the same memory."""
+    try:
+        from cuda.bindings import driver as cu
+    except ImportError:
+        from cuda import cuda as cu
+    obj = samples_scene2
+    w, h = 512, 288
+    p = params(w, h, 4)
+
+    def ok(res):
+        err, rest = res[0], res[1:]
+        assert int(err) == 0, f"driver API error {err}"
+        return rest[0] if len(rest) == 1 else rest
+
+    with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as rt:
+        want = rt.RenderAsync(obj, p).pixels
+        ok(cu.cuInit(0))
+        dev = ok(cu.cuDeviceGet(0))
+        ctx = ok(cu.cuDevicePrimaryCtxRetain(dev))
+        ok(cu.cuCtxSetCurrent(ctx))
+        prop = cu.CUmemAllocationProp()
+        prop.type = cu.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
+        prop.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        prop.location.id = 0
+        prop.requestedHandleTypes = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+        gran = ok(cu.cuMemGetAllocationGranularity(prop, cu.CUmemAllocationGranularity_flags.CU_MEM_ALLOC_GRANULARITY_MINIMUM))
+        size = (w * h * 4 + gran - 1) // gran * gran
+        handle = ok(cu.cuMemCreate(size, prop, 0))
+        fd = ok(cu.cuMemExportToShareableHandle(handle, cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0))
+        va = ok(cu.cuMemAddressReserve(size, 0, 0, 0))
+        ok(cu.cuMemMap(va, size, 0, handle, 0))
+        acc = cu.CUmemAccessDesc()
+        acc.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        acc.location.id = 0
+        acc.flags = cu.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
+        ok(cu.cuMemSetAccess(va, size, [acc], 1))
+        ok(cu.cuMemsetD8(va, 0, size))
+        ptr = rt.external_import(abi.RTB_EXT_OPAQUE_FD, int(fd), size)
+        assert ptr
+        rt.RenderToTexture(obj, p, ptr, w * h * 4, sync=True)
+        got = np.zeros((h, w, 4), np.uint8)
+        ok(cu.cuMemcpyDtoH(got.ctypes.data, va, got.nbytes))
+        assert (got == want).all(), f"{(got != want).any(axis=-1).sum()} pixels differ"
+        # a second frame with other settings into the same mapping (the realtime loop reuses its target, RayTracer.cs:126-132)
+        p2 = params(w, h, 2, has_fov=1, fov_deg=20.0)
+        want2 = rt.RenderAsync(obj, p2).pixels
+        rt.RenderToTexture(obj, p2, ptr, w * h * 4, sync=True)
+        ok(cu.cuMemcpyDtoH(got.ctypes.data, va, got.nbytes))
+        assert (got == want2).all()
+        rt.external_release(ptr)
+        with pytest.raises(rt_mod.RtbError):
+            rt.external_release(ptr)
+        ok(cu.cuMemUnmap(va, size))
+        ok(cu.cuMemAddressFree(va, size))
+        ok(cu.cuMemRelease(handle))
+
+
+# ---- the process-per-GPU frame ring inside the library (rtb_group_*) -------------------------------------------------------------------
+_GROUP_CHILD = r"""
+import importlib, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+from util import abi, params, synth
+rt_mod = importlib.import_module("cosig-raytracing_b200.raytracer")
+handle = bytes.fromhex(sys.stdin.readline().strip())
+obj = synth.sample_scene("test_scene_2")
+rt = rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH)
+rt.group_create(1, 2, {w} * {h} * 4, {nbuf}, handle)
+print("joined", flush=True)
+tickets = [rt.GroupRenderBegin(obj, params({w}, {h}, 4, 1, has_fov=1, fov_deg=20.0 + 2.0 * k)) for k in range({frames})]
+for t in tickets:
+    rt.GroupRenderEnd(t)
+print("stored", flush=True)
+sys.stdin.readline()
+rt.close()
+"""
+
+
+def test_group_frame_ring_two_processes_one_gpu(samples_scene2):
+    """rtb_group_*: two ranks (two processes; here on the same GPU) render the bands of a stream of frames into rank 0's ring of
+    frame buffers and rank 0 reads them back, with more frames in flight than buffers.  Every frame must equal the one-context
+    render bit for bit, in order."""
+    obj = samples_scene2
+    w, h, frames, nbuf = 400, 240, 7, 2
+    settings = [params(w, h, 4, 1, has_fov=1, fov_deg=20.0 + 2.0 * k) for k in range(frames)]
+    with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as one:
+        want = [one.RenderAsync(obj, p).pixels for p in settings]
+    rt = rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH)
+    child = None
+    try:
+        handle = rt.group_create(0, 2, w * h * 4, nbuf)
+        child = subprocess.Popen([sys.executable, "-c", _GROUP_CHILD.format(root=ROOT, tests=os.path.join(ROOT, "tests"), w=w, h=h, nbuf=nbuf, frames=frames)],
+                                 stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
+        child.stdin.write(handle.hex() + "\n"); child.stdin.flush()
+
+        def expect(word):
+            line = ""
+            for _ in range(50):
+                line = child.stdout.readline()
+                if not line or line.strip() == word:
+                    break
+            assert line.strip() == word, f"child ended with {line!r} instead of {word!r} (exit code {child.poll()})"
+
+        expect("joined")
+        outs = [np.zeros((h, w, 4), np.uint8) for _ in settings]
+        tickets = [rt.GroupRenderBegin(obj, p, o) for p, o in zip(settings, outs)]
+        for t in tickets:
+            rt.GroupRenderEnd(t)
+        expect("stored")
+        for k, (o, wnt) in enumerate(zip(outs, want)):
+            assert (o == wnt).all(), f"frame {k}: {(o != wnt).any(axis=-1).sum()} pixels differ"
+        child.stdin.write("done\n"); child.stdin.flush()
+        assert child.wait(timeout=120) == 0
+    finally:
+        if child is not None and child.poll() is None:
+            child.kill()
+        rt.close()
+
+
+def test_group_of_one_equals_render_begin(samples_scene2):
+    """world = 1: the ring degenerates to rtb_render_begin / rtb_render_end (and a missing peer is an error, not a hang)."""
+    obj = samples_scene2
+    p = params(320, 200, 3)
+    with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as rt:
+        want = rt.RenderAsync(obj, p).pixels
+        rt.group_create(0, 1, 320 * 200 * 4, 2)
+        outs = [np.zeros((200, 320, 4), np.uint8) for _ in range(5)]
+        for t in [rt.GroupRenderBegin(obj, p, o) for o in outs]:
+            rt.GroupRenderEnd(t)
+        assert all((o == want).all() for o in outs)
+        rt.group_destroy()
+    import os as _os
+    _os.environ["RTB_GROUP_TIMEOUT_MS"] = "300"
+    try:
+        with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as rt:
+            rt.group_create(0, 2, 320 * 200 * 4, 2)  # rank 1 never joins
+            out = np.zeros((200, 320, 4), np.uint8)
+            t = rt.GroupRenderBegin(obj, p, out)
+            with pytest.raises(rt_mod.RtbError):
+                rt.GroupRenderEnd(t)
+    finally:
+        del _os.environ["RTB_GROUP_TIMEOUT_MS"]
