@@ -93,6 +93,7 @@ class Stats(C.Structure):
         ("ms_traverse", C.c_float), ("ms_shade", C.c_float), ("ms_resolve", C.c_float),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("reserved", C.c_int64 * 4),
+        ("rays_traversed", C.c_int64), ("packet_node_fetches", C.c_int64), ("packet_tri_fetches", C.c_int64), ("bytes_per_slot", C.c_int64),
     ]
 
 

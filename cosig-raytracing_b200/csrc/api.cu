@@ -548,7 +548,7 @@ int collect_stats(rtb_context* ctx) {
   st.rays_primary = st.rays_continuation = st.rays_shadow = st.paths_hit_primary = 0;
   st.ms_render_device = 0.0f;
   st.ms_traverse = st.ms_shade = st.ms_resolve = 0.0f;
-  int64_t overflow = 0, nodes = 0, tris = 0, longest = 0;
+  int64_t overflow = 0, nodes = 0, tris = 0, longest = 0, entered = 0, pk_nodes = 0, pk_tris = 0;
   for (auto& d : ctx->devs) {
     device_sync(d);
     CK(ctx, cudaGetLastError());
@@ -568,6 +568,7 @@ int collect_stats(rtb_context* ctx) {
       st.rays_primary += (int64_t)t[0]; st.rays_continuation += (int64_t)t[1]; st.rays_shadow += (int64_t)t[2];
       st.paths_hit_primary += (int64_t)t[3]; overflow += (int64_t)t[4]; nodes += (int64_t)t[5]; tris += (int64_t)t[6];
       longest = std::max(longest, (int64_t)t[7]);
+      entered += (int64_t)t[RTB_TOT_ENTERED]; pk_nodes += (int64_t)t[RTB_TOT_PACKET_NODES]; pk_tris += (int64_t)t[RTB_TOT_PACKET_TRIS];
       float ms = 0.0f;
       if (cudaEventElapsedTime(&ms, l.ev_begin, l.ev_end) == cudaSuccess) st.ms_render_device = std::max(st.ms_render_device, ms);
       else cudaGetLastError();
@@ -582,6 +583,10 @@ int collect_stats(rtb_context* ctx) {
   st.reserved[1] = nodes;
   st.reserved[2] = tris;
   st.reserved[3] = longest;
+  st.rays_traversed = entered + st.rays_continuation + st.rays_shadow;
+  st.packet_node_fetches = pk_nodes;
+  st.packet_tri_fetches = pk_tris;
+  st.bytes_per_slot = 12 * (int64_t)sizeof(float4);
   cudaSetDevice(ctx->devs[0].device);
   return RTB_OK;
 }

@@ -24,6 +24,7 @@ namespace rtb {
 #endif
 #define RTB_TOTALS 80     /* 8 counters + 16 depths x 4 timeline words (diagnostic builds, RTB_RAY_STATS) + packet counters */
 #define RTB_TOT_PACKET_NODES 72 /* node records fetched by the packet kernels (one per warp and visit) */
+#define RTB_TOT_ENTERED 74      /* primary rays that entered the BVH (the depth-0 queue) */
 #define RTB_TOT_PACKET_TRIS 73  /* triangle records fetched by the packet kernels (one per warp and test) */
 #define RTB_STACK_LBVH 96  /* LBVH ordered traversal: one deferred sibling per level */
 #ifndef RTB_LEAF_MAX

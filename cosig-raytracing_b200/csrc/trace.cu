@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
   }
 #endif
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (depth == 0 && n_closest > 0) atomicAdd(&q.totals[RTB_TOT_ENTERED], (unsigned long long)n_closest);
     if (depth > 0 && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
     if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
   }
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
   }
 #endif
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (depth == 0 && n_closest > 0) atomicAdd(&q.totals[RTB_TOT_ENTERED], (unsigned long long)n_closest);
     if (depth > 0 && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
     if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
   }
@@ -497,6 +499,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
   const int32_t total = n_closest + n_shadow;
   const int in_q = depth & 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (depth == 0 && n_closest > 0) atomicAdd(&q.totals[RTB_TOT_ENTERED], (unsigned long long)n_closest);
     if (depth > 0 && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
     if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
   }
@@ -741,7 +744,7 @@ __global__ void __launch_bounds__(kStreamBlock) k_primary(const FrameParams f, c
     }
   }
   for (int o = 16; o > 0; o >>= 1) n_valid += __shfl_xor_sync(kFull, n_valid, o);
-  if (lane == 0 && n_valid) atomicAdd(&q.totals[0], (unsigned long long)n_valid);
+  if (lane == 0 && n_valid) { atomicAdd(&q.totals[0], (unsigned long long)n_valid); atomicAdd(&q.totals[RTB_TOT_ENTERED], (unsigned long long)n_valid); }
   packet_counters(q, overflow, n_nodes, n_tris, w_nodes, w_tris);
 }
 

@@ -116,7 +116,12 @@ typedef struct rtb_stats {
   float ms_traverse, ms_shade, ms_resolve; /* per kernel family (k_traverse = all BVH queries, k_shade, k_resolve), summed over
                                              depths/chunks on device 0; only when profiling is enabled */
   int64_t h2d_bytes, d2h_bytes;   /* bytes copied across PCIe by the last render call */
-  int64_t reserved[4];            /* [0] traversal-stack overflows (must be 0) [1] BVH nodes fetched [2] triangles tested */
+  int64_t reserved[4];            /* [0] traversal-stack overflows (must be 0) [1] BVH node visits (per ray) [2] triangles tested (per ray)
+                                     [3] diagnostic builds: node visits of the longest ray */
+  int64_t rays_traversed;         /* rays that entered the BVH: all rays minus the primary rays k_raygen resolved against the scene's
+                                     root box (they count as rays — the reference traces them — but cost one box test) */
+  int64_t packet_node_fetches, packet_tri_fetches; /* record fetches of the packet kernels (one per warp and visit), when enabled */
+  int64_t bytes_per_slot;         /* wavefront queue state per pixel-sample slot and lane */
 } rtb_stats;
 
 /* new RayTracer() + SetComputeShader, RayTracer.cs:17-32.  device_ids == NULL -> {0}.  With n_devices > 1 the frame is
