@@ -371,6 +371,23 @@ def test_cpp_host_mirror_render_matches_oracle(samples, tmp_path):
     assert (got == osc.render(params(160, 120, 4))["rgba8"]).all()
 
 
+def test_c_binding_sequence_on_the_gpu(samples, tmp_path):
+    """tests/c/binding_sequence.c walks the call sequence of csharp/RayTracerNative.cs (upload, RenderAsync with the cancel flag,
+    RenderToTexture's begin / end, tickets in flight, invalidate / re-upload, clear target, a file scene, the rotation GIF) from
+    plain C; the frame it renders from the scene file must be the oracle's."""
+    import subprocess
+    from test_host_cpu import build_binding_sequence
+    exe = build_binding_sequence()
+    obj, osc, _ = samples["test_scene_1"]
+    scene_file, out = tmp_path / "scene.txt", tmp_path / "out.rgba"
+    scene_file.write_bytes(synth.scene_to_text(obj).encode())
+    r = subprocess.run([exe, "gpu", str(scene_file), str(out), "200", "150"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(out, np.uint8).reshape(150, 200, 4)
+    assert (got == osc.render(params(200, 150, 3))["rgba8"]).all()
+    assert os.path.getsize(str(out) + ".gif") > 1000
+
+
 def test_multi_device_context_matches_single(samples):
     """One process driving two GPUs: bands over the devices, peers store into device 0's frame (needs >= 2 GPUs)."""
     import torch

@@ -351,6 +351,44 @@ def test_cpp_host_mirror_builds_and_runs_host_checks(pkg, tmp_path):
 
 
 # ---- bench.py contract: one JSON line on stdout ------------------------------------------------------------------------------------
+def build_binding_sequence():
+    """tests/c/binding_sequence.c: the call sequence of csharp/RayTracerNative.cs in plain C (gcc, C11) against include/rtb.h."""
+    exe = os.path.join(ROOT, "tests", "c", "binding_sequence")
+    src = os.path.join(ROOT, "tests", "c", "binding_sequence.c")
+    lib_dir = os.path.join(ROOT, "cosig-raytracing_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-O1", src, "-I", os.path.join(ROOT, "include"), "-L", lib_dir, "-lrtb200",
+                           f"-Wl,-rpath,{lib_dir}", "-o", exe])
+    return exe
+
+
+def test_c_binding_sequence_host_part(pkg):
+    """The header is usable from C (not only C++), and the host-only calls the C# static constructor / marshalling make behave."""
+    exe = build_binding_sequence()
+    r = subprocess.run([exe, "host"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+
+
+def test_csharp_binding_declares_what_it_calls():
+    """csharp/RayTracerNative.cs cannot be compiled here; at least every entry point it imports must exist in rtb.h with the same
+    number of parameters, and it must actually upload scenes and define the reference's public surface."""
+    src = open(os.path.join(ROOT, "csharp", "RayTracerNative.cs")).read()
+    header = open(os.path.join(ROOT, "include", "rtb.h")).read()
+    imports = re.findall(r"\[DllImport\(Lib\)\]\s+public static extern (?:unsafe )?[\w\*]+ (rtb_\w+)\(([^)]*)\)", src)
+    assert len(imports) >= 22
+    for name, args in imports:
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\);", header, re.S)
+        assert m, f"{name} is imported by the C# binding but not declared in rtb.h"
+        n_cs = 0 if not args.strip() else len(args.split(","))
+        n_c = 0 if m.group(1).strip() in ("", "void") else len(m.group(1).split(","))
+        assert n_cs == n_c, f"{name}: {n_cs} parameters in C#, {n_c} in rtb.h"
+    body = src[src.index("unsafe void EnsureScene"):]
+    assert "RtbNative.rtb_upload_scene(ctx, &d, PrimitiveMode, BvhMode)" in body and "omitted" not in src
+    for member in ("SetComputeShader", "InvalidateBVHCache", "ReleaseBuffers", "ClearRenderTarget", "RenderTexture RenderToTexture(ObjectData scene, RenderSettings settings)",
+                   "Task<Texture2D> RenderAsync(ObjectData scene, RenderSettings settings, IProgress<float> progress, CancellationToken token)", "SaveTexture",
+                   "RenderBegin", "RenderEnd", "GetStats"):
+        assert member in src, member
+
+
 def test_bench_reference_arm_prints_exactly_one_json_line():
     """`bench.py --impl reference` (the CPU restatement on the host cores; needs no GPU) must put ONE JSON line on stdout with the
     driver's keys; everything else (library banners, warnings) goes to stderr."""
