@@ -35,6 +35,30 @@ struct DeviceScene {
   int node_floats = 8;
 };
 
+// Device memory of the scene arrays and of the upload's temporaries, kept across rtb_invalidate / rtb_upload_scene: a re-upload
+// of a scene that fits does no cudaMalloc and no cudaFree (each of which synchronises the device and, next to gigabytes of live
+// wavefront queues, cost tens of milliseconds: round 1 measured 601 ms for rtb_invalidate and 14-16 ms of allocation per upload).
+struct Pool {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+enum { kPoolMaterials, kPoolPrims, kPoolTriIn, kPoolObjs, kPoolRaw, kPoolNrm, kPoolIsect, kPoolShade, kPoolPerm, kPoolNodes, kPoolWorkspace, kPoolRoot, kPoolCount };
+template <typename T>
+cudaError_t pool_reserve(Pool& pl, T*& out, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (pl.cap < bytes) {
+    if (pl.p) cudaFree(pl.p);
+    pl.p = nullptr;
+    pl.cap = 0;
+    const size_t want = bytes + bytes / 8;  // headroom: a slightly larger scene next time still fits
+    cudaError_t e = cudaMalloc(&pl.p, want);
+    if (e != cudaSuccess) return e;
+    pl.cap = want;
+  }
+  out = (T*)pl.p;
+  return cudaSuccess;
+}
+
 struct Queues {
   float4* base = nullptr;      // one allocation: 12 arrays of capacity slots
   int32_t* counters = nullptr;
@@ -76,8 +100,10 @@ struct DeviceState {
   size_t index_async_bytes[kMaxLanes] = {};
   float* sphere_table = nullptr;
   DeviceScene scene;
+  Pool pool[kPoolCount];  // backing store of `scene` and of the upload's temporaries
   void* frame = nullptr;  // RGBA8 frame (device 0) — also the IPC-exported buffer
   size_t frame_bytes = 0;
+  bool frame_exported = false;  // rtb_frame_export handed out an IPC handle: peers may have it mapped, so it must neither move nor go
   int32_t *aux_prim = nullptr, *aux_mat = nullptr;
   float* aux_t = nullptr;
   size_t aux_px = 0;
@@ -158,11 +184,17 @@ void dfree(T*& p) {
   p = nullptr;
 }
 
-void free_scene(DeviceState& d) {
+// Forgets the scene; its memory stays in the pool for the next upload.
+void free_scene(DeviceState& d) { d.scene = DeviceScene(); }
+
+// Returns the pool to the driver (rtb_destroy; rtb_clear_target when no scene is resident).
+void release_scene_pool(DeviceState& d) {
   cudaSetDevice(d.device);
-  DeviceScene& s = d.scene;
-  dfree(s.raw); dfree(s.nrm); dfree(s.isect); dfree(s.shade); dfree(s.nodes); dfree(s.materials); dfree(s.perm); dfree(s.prims);
-  s = DeviceScene();
+  d.scene = DeviceScene();
+  for (auto& pl : d.pool) {
+    if (pl.p) cudaFree(pl.p);
+    pl = Pool();
+  }
 }
 
 void device_sync(DeviceState& d) {
@@ -243,6 +275,8 @@ SceneView scene_view(const DeviceScene& s) {
 
 int ensure_frame(rtb_context* ctx, DeviceState& d, size_t bytes) {
   if (d.frame_bytes >= bytes) return RTB_OK;
+  if (d.frame_exported)
+    return fail(ctx, RTB_E_ARG, "the context's frame buffer is exported over IPC and too small for this frame: export a larger one first (peers would keep storing into freed memory)");
   dfree(d.frame);
   d.frame_bytes = 0;
   CK(ctx, cudaMalloc(&d.frame, bytes));
@@ -278,30 +312,29 @@ int upload_on_device(rtb_context* ctx, DeviceState& d, const rtb_scene_desc& des
   s.flavour = wide ? RTB_BVH_WIDE : bvh_mode;
   s.n_tris = n_out;
   s.n_mats = (int32_t)(mats.size() / 8);
-  CK(ctx, cudaMalloc(&s.materials, mats.size() * sizeof(float)));
+  CK(ctx, pool_reserve(d.pool[kPoolMaterials], s.materials, mats.size() * sizeof(float)));
   CK(ctx, cudaMemcpyAsync(s.materials, mats.data(), mats.size() * sizeof(float), cudaMemcpyHostToDevice, d.stream));
   if (n_out == 0) { CK(ctx, cudaStreamSynchronize(d.stream)); return RTB_OK; }
   s.n_prims = (int32_t)(prims.size() / 24);
   if (s.n_prims > 0) {
-    CK(ctx, cudaMalloc(&s.prims, prims.size() * sizeof(float)));
+    CK(ctx, pool_reserve(d.pool[kPoolPrims], s.prims, prims.size() * sizeof(float)));
     CK(ctx, cudaMemcpyAsync(s.prims, prims.data(), prims.size() * sizeof(float), cudaMemcpyHostToDevice, d.stream));
   }
 
   float* tri_in = nullptr;
   FlattenObject* dobjs = nullptr;
-  struct Guard { float*& a; FlattenObject*& b; ~Guard() { if (a) cudaFree(a); if (b) cudaFree(b); } } guard{tri_in, dobjs};
   if (desc.n_triangles > 0) {
-    CK(ctx, cudaMalloc(&tri_in, (size_t)desc.n_triangles * sizeof(rtb_triangle)));
+    CK(ctx, pool_reserve(d.pool[kPoolTriIn], tri_in, (size_t)desc.n_triangles * sizeof(rtb_triangle)));
     CK(ctx, cudaMemcpyAsync(tri_in, desc.triangles, (size_t)desc.n_triangles * sizeof(rtb_triangle), cudaMemcpyHostToDevice, d.stream));
   }
-  CK(ctx, cudaMalloc(&dobjs, objs.size() * sizeof(FlattenObject)));
+  CK(ctx, pool_reserve(d.pool[kPoolObjs], dobjs, objs.size() * sizeof(FlattenObject)));
   CK(ctx, cudaMemcpyAsync(dobjs, objs.data(), objs.size() * sizeof(FlattenObject), cudaMemcpyHostToDevice, d.stream));
   const size_t tri_bytes = (size_t)n_out * 3 * sizeof(float4);
-  CK(ctx, cudaMalloc(&s.raw, tri_bytes));
-  CK(ctx, cudaMalloc(&s.nrm, tri_bytes));
-  CK(ctx, cudaMalloc(&s.isect, (size_t)n_out * RTB_TRI_F4 * sizeof(float4)));
-  CK(ctx, cudaMalloc(&s.shade, tri_bytes));
-  CK(ctx, cudaMalloc(&s.perm, (size_t)n_out * sizeof(int32_t)));
+  CK(ctx, pool_reserve(d.pool[kPoolRaw], s.raw, tri_bytes));
+  CK(ctx, pool_reserve(d.pool[kPoolNrm], s.nrm, tri_bytes));
+  CK(ctx, pool_reserve(d.pool[kPoolIsect], s.isect, (size_t)n_out * RTB_TRI_F4 * sizeof(float4)));
+  CK(ctx, pool_reserve(d.pool[kPoolShade], s.shade, tri_bytes));
+  CK(ctx, pool_reserve(d.pool[kPoolPerm], s.perm, (size_t)n_out * sizeof(int32_t)));
 
   CK(ctx, cudaEventRecord(d.ev_begin, d.stream));
   launch_flatten(tri_in, dobjs, (int)objs.size(), d.sphere_table, n_out, s.raw, s.nrm, d.stream);
@@ -317,7 +350,7 @@ int upload_on_device(rtb_context* ctx, DeviceState& d, const rtb_scene_desc& des
     build_reference_bvh(raw_host.data(), n_out, bvh);
     s.n_nodes = (int32_t)(bvh.nodes.size() / 8);
     s.node_floats = 8;
-    CK(ctx, cudaMalloc(&s.nodes, bvh.nodes.size() * sizeof(float)));
+    CK(ctx, pool_reserve(d.pool[kPoolNodes], s.nodes, bvh.nodes.size() * sizeof(float)));
     CK(ctx, cudaMemcpyAsync(s.nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(float), cudaMemcpyHostToDevice, d.stream));
     CK(ctx, cudaMemcpyAsync(s.perm, bvh.perm.data(), (size_t)n_out * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
     launch_pack(s.raw, s.nrm, s.perm, n_out, s.isect, s.shade, d.stream);
@@ -325,38 +358,31 @@ int upload_on_device(rtb_context* ctx, DeviceState& d, const rtb_scene_desc& des
     CK(ctx, cudaEventRecord(d.ev_end, d.stream));
     CK(ctx, cudaStreamSynchronize(d.stream));  // bvh vectors go out of scope
   } else {
+    // The records are built in place in a worst-case sized array (n - 1 records; the binary tree uses about a third of them,
+    // the rest is never touched): no second allocation, no copy.
     const int32_t max_nodes = n_out > 1 ? n_out - 1 : 1;
     const int rec_f4 = node_record_f4(s.flavour);
     s.node_floats = 4 * rec_f4;
-    float4* big = nullptr;  // worst-case sized; the records actually written are copied into an exact allocation below
-    CK(ctx, cudaMalloc(&big, (size_t)max_nodes * rec_f4 * sizeof(float4)));
+    CK(ctx, pool_reserve(d.pool[kPoolNodes], s.nodes, (size_t)max_nodes * rec_f4 * sizeof(float4)));
     LbvhBuffers b;
-    b.nodes = big;
+    b.nodes = s.nodes;
     b.perm = s.perm;
     b.workspace_bytes = lbvh_workspace_bytes(n_out);
     void* ws = nullptr;
     int32_t* root_dev = nullptr;
     int32_t root_host[2] = {0, 0};
-    if (cudaMalloc(&ws, b.workspace_bytes) != cudaSuccess) { cudaFree(big); return fail(ctx, RTB_E_CUDA, "cudaMalloc(LBVH workspace) failed"); }
-    if (cudaMalloc(&root_dev, 2 * sizeof(int32_t)) != cudaSuccess) { cudaFree(ws); cudaFree(big); return fail(ctx, RTB_E_CUDA, "cudaMalloc(root) failed"); }
+    CK(ctx, pool_reserve(d.pool[kPoolWorkspace], ws, b.workspace_bytes));
+    CK(ctx, pool_reserve(d.pool[kPoolRoot], root_dev, 2 * sizeof(int32_t)));
     b.workspace = ws;
     b.root_out = root_dev;
     cudaError_t e = lbvh_build(s.raw, n_out, b, d.stream, wide);
     if (e == cudaSuccess) { launch_pack(s.raw, s.nrm, s.perm, n_out, s.isect, s.shade, d.stream); e = cudaGetLastError(); }
     if (e == cudaSuccess) e = cudaMemcpyAsync(root_host, root_dev, sizeof root_host, cudaMemcpyDeviceToHost, d.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
-    if (e == cudaSuccess) {
-      s.root = root_host[0];
-      s.n_nodes = std::max(1, std::min(root_host[1], max_nodes));
-      e = cudaMalloc(&s.nodes, (size_t)s.n_nodes * rec_f4 * sizeof(float4));
-      if (e == cudaSuccess) e = cudaMemcpyAsync(s.nodes, big, (size_t)s.n_nodes * rec_f4 * sizeof(float4), cudaMemcpyDeviceToDevice, d.stream);
-    }
     if (e == cudaSuccess) e = cudaEventRecord(d.ev_end, d.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
-    cudaFree(ws);
-    cudaFree(root_dev);
-    cudaFree(big);
     if (e != cudaSuccess) return fail(ctx, RTB_E_CUDA, std::string("LBVH build failed: ") + cudaGetErrorString(e));
+    s.root = root_host[0];
+    s.n_nodes = std::max(1, std::min(root_host[1], max_nodes));
   }
   CK(ctx, cudaEventElapsedTime(&ms_build, d.ev_begin, d.ev_end));
   return RTB_OK;
@@ -717,7 +743,7 @@ void rtb_destroy(rtb_context* ctx) {
   }
   for (auto& d : ctx->devs) {
     device_sync(d);
-    free_scene(d);
+    release_scene_pool(d);
     free_targets(d);
     dfree(d.sphere_table);
     for (auto* pool : {&d.prof_trace, &d.prof_shadow, &d.prof_resolve})
@@ -777,7 +803,7 @@ int rtb_upload_scene(rtb_context* ctx, const rtb_scene_desc* scene, int32_t prim
 
 int rtb_invalidate(rtb_context* ctx) {
   if (!ctx) return RTB_E_ARG;
-  for (auto& d : ctx->devs) { device_sync(d); free_scene(d); }
+  for (auto& d : ctx->devs) { device_sync(d); free_scene(d); }  // the arrays stay pooled for the next upload (rtb_clear_target returns them)
   cudaSetDevice(ctx->devs[0].device);
   ctx->has_scene = false;
   return RTB_OK;
@@ -785,8 +811,14 @@ int rtb_invalidate(rtb_context* ctx) {
 
 int rtb_clear_target(rtb_context* ctx) {
   if (!ctx) return RTB_E_ARG;
-  if (!ctx->ipc_opened.empty()) return fail(ctx, RTB_E_ARG, "frame buffers are shared over IPC; destroy the context instead");
-  for (auto& d : ctx->devs) { device_sync(d); free_targets(d); }
+  if (!ctx->ipc_opened.empty() || ctx->group.active) return fail(ctx, RTB_E_ARG, "frame buffers are shared over IPC; destroy the context instead");
+  for (auto& d : ctx->devs)
+    if (d.frame_exported) return fail(ctx, RTB_E_ARG, "the frame buffer is exported over IPC (peers may have it mapped); destroy the context instead");
+  for (auto& d : ctx->devs) {
+    device_sync(d);
+    free_targets(d);
+    if (!ctx->has_scene) release_scene_pool(d);  // ReleaseBuffers (RayTracer.cs:47-59) = rtb_invalidate + rtb_clear_target: everything goes
+  }
   cudaSetDevice(ctx->devs[0].device);
   return RTB_OK;
 }
@@ -1059,15 +1091,19 @@ void* rtb_alloc_pinned(size_t bytes) {
 void rtb_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
 int rtb_frame_export(rtb_context* ctx, size_t bytes, void** dev_ptr, uint8_t handle64[64]) {
-  if (!ctx || !handle64) return fail(ctx, RTB_E_ARG, "null argument");
+  if (!ctx || (!handle64 && !dev_ptr)) return fail(ctx, RTB_E_ARG, "null argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   DeviceState& d = ctx->devs[0];
   CK(ctx, cudaSetDevice(d.device));
+  if (d.frame_exported && d.frame_bytes < bytes) return fail(ctx, RTB_E_ARG, "a smaller frame buffer was already exported; its importers would be left with a dangling mapping");
   const int rc = ensure_frame(ctx, d, bytes);
   if (rc != RTB_OK) return rc;
-  cudaIpcMemHandle_t h;
-  CK(ctx, cudaIpcGetMemHandle(&h, d.frame));
-  std::memcpy(handle64, &h, 64);
+  if (handle64) {  // without a handle the call only names the context's own frame buffer (nothing leaves the process)
+    d.frame_exported = true;
+    cudaIpcMemHandle_t h;
+    CK(ctx, cudaIpcGetMemHandle(&h, d.frame));
+    std::memcpy(handle64, &h, 64);
+  }
   if (dev_ptr) *dev_ptr = d.frame;
   return RTB_OK;
 }

@@ -214,8 +214,7 @@ class RayTracer:
         w, h = self.resolve(self._cached_scene, p)
         if dst_ptr is None:
             ptr = C.c_void_p()
-            handle = (C.c_uint8 * 64)()
-            self._check(self._lib.rtb_frame_export(self._ctx, w * h * 4, C.byref(ptr), handle))
+            self._check(self._lib.rtb_frame_export(self._ctx, w * h * 4, C.byref(ptr), None))  # the context's own frame, not exported
             dst_ptr, dst_bytes = ptr.value, w * h * 4
         self._check(self._lib.rtb_render_device(self._ctx, C.byref(p), dst_ptr, dst_bytes, 1 if sync else 0))
         return DeviceTexture(dst_ptr, w, h)

@@ -193,7 +193,9 @@ void rtb_free_pinned(void* p);
 
 /* CUDA IPC plumbing for process-per-GPU hosts (bench.py under torchrun): export the context's device-0 frame buffer of
  * `bytes` bytes (allocated on demand) as a 64-byte handle; open a peer's handle and get a device pointer usable as
- * `dst_device`.  Opened pointers are closed by rtb_destroy. */
+ * `dst_device`.  Opened pointers are closed by rtb_destroy.  handle64 == NULL: no export, the call only returns the pointer of the
+ * context's own frame buffer.  Once exported the buffer neither moves nor shrinks: a later call that would need a larger one, and
+ * rtb_clear_target, fail with RTB_E_ARG instead of leaving importers with a dangling mapping. */
 int rtb_frame_export(rtb_context* ctx, size_t bytes, void** dev_ptr, uint8_t handle64[64]);
 int rtb_frame_import(rtb_context* ctx, const uint8_t handle64[64], void** dev_ptr);
 /* Process-per-GPU rendering of ONE frame stream by `world` ranks (one process and one single-device context each): the

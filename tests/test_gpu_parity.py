@@ -524,3 +524,29 @@ def test_c5_shape_8k_16spp_many_chunks(tracers, samples):
     rows = np.arange(7, 4320, 270)
     ref = osc.render(p, rows=(7, -1, 270))
     assert (tex[rows] == ref["rgba8"][rows]).all()
+
+
+def test_exported_frame_is_never_moved_under_its_importers(samples):
+    """once rtb_frame_export has handed out an IPC handle, a render that would need a larger internal frame and
+    rtb_clear_target must fail instead of freeing memory peers may still store into; re-uploads reuse pooled memory."""
+    obj = samples["test_scene_1"][0]
+    rt = rt_mod.RayTracer()
+    ptr, handle = rt.frame_export(64 * 48 * 4)
+    assert rt.RenderAsync(obj, params(64, 48, 2)) is not None          # fits the exported buffer
+    with pytest.raises(rt_mod.RtbError):
+        rt.RenderAsync(obj, params(128, 96, 2))                          # would have to reallocate it
+    with pytest.raises(rt_mod.RtbError):
+        rt.ClearRenderTarget()
+    with pytest.raises(rt_mod.RtbError):
+        rt.frame_export(128 * 96 * 4)
+    ptr2, _ = rt.frame_export(64 * 48 * 4)
+    assert ptr2 == ptr
+    rt.close()
+    rt = rt_mod.RayTracer()
+    a = rt.RenderAsync(obj, params(160, 120, 3)).pixels
+    for _ in range(3):                                                   # invalidate + upload cycles: pooled memory, same frame
+        rt.InvalidateBVHCache()
+        assert (rt.RenderAsync(obj, params(160, 120, 3)).pixels == a).all()
+    rt.ReleaseBuffers()
+    assert (rt.RenderAsync(obj, params(160, 120, 3)).pixels == a).all()
+    rt.close()
