@@ -880,7 +880,6 @@ namespace {
 int begin_frame(rtb_context* ctx, const rtb_render_params* p, uint8_t* host_dst, size_t bytes, int32_t* ticket, bool indexed) {
   if (!ctx || !p || !host_dst || !ticket) return fail(ctx, RTB_E_ARG, "null argument");
   if (p->band_world > 1) return fail(ctx, RTB_E_ARG, "rtb_render_begin renders whole frames");
-  if (ctx->devs.size() > 1) return fail(ctx, RTB_E_ARG, "rtb_render_begin needs a single-device context (use rtb_render)");
   if (!ctx->has_scene) return fail(ctx, RTB_E_NOSCENE, "no scene uploaded (rtb_upload_scene)");
   FrameParams f;
   std::string why;
@@ -910,16 +909,25 @@ int begin_frame(rtb_context* ctx, const rtb_render_params* p, uint8_t* host_dst,
     CK(ctx, cudaMalloc(&d.index_async[buf], need_out));
     d.index_async_bytes[buf] = need_out;
   }
-  // this frame reuses the device buffer of the frame issued n_buf calls ago: its readback must have finished
+  // this frame reuses the device buffer of the frame issued n_buf calls ago: its readback must have finished (on every device
+  // of a multi-device context: the peers store their bands into the same buffer)
   if (n >= (uint64_t)n_buf) {
     cudaEvent_t prev = ctx->ticket_event[(n - (uint64_t)n_buf) % rtb_context::kTickets];
-    for (auto& l : d.lane) CK(ctx, cudaStreamWaitEvent(l.stream, prev, 0));
+    for (auto& dev : ctx->devs) {
+      CK(ctx, cudaSetDevice(dev.device));
+      for (auto& l : dev.lane) CK(ctx, cudaStreamWaitEvent(l.stream, prev, 0));
+    }
+    CK(ctx, cudaSetDevice(d.device));
   }
   const int rc = render_frame(ctx, p, d.frame_async[buf], d.frame_async_bytes[buf], /*to_internal_frame=*/false, /*sync=*/false, f);
   if (rc != RTB_OK) return rc;
   LaneState& last = d.lane[d.last_lane];
   for (int k = 0; k < DeviceState::kMaxLanes; k++)  // multi-chunk frame: every lane that carried one of its chunks
     if (k != d.last_lane && d.lane[k].stream && d.lane[k].frame_id == ctx->frame_id) CK(ctx, cudaStreamWaitEvent(last.stream, d.lane[k].ev_done, 0));
+  if (ctx->devs.size() > 1) {  // render_frame made device 0's primary stream wait for the peers' stores: order the readback behind it
+    CK(ctx, cudaEventRecord(d.ev_done, d.stream));
+    if (last.stream != d.stream) CK(ctx, cudaStreamWaitEvent(last.stream, d.ev_done, 0));
+  }
   if (indexed) {  // ConvertToIndexed, GifGenerator.cs:346-369
     launch_palette(d.frame_async[buf], f.width, f.height, (uint8_t*)d.index_async[buf], last.stream);
     ctx->stats.kernel_launches++;

@@ -154,7 +154,9 @@ int rtb_render(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, siz
 /* Pipelined RenderAsync for hosts that render a stream of frames (the reference's realtime mode calls its renderer once per
  * Unity frame, SceneBuilder.cs:521-537): rtb_render_begin enqueues the frame and its readback into `rgba8` (page-locked memory,
  * see rtb_alloc_pinned, for a truly asynchronous copy) and returns a ticket; rtb_render_end blocks until that frame is in
- * `rgba8`.  Up to 16 frames may be in flight; `rgba8` must stay valid until its rtb_render_end.  Single-device contexts. */
+ * `rgba8`.  Up to 16 frames may be in flight; `rgba8` must stay valid until its rtb_render_end.  Multi-device contexts
+ * (rtb_create with several device ids) pipeline the same way: every device renders its bands of frame k+1 while device 0
+ * copies frame k out. */
 int rtb_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* ticket);
 int rtb_render_end(rtb_context* ctx, int32_t ticket);
 

@@ -401,8 +401,18 @@ def test_multi_device_context_matches_single(samples):
     two = rt_mod.RayTracer(devices=[0, 1])
     got = two.RenderAsync(obj, p).pixels
     st = two.stats()
-    two.close()
     assert st.n_devices == 2 and (got == ref).all()
+    # pipelined frames on the two-device context: more tickets in flight than device frame buffers
+    settings = [params(640, 360, 4, has_fov=1, fov_deg=20.0 + 2.0 * k) for k in range(9)]
+    outs = [np.zeros((360, 640, 4), np.uint8) for _ in settings]
+    tickets = [two.RenderBegin(obj, s, o) for s, o in zip(settings, outs)]
+    for t in tickets:
+        two.RenderEnd(t)
+    two.close()
+    one = rt_mod.RayTracer(devices=[0])
+    for s, o in zip(settings, outs):
+        assert (one.RenderAsync(obj, s).pixels == o).all()
+    one.close()
 
 
 # ---- wavefront (one launch pair per depth) and fused tail (k_tail) are two schedules of the same arithmetic ---------------------
