@@ -1,5 +1,5 @@
 """Deterministic synthetic scenes for the perf configurations C3-C5 and a loader for the packed copies
-of the reference's three sample scenes (tests/golden/scenes/*.npz, made by tests/golden/make_golden.py).
+of the reference's three sample scenes (cosig-raytracing_b200/scenes/*.npz, made by tests/golden/make_golden.py).
 
 No RNG state: every value is a closed-form function of indices, so every process (and every rank of a multi-GPU run)
 builds bit-identical scenes.
@@ -14,7 +14,7 @@ from . import abi
 from .scene import (BoxDescription, CameraSettings, CompositeTransformation, ImageSettings, LightSource, MaterialDescription,
                     ObjectData, SphereDescription, TransformElement, TrianglesMesh)
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "scenes")
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scenes")  # packed copies of the reference's three sample scenes, part of the package
 
 
 def _sample_camera_and_light(scene: ObjectData):

@@ -1,7 +1,7 @@
 """Regenerates tests/golden/* from the reference's shipped scene files with the CPU oracle.
 
 Run in the build container (needs /root/reference):  python tests/golden/make_golden.py
-  scenes/<name>.npz      packed copy of Assets/Resources/Scenes/<name>.txt (parsed by the oracle's SceneService restatement)
+  ../../cosig-raytracing_b200/scenes/<name>.npz      packed copy of Assets/Resources/Scenes/<name>.txt (parsed by the oracle's SceneService restatement)
   <name>_c1.npz          oracle outputs at the C1 settings (320x240, depth 3, AA 1): primary prim_id / t / material maps and
                          the RGBA8 frame; plus the AA-4 frame
   summary.json           triangle / node counts, counters and SHA-256 of the flattened triangle arrays and BVH nodes
@@ -47,9 +47,9 @@ def main():
     for name in synth.SAMPLE_SCENES:
         sc = O.OracleScene.from_file(os.path.join(REF, name + ".txt"))
         obj = scene_mod.unpack_scene(sc.desc)
-        synth.save_scene_npz(os.path.join(HERE, "scenes", name + ".npz"), obj)
+        synth.save_scene_npz(os.path.join(HERE, "..", "..", "cosig-raytracing_b200", "scenes", name + ".npz"), obj)
         # the packed copy must rebuild the very same oracle scene
-        packed = scene_mod.pack_scene(synth.load_scene_npz(os.path.join(HERE, "scenes", name + ".npz")))  # keep the buffers alive
+        packed = scene_mod.pack_scene(synth.load_scene_npz(os.path.join(HERE, "..", "..", "cosig-raytracing_b200", "scenes", name + ".npz")))  # keep the buffers alive
         again = O.OracleScene.from_desc(packed.desc)
         vn, mat, cen = sc.triangles()
         vn2, mat2, cen2 = again.triangles()
