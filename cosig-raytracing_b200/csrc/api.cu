@@ -71,6 +71,8 @@ struct Queues {
 struct LaneState {
   cudaStream_t stream = nullptr;
   Queues q;
+  void* pool_scratch = nullptr;   // k_traverse_pool's stack scratch (RTB_POOL=1)
+  size_t pool_scratch_bytes = 0;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_done = nullptr;
   uint64_t frame_id = 0;   // last frame that used this lane (its totals belong to that frame)
   bool used = false;       // work was enqueued since the last join
@@ -108,6 +110,7 @@ struct DeviceState {
   float* aux_t = nullptr;
   size_t aux_px = 0;
   int grid_traverse[3] = {0, 0, 0};
+  int grid_pool = 0;
   size_t smem_limit = 0;       // opt-in dynamic shared memory per block
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_trace, prof_shadow, prof_resolve;
   size_t prof_used[3] = {0, 0, 0};
@@ -130,6 +133,7 @@ struct rtb_context {
   int n_lanes = 4;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues
   uint64_t frame_id = 0;
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
+  int pool = 0;               // RTB_POOL=1: binary-LBVH scenes in global memory are traversed by the regrouping kernel k_traverse_pool
   int wide = 0;               // RTB_WIDE=1: RTB_BVH_LBVH scenes are stored as 8-wide quantised records instead of binary two-box records (measured slower: profiles/r2_sweep_wide.log)
   int packet_closest = -1;     // RTB_PACKET_CLOSEST: closest-hit rays of depth <= this go through the packet kernels (-1: none, k_raygen + per-lane)
   int packet_shadow = -1;     // RTB_PACKET_SHADOW: shadow rays emitted at depth <= this go through k_packet (-1: none)
@@ -229,8 +233,9 @@ void free_targets(DeviceState& d) {
   for (auto& l : d.lane) {
     dfree(l.q.base); dfree(l.q.counters); dfree(l.q.totals);
     l.q = Queues();
+    dfree(l.pool_scratch); l.pool_scratch_bytes = 0;
   }
-  dfree(d.frame); d.frame_bytes = 0;
+  dfree(d.frame); d.frame_bytes = 0; d.frame_exported = false;
   for (int k = 0; k < DeviceState::kMaxLanes; k++) { dfree(d.frame_async[k]); d.frame_async_bytes[k] = 0; }
   for (int k = 0; k < DeviceState::kMaxLanes; k++) { dfree(d.index_async[k]); d.index_async_bytes[k] = 0; }
   dfree(d.gif_scratch); d.gif_scratch_bytes = 0;
@@ -429,6 +434,20 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
       if (rc != RTB_OK) return rc;
     }
     const QueueView qv = queue_view(L.q);
+    const bool use_pool = ctx->pool != 0 && bvh == RTB_BVH_LBVH && smem_bytes == 0;
+    int pool_grid = 0;
+    if (use_pool) {
+      if (!d.grid_pool) d.grid_pool = d.sm_count * pool_blocks_per_sm();
+      pool_grid = d.grid_pool;
+      const size_t need = pool_scratch_bytes(pool_grid);
+      if (L.pool_scratch_bytes < need) {
+        CK(ctx, cudaStreamSynchronize(stream));
+        dfree(L.pool_scratch);
+        L.pool_scratch_bytes = 0;
+        CK(ctx, cudaMalloc(&L.pool_scratch, need));
+        L.pool_scratch_bytes = need;
+      }
+    }
     if (L.frame_id != ctx->frame_id) {  // first chunk of this frame on this lane
       L.frame_id = ctx->frame_id;
       CK(ctx, cudaEventRecord(L.ev_begin, stream));
@@ -492,8 +511,10 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
             if (depth - 1 <= pk_shadow) timed(0, [&] { launch_packet(bvh, sv, qv, depth - 1, 1, packet_grid, stream); });
             else mode |= 2;
           }
-          if (mode != 0)
-            timed(0, [&] { launch_traverse(bvh, sv, qv, depth, mode, smem_bytes ? d.sm_count : d.grid_traverse[bvh], smem_bytes, stream); });
+          if (mode != 0) {
+            if (use_pool) timed(0, [&] { launch_traverse_pool(sv, qv, depth, mode, pool_grid, L.pool_scratch, stream); });
+            else timed(0, [&] { launch_traverse(bvh, sv, qv, depth, mode, smem_bytes ? d.sm_count : d.grid_traverse[bvh], smem_bytes, stream); });
+          }
           if (depth < f.max_depth) {
             timed(1, [&] { launch_shade(f, sv, qv, c, depth, ctx->tail_max, shade_grid, stream); });
             if (ctx->tail_max > 0) timed(0, [&] { launch_tail(bvh, f, sv, qv, c, depth, ctx->tail_max, d.sm_count * 4, stream); });
@@ -680,6 +701,7 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
   if (const char* env = std::getenv("RTB_SMEM")) ctx->smem_mode = std::atoi(env);
   if (const char* env = std::getenv("RTB_SPLIT_BLOCKING")) ctx->split_blocking = std::atoi(env);
   if (const char* env = std::getenv("RTB_WIDE")) ctx->wide = std::atoi(env);
+  if (const char* env = std::getenv("RTB_POOL")) ctx->pool = std::atoi(env);
   if (const char* env = std::getenv("RTB_PACKET_CLOSEST")) ctx->packet_closest = std::atoi(env);
   if (const char* env = std::getenv("RTB_PACKET_SHADOW")) ctx->packet_shadow = std::atoi(env);
   if (const char* env = std::getenv("RTB_TAIL_MAX")) ctx->tail_max = (int32_t)std::max(0LL, std::atoll(env));

@@ -46,6 +46,11 @@ void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth,
 void launch_primary(int bvh, const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int grid, cudaStream_t st);
 void launch_packet(int bvh, const SceneView& s, const QueueView& q, int depth, int kind, int grid, cudaStream_t st);
 int stream_block_threads();
+// The regrouping per-lane kernel (k_traverse_pool, RTB_POOL=1): binary LBVH records only.  `scratch` = pool_scratch_bytes(grid)
+// bytes of device memory private to the launching stream.
+int pool_blocks_per_sm();
+size_t pool_scratch_bytes(int grid);
+void launch_traverse_pool(const SceneView& s, const QueueView& q, int depth, int mode, int grid, void* scratch, cudaStream_t st);
 size_t traverse_smem_bytes(int bvh, const SceneView& s);
 cudaError_t traverse_enable_smem(int bvh, size_t bytes);
 // k_shade handles depth `depth` when its queue holds >= tail_max rays; otherwise k_tail runs the remaining paths to their

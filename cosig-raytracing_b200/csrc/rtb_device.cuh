@@ -31,6 +31,7 @@ namespace rtb {
 #define RTB_LEAF_MAX 4     /* LBVH leaf size (<= 8) */
 #endif
 #define RTB_BVH_WIDE 2      /* kernel-side flavour: RTB_BVH_LBVH with 8-wide quantised node records (RTB_WIDE=1; the default keeps the binary records) */
+#define RTB_POOL_SLOTS 64   /* rays a warp of k_traverse_pool keeps in flight */
 #define RTB_WIDE_F4 6       /* float4 per 8-wide node record (96 bytes = three 32-byte sectors) */
 #define RTB_REF_DONE ((int32_t)0x80000000) /* LBVH traversal: "no more work" reference (never a valid leaf: n < 2^28) */
 #define RTB_REF_MISS ((int32_t)0x80000001) /* lbvh_visit: no child of the node was hit (the caller pops its stack) */

@@ -562,6 +562,217 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_traverse_pool: the per-lane kernel's answer to its own profile — 13 of 32 lanes live, because a warp's lanes wait for each
+// other at every phase change (all descend, then all intersect) while every ray's steps are strictly sequential.  Here a warp
+// keeps RTB_POOL_SLOTS = 64 rays in flight, their state in shared memory and their stacks in a slot-interleaved global scratch
+// area, and REGROUPS: in the node phase the 32 lanes take 32 slots that need a node step, run until fewer than kPoolRunMin of
+// them still descend, write back and pick again, until no slot needs a node step; then the same over the slots holding a leaf.
+// Same node visits, same triangle tests, same per-ray order as k_traverse_lbvh — only which lane does them changes.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef RTB_POOL_MIN_BLOCKS
+#define RTB_POOL_MIN_BLOCKS 6
+#endif
+#ifndef RTB_POOL_RUN_MIN
+#define RTB_POOL_RUN_MIN 20
+#endif
+#ifndef RTB_POOL_REFILL
+#define RTB_POOL_REFILL 16
+#endif
+constexpr int kPoolBlock = 128;
+enum { PW_INV = 0, PW_OMN = 3, PW_OMX = 6, PW_O = 9, PW_D = 12, PW_T = 15, PW_U = 16, PW_V = 17, PW_TRI = 18, PW_ITEM = 19, PW_CUR = 20, PW_SP = 21, PW_WORDS = 22 };
+
+// Lanes [0, n) receive the slots whose bit is set in (lo, hi), lowest slot first (at most 32); returns the lane's slot or -1.
+__device__ __forceinline__ int pool_assign(unsigned lo, unsigned hi, int* sel, int lane, bool& backlog) {
+  const unsigned lt = (1u << lane) - 1u;
+  const int n_lo = __popc(lo), n_all = n_lo + __popc(hi);
+  __syncwarp();
+  if ((lo >> lane) & 1u) sel[__popc(lo & lt)] = lane;
+  const int r_hi = n_lo + __popc(hi & lt);
+  if (((hi >> lane) & 1u) && r_hi < 32) sel[r_hi] = lane + 32;
+  __syncwarp();
+  backlog = n_all > 32;
+  return lane < (n_all < 32 ? n_all : 32) ? sel[lane] : -1;
+}
+
+template <bool ANALYTIC>
+__global__ void __launch_bounds__(kPoolBlock, RTB_POOL_MIN_BLOCKS) k_traverse_pool(const SceneView s, const QueueView q, const int depth, const int mode,
+                                                                                    float2* __restrict__ scratch) {
+  __shared__ float sm_state[kPoolBlock / 32][PW_WORDS][RTB_POOL_SLOTS];
+  __shared__ int sm_sel[kPoolBlock / 32][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float (*S)[RTB_POOL_SLOTS] = sm_state[wib];
+  int* sel = sm_sel[wib];
+  float2* const stk_base = scratch + ((size_t)blockIdx.x * (kPoolBlock / 32) + (size_t)wib) * (size_t)(RTB_STACK_LBVH * RTB_POOL_SLOTS);
+  const float4* nodes = s.nodes;
+  const float4* tri_isect = s.tri_isect;
+  const int32_t n_closest = (mode & 1) ? RTB_CNT_RAY(q, depth) : 0;
+  const int32_t n_shadow = (depth == 0 || !(mode & 2)) ? 0 : RTB_CNT_SHADOW(q, depth - 1);
+  const int32_t total = n_closest + n_shadow;
+  const int in_q = depth & 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (depth == 0 && n_closest > 0) atomicAdd(&q.totals[RTB_TOT_ENTERED], (unsigned long long)n_closest);
+    if (depth > 0 && n_closest > 0) atomicAdd(&q.totals[1], (unsigned long long)n_closest);
+    if (n_shadow > 0) atomicAdd(&q.totals[2], (unsigned long long)n_shadow);
+  }
+  S[PW_ITEM][lane] = __int_as_float(-1); S[PW_ITEM][lane + 32] = __int_as_float(-1);
+  S[PW_CUR][lane] = __int_as_float(RTB_REF_DONE); S[PW_CUR][lane + 32] = __int_as_float(RTB_REF_DONE);
+  WorkPool pool;
+  unsigned overflow = 0, n_nodes = 0, n_tris = 0;
+
+  for (;;) {
+    // ---- publish finished slots, refill free ones (each lane looks after slots lane and lane + 32) ----
+    __syncwarp();
+    bool is_free[2];
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int sidx = lane + 32 * b;
+      int32_t item = __float_as_int(S[PW_ITEM][sidx]);
+      if (item >= 0 && __float_as_int(S[PW_CUR][sidx]) == RTB_REF_DONE) {
+        Lane L;
+        L.item = item; L.shadow = item >= n_closest; L.done = true;
+        L.t = S[PW_T][sidx]; L.u = S[PW_U][sidx]; L.v = S[PW_V][sidx]; L.tri = __float_as_int(S[PW_TRI][sidx]);
+        L.o = L.d = L.inv = mk3(0.0f, 0.0f, 0.0f);
+        lane_finish(L, q, n_closest);
+        item = -1;
+        S[PW_ITEM][sidx] = __int_as_float(-1);
+      }
+      is_free[b] = item < 0;
+    }
+    const int n_free = __popc(__ballot_sync(kFull, is_free[0])) + __popc(__ballot_sync(kFull, is_free[1]));
+    if (n_free >= RTB_POOL_REFILL && !pool.exhausted) {
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        const int sidx = lane + 32 * b;
+        const int32_t item = pool_take(pool, &RTB_CNT_FETCH(q, depth), total, is_free[b], lane);
+        if (item >= 0) {
+          Lane L;
+          lane_load(L, q, item, n_closest, in_q);
+          const SlabRay sr = make_slab_ray(L.o, L.d);
+          S[PW_INV][sidx] = sr.inv.x; S[PW_INV + 1][sidx] = sr.inv.y; S[PW_INV + 2][sidx] = sr.inv.z;
+          S[PW_OMN][sidx] = sr.ood_mn.x; S[PW_OMN + 1][sidx] = sr.ood_mn.y; S[PW_OMN + 2][sidx] = sr.ood_mn.z;
+          S[PW_OMX][sidx] = sr.ood_mx.x; S[PW_OMX + 1][sidx] = sr.ood_mx.y; S[PW_OMX + 2][sidx] = sr.ood_mx.z;
+          S[PW_O][sidx] = L.o.x; S[PW_O + 1][sidx] = L.o.y; S[PW_O + 2][sidx] = L.o.z;
+          S[PW_D][sidx] = L.d.x; S[PW_D + 1][sidx] = L.d.y; S[PW_D + 2][sidx] = L.d.z;
+          S[PW_T][sidx] = L.t; S[PW_U][sidx] = 0.0f; S[PW_V][sidx] = 0.0f; S[PW_TRI][sidx] = __int_as_float(-1);
+          S[PW_ITEM][sidx] = __int_as_float(item);
+          S[PW_CUR][sidx] = __int_as_float(s.n_tris > 0 ? s.root : RTB_REF_DONE);
+          S[PW_SP][sidx] = __int_as_float(0);
+          is_free[b] = false;
+        }
+      }
+    }
+    if ((__ballot_sync(kFull, !is_free[0]) | __ballot_sync(kFull, !is_free[1])) == 0u) {
+      if (pool.exhausted) break;
+      continue;
+    }
+
+    // ---- node phase: until no occupied slot needs a node step ----
+    for (;;) {
+      __syncwarp();
+      const int32_t c0 = __float_as_int(S[PW_CUR][lane]), c1 = __float_as_int(S[PW_CUR][lane + 32]);
+      const unsigned lo = __ballot_sync(kFull, __float_as_int(S[PW_ITEM][lane]) >= 0 && c0 >= 0);
+      const unsigned hi = __ballot_sync(kFull, __float_as_int(S[PW_ITEM][lane + 32]) >= 0 && c1 >= 0);
+      if ((lo | hi) == 0u) break;
+      bool backlog;
+      const int my = pool_assign(lo, hi, sel, lane, backlog);
+      SlabRay sr;
+      sr.inv = sr.ood_mn = sr.ood_mx = mk3(0.0f, 0.0f, 0.0f);
+      float t = 0.0f;
+      int32_t cur = RTB_REF_DONE;
+      int sp = 0;
+      float2* stk = stk_base;
+      if (my >= 0) {
+        sr.inv = mk3(S[PW_INV][my], S[PW_INV + 1][my], S[PW_INV + 2][my]);
+        sr.ood_mn = mk3(S[PW_OMN][my], S[PW_OMN + 1][my], S[PW_OMN + 2][my]);
+        sr.ood_mx = mk3(S[PW_OMX][my], S[PW_OMX + 1][my], S[PW_OMX + 2][my]);
+        t = S[PW_T][my];
+        cur = __float_as_int(S[PW_CUR][my]);
+        sp = __float_as_int(S[PW_SP][my]);
+        stk = stk_base + my;
+      }
+      for (;;) {
+        if (cur >= 0) {
+          n_nodes++;
+          const int32_t next = lbvh_visit<false, RTB_POOL_SLOTS>(nodes, cur, sr, t, stk, sp, overflow);
+          if (next != RTB_REF_MISS) cur = next;
+          else {
+            cur = RTB_REF_DONE;
+            while (sp > 0) {
+              sp--;
+              const float2 e = stk[(size_t)sp * RTB_POOL_SLOTS];
+              if (!(e.x > t)) { cur = __float_as_int(e.y); break; }
+            }
+          }
+        }
+        const int n_act = __popc(__ballot_sync(kFull, cur >= 0));
+        if (n_act == 0 || (backlog && n_act < RTB_POOL_RUN_MIN)) break;
+      }
+      if (my >= 0) { S[PW_CUR][my] = __int_as_float(cur); S[PW_SP][my] = __int_as_float(sp); }
+    }
+
+    // ---- leaf phase: until no occupied slot holds a leaf ----
+    for (;;) {
+      __syncwarp();
+      const int32_t c0 = __float_as_int(S[PW_CUR][lane]), c1 = __float_as_int(S[PW_CUR][lane + 32]);
+      const unsigned lo = __ballot_sync(kFull, __float_as_int(S[PW_ITEM][lane]) >= 0 && c0 < 0 && c0 != RTB_REF_DONE);
+      const unsigned hi = __ballot_sync(kFull, __float_as_int(S[PW_ITEM][lane + 32]) >= 0 && c1 < 0 && c1 != RTB_REF_DONE);
+      if ((lo | hi) == 0u) break;
+      bool backlog;
+      const int my = pool_assign(lo, hi, sel, lane, backlog);
+      Lane L;
+      L.item = -1; L.shadow = false; L.done = false; L.t = 0.0f; L.u = 0.0f; L.v = 0.0f; L.tri = -1;
+      L.o = L.d = L.inv = mk3(0.0f, 0.0f, 0.0f);
+      int32_t cur = RTB_REF_DONE;
+      int sp = 0;
+      float2* stk = stk_base;
+      if (my >= 0) {
+        L.o = mk3(S[PW_O][my], S[PW_O + 1][my], S[PW_O + 2][my]);
+        L.d = mk3(S[PW_D][my], S[PW_D + 1][my], S[PW_D + 2][my]);
+        L.t = S[PW_T][my]; L.u = S[PW_U][my]; L.v = S[PW_V][my]; L.tri = __float_as_int(S[PW_TRI][my]);
+        L.item = __float_as_int(S[PW_ITEM][my]);
+        L.shadow = L.item >= n_closest;
+        cur = __float_as_int(S[PW_CUR][my]);
+        sp = __float_as_int(S[PW_SP][my]);
+        stk = stk_base + my;
+      }
+      for (;;) {
+        if (cur < 0 && cur != RTB_REF_DONE) {
+          const int32_t code = ~cur;
+          const int32_t first = code >> 3, count = (code & 7) + 1;
+          bool occluded = false;
+          n_tris += count;
+          for (int32_t i = 0; i < count && !occluded; i++) occluded = lane_test_triangle<false, ANALYTIC, true>(L, s, tri_isect, first + i);
+          cur = RTB_REF_DONE;
+          if (occluded) sp = 0;
+          while (sp > 0) {
+            sp--;
+            const float2 e = stk[(size_t)sp * RTB_POOL_SLOTS];
+            if (!(e.x > L.t)) { cur = __float_as_int(e.y); break; }
+          }
+        }
+        const int n_leaf = __popc(__ballot_sync(kFull, cur < 0 && cur != RTB_REF_DONE));
+        if (n_leaf == 0 || (backlog && n_leaf < RTB_POOL_RUN_MIN)) break;
+      }
+      if (my >= 0) {
+        S[PW_T][my] = L.t; S[PW_U][my] = L.u; S[PW_V][my] = L.v; S[PW_TRI][my] = __int_as_float(L.tri);
+        S[PW_CUR][my] = __int_as_float(cur); S[PW_SP][my] = __int_as_float(sp);
+      }
+    }
+  }
+
+  for (int o = 16; o > 0; o >>= 1) {
+    overflow += __shfl_xor_sync(kFull, overflow, o);
+    n_nodes += __shfl_xor_sync(kFull, n_nodes, o);
+    n_tris += __shfl_xor_sync(kFull, n_tris, o);
+  }
+  if (lane == 0) {
+    if (overflow) atomicAdd(&q.totals[4], (unsigned long long)overflow);
+    if (n_nodes) atomicAdd(&q.totals[5], (unsigned long long)n_nodes);
+    if (n_tris) atomicAdd(&q.totals[6], (unsigned long long)n_tris);
+  }
+}
+
 // =====================================================================================================================
 // Packet traversal: a warp walks the BVH ONCE for its 32 rays.  Rays that are neighbours on the screen (primary rays of an
 // 8x4 tile, the shadow rays those pixels emit towards the one light) visit nearly the same nodes, so the per-lane kernels
@@ -1244,6 +1455,18 @@ void launch_packet(int bvh, const SceneView& s, const QueueView& q, int depth, i
 }
 
 int stream_block_threads() { return kStreamBlock; }
+
+// k_traverse_pool (binary LBVH records, scene in global memory): persistent grid, slot-interleaved stack scratch per warp.
+int pool_blocks_per_sm() {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse_pool<false>, kPoolBlock, 0) != cudaSuccess || n < 1) n = 1;
+  return n;
+}
+size_t pool_scratch_bytes(int grid) { return (size_t)grid * (kPoolBlock / 32) * (size_t)(RTB_STACK_LBVH * RTB_POOL_SLOTS) * sizeof(float2); }
+void launch_traverse_pool(const SceneView& s, const QueueView& q, int depth, int mode, int grid, void* scratch, cudaStream_t st) {
+  if (s.n_prims > 0) k_traverse_pool<true><<<grid, kPoolBlock, 0, st>>>(s, q, depth, mode, (float2*)scratch);
+  else k_traverse_pool<false><<<grid, kPoolBlock, 0, st>>>(s, q, depth, mode, (float2*)scratch);
+}
 
 void launch_shade(const FrameParams& f, const SceneView& s, const QueueView& q, const ChunkView& c, int depth, int32_t tail_max, int grid,
                   cudaStream_t st) {

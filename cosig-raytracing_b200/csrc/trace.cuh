@@ -382,7 +382,9 @@ __device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, 
   return r0;
 }
 #else
-template <bool SMEM>
+// STRIDE: distance between consecutive stack entries (1: a thread-private array; RTB_POOL_SLOTS: the slot-interleaved scratch of
+// k_traverse_pool).
+template <bool SMEM, int STRIDE = 1>
 __device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, const SlabRay& sr, float bound, float2* stack,
                                               int& sp, unsigned& overflow) {
   float4 n0, n1, n2, n3;
@@ -394,7 +396,7 @@ __device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, 
   const int32_t lref = __float_as_int(n0.w), rref = __float_as_int(n1.w);
   if (hl && hr) {
     const bool left_first = !(dr < dl);
-    if (sp < RTB_STACK_LBVH) { stack[sp] = make_float2(left_first ? dr : dl, __int_as_float(left_first ? rref : lref)); sp++; }
+    if (sp < RTB_STACK_LBVH) { stack[(size_t)sp * STRIDE] = make_float2(left_first ? dr : dl, __int_as_float(left_first ? rref : lref)); sp++; }
     else overflow++;
     return left_first ? lref : rref;
   }
