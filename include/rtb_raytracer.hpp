@@ -193,8 +193,7 @@ class RayTracer {
     check_create(rtb_resolve_frame(packed_->desc(), &p, nullptr, wh));
     RenderTexture rt;
     rt.width = wh[0]; rt.height = wh[1];
-    uint8_t handle[64];
-    check(rtb_frame_export(ctx_, (size_t)wh[0] * wh[1] * 4, &rt.device_ptr, handle));
+    check(rtb_frame_export(ctx_, (size_t)wh[0] * wh[1] * 4, &rt.device_ptr, nullptr));  // the context's own frame buffer; nothing is exported
     check(rtb_render_device(ctx_, &p, rt.device_ptr, (size_t)wh[0] * wh[1] * 4, 1));
     return rt;
   }
