@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """tools/ncu_counters.py [workload ...] — regenerates profiles/ncu_counters.json on the GPU box (run it under gpurun, ONE GPU).
 
-For every workload: one `ncu --set full --clock-control none` pass over the k_traverse* / k_packet / k_primary launches of one warm
+For every workload: one `ncu --metrics <the eight below> --clock-control none` pass over the k_traverse* / k_packet / k_primary launches of one warm
 frame of `bench.py --workload W` (RTB_LANES=1 so launches keep program order), after the same command has run without ncu.  From
 the raw page it keeps, per frame: DRAM bytes read + written (`roofline.traffic`), and — weighted by each launch's duration — active
 lanes per instruction, issue-slot utilisation, L1 data-pipe wavefront utilisation and the L2 hit rate.  The file is keyed to
@@ -50,7 +50,8 @@ def capture(workload, out_dir):
     n = frame_launch_count(workload)
     rep = os.path.join(out_dir, f"counters_{workload}")
     # skip the launches of the upload frame and of one warm-up frame: capture one frame of the timed region
-    ncu = ["ncu", "--set", "full", "--clock-control", "none", "-k", f"regex:{KERNELS}", "-s", str(2 * n), "-c", str(n), "-f", "-o", rep] + cmd
+    # only the metrics this file reads (a handful of replay passes instead of --set full's ~40: the capture costs GPU minutes)
+    ncu = ["ncu", "--metrics", ",".join(M.values()), "--clock-control", "none", "-k", f"regex:{KERNELS}", "-s", str(2 * n), "-c", str(n), "-f", "-o", rep] + cmd
     r = subprocess.run(ncu, env=env, capture_output=True, text=True)
     if r.returncode != 0:
         raise SystemExit(f"ncu failed:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
@@ -84,7 +85,7 @@ def main():
     out_dir = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out_dir, exist_ok=True)
     doc = {"source_hash": bench.source_hash(), "generated_by": "tools/ncu_counters.py " + " ".join(workloads),
-           "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "how": "ncu --set full --clock-control none, one warm frame, RTB_LANES=1",
+           "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "how": "ncu --metrics (dram bytes, lanes per instruction, issue active, L1 wavefronts, L2 hit rate) --clock-control none, one warm frame, RTB_LANES=1",
            "workloads": {}}
     for wl in workloads:
         doc["workloads"][wl] = capture(wl, out_dir)
