@@ -355,6 +355,9 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
           if (!(e.x > L.t)) { cur = __float_as_int(e.y); break; }
         }
       }
+#if RTB_PREFETCH_LEAF
+      if (!SMEM && cur < 0 && cur != RTB_REF_DONE) prefetch_leaf(tri_isect, cur);  // this lane now waits for the others: warm its triangles up
+#endif
     }
 
     // ---- leaf ----

@@ -382,6 +382,24 @@ __device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, 
   return r0;
 }
 #else
+// Software prefetch (build-time experiments, tools/build_variants.sh): RTB_PREFETCH_PUSH 1 / 2 = when a child is deferred, ask L1 / L2
+// for its record, so that the pop which visits it later does not pay the full miss; RTB_PREFETCH_LEAF 1 = a lane that has
+// reached a leaf asks for its triangle records while the other lanes of the warp still descend.
+#ifndef RTB_PREFETCH_PUSH
+#define RTB_PREFETCH_PUSH 0
+#endif
+#ifndef RTB_PREFETCH_LEAF
+#define RTB_PREFETCH_LEAF 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_leaf(const float4* tri_isect, int32_t leaf_ref) {
+  const int32_t code = ~leaf_ref;
+  const int32_t first = code >> 3, count = (code & 7) + 1;
+  prefetch_l1(&tri_isect[RTB_TRI_F4 * (size_t)first]);
+  if (count > 2) prefetch_l1(&tri_isect[RTB_TRI_F4 * (size_t)(first + count) - 1]);
+}
+
 // STRIDE: distance between consecutive stack entries (1: a thread-private array; RTB_POOL_SLOTS: the slot-interleaved scratch of
 // k_traverse_pool).
 template <bool SMEM, int STRIDE = 1>
@@ -398,6 +416,12 @@ __device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, 
     const bool left_first = !(dr < dl);
     if (sp < RTB_STACK_LBVH) { stack[(size_t)sp * STRIDE] = make_float2(left_first ? dr : dl, __int_as_float(left_first ? rref : lref)); sp++; }
     else overflow++;
+#if RTB_PREFETCH_PUSH
+    if (!SMEM) {
+      const int32_t far = left_first ? rref : lref;
+      if (far >= 0) { if (RTB_PREFETCH_PUSH == 1) prefetch_l1(&nodes[4 * (size_t)far]); else prefetch_l2(&nodes[4 * (size_t)far]); }
+    }
+#endif
     return left_first ? lref : rref;
   }
   if (hl) return lref;
