@@ -213,16 +213,30 @@ __device__ __forceinline__ float pad_lo(float v, float radius) { return v - 1e-6
 __device__ __forceinline__ float pad_hi(float v, float radius) { return v + 1e-6f * (fabsf(v) + radius); }
 
 #if RTB_LBVH_WIDTH != 4
+// Only the tree nodes whose range holds more than RTB_LEAF_MAX triangles become records (about a third of the n - 1 Karras
+// nodes); k_mark_live flags them and an exclusive scan gives each its slot, so the records are DENSE: a 128-byte cache line
+// holds two live records instead of 0.7 on average, which is what L1 and L2 capacity are spent on.  Karras order is kept (a
+// subtree's records stay contiguous), only the holes go.
+__global__ void __launch_bounds__(kBlock) k_mark_live(int32_t n, const int2* __restrict__ range, int32_t* __restrict__ flag) {
+  const int32_t n_int = n - 1;
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_int; i += gridDim.x * blockDim.x) {
+    const int2 rg = range[i];
+    flag[i] = rg.y - rg.x + 1 > RTB_LEAF_MAX ? 1 : 0;
+  }
+}
+
 __global__ void __launch_bounds__(kBlock) k_emit(int32_t n, const int2* __restrict__ child, const int2* __restrict__ range,
-                                                 const float4* __restrict__ box, const unsigned* __restrict__ bounds, float4* __restrict__ nodes,
-                                                 int32_t* __restrict__ root_out) {
+                                                 const float4* __restrict__ box, const unsigned* __restrict__ bounds, const int32_t* __restrict__ flag,
+                                                 const int32_t* __restrict__ slot, float4* __restrict__ nodes, int32_t* __restrict__ root_out) {
   const int32_t n_int = n - 1;
   float radius = 0.0f;
   for (int a = 0; a < 6; a++) radius = fmaxf(radius, fabsf(o2f(bounds[a])));
-  if (blockIdx.x == 0 && threadIdx.x == 0) { root_out[0] = (n <= RTB_LEAF_MAX) ? lbvh_leaf_ref(0, n) : 0; root_out[1] = n_int > 0 ? n_int : 1; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    root_out[0] = (n <= RTB_LEAF_MAX) ? lbvh_leaf_ref(0, n) : 0;  // the root is node 0 and, being live, gets slot 0
+    root_out[1] = n_int > 0 ? max(1, slot[n_int - 1] + flag[n_int - 1]) : 1;
+  }
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_int; i += gridDim.x * blockDim.x) {
-    const int2 rg = range[i];
-    if (rg.y - rg.x + 1 <= RTB_LEAF_MAX) continue;  // inside a collapsed leaf: never referenced
+    if (!flag[i]) continue;  // inside a collapsed leaf: never referenced
     const int2 ch = child[i];
     int32_t ref[2];
     size_t bi[2];
@@ -232,15 +246,16 @@ __global__ void __launch_bounds__(kBlock) k_emit(int32_t n, const int2* __restri
       else {
         const int2 cr = range[cc[k]];
         const int32_t cnt = cr.y - cr.x + 1;
-        ref[k] = cnt <= RTB_LEAF_MAX ? lbvh_leaf_ref(cr.x, cnt) : cc[k];
+        ref[k] = cnt <= RTB_LEAF_MAX ? lbvh_leaf_ref(cr.x, cnt) : slot[cc[k]];
         bi[k] = (size_t)cc[k];
       }
     }
     const float4 lmn = box[2 * bi[0]], lmx = box[2 * bi[0] + 1], rmn = box[2 * bi[1]], rmx = box[2 * bi[1] + 1];
-    nodes[4 * (size_t)i] = make_float4(pad_lo(lmn.x, radius), pad_lo(lmn.y, radius), pad_lo(lmn.z, radius), __int_as_float(ref[0]));
-    nodes[4 * (size_t)i + 1] = make_float4(pad_hi(lmx.x, radius), pad_hi(lmx.y, radius), pad_hi(lmx.z, radius), __int_as_float(ref[1]));
-    nodes[4 * (size_t)i + 2] = make_float4(pad_lo(rmn.x, radius), pad_lo(rmn.y, radius), pad_lo(rmn.z, radius), 0.0f);
-    nodes[4 * (size_t)i + 3] = make_float4(pad_hi(rmx.x, radius), pad_hi(rmx.y, radius), pad_hi(rmx.z, radius), 0.0f);
+    float4* rec = nodes + 4 * (size_t)slot[i];
+    rec[0] = make_float4(pad_lo(lmn.x, radius), pad_lo(lmn.y, radius), pad_lo(lmn.z, radius), __int_as_float(ref[0]));
+    rec[1] = make_float4(pad_hi(lmx.x, radius), pad_hi(lmx.y, radius), pad_hi(lmx.z, radius), __int_as_float(ref[1]));
+    rec[2] = make_float4(pad_lo(rmn.x, radius), pad_lo(rmn.y, radius), pad_lo(rmn.z, radius), 0.0f);
+    rec[3] = make_float4(pad_hi(rmx.x, radius), pad_hi(rmx.y, radius), pad_hi(rmx.z, radius), 0.0f);
   }
 }
 
@@ -519,7 +534,13 @@ cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaS
   }
   k_emit4<<<grid_for(n > 1 ? n - 1 : 1), kBlock, 0, st>>>(n, w.child, w.range, w.box, w.bounds, w.flag, w.idx4, b.nodes, b.root_out);
 #else
-  k_emit<<<grid_for(n > 1 ? n - 1 : 1), kBlock, 0, st>>>(n, w.child, w.range, w.box, w.bounds, b.nodes, b.root_out);
+  if (n > 1) {  // w.flag has done its job in k_refit: reuse it for the live flags
+    k_mark_live<<<grid_for(n - 1), kBlock, 0, st>>>(n, w.range, w.flag);
+    temp = w.cub_bytes;
+    e = cub::DeviceScan::ExclusiveSum(w.cub_temp, temp, (const int32_t*)w.flag, w.idx4, n - 1, st);
+    if (e != cudaSuccess) return e;
+  }
+  k_emit<<<grid_for(n > 1 ? n - 1 : 1), kBlock, 0, st>>>(n, w.child, w.range, w.box, w.bounds, w.flag, w.idx4, b.nodes, b.root_out);
 #endif
   return cudaGetLastError();
 }
