@@ -130,7 +130,7 @@ struct rtb_context {
   int64_t chunk_slots_once = 0;  // rtb_render: chunk size of the frame being enqueued (a blocking frame is split over the lanes), 0 = chunk_slots
   int split_blocking = 1;        // RTB_SPLIT_BLOCKING: 0 = one chunk per blocking frame as long as it fits chunk_slots
   int64_t chunk_slots = 1 << 24;  // RTB_CHUNK_SLOTS: pixel-samples per chunk (192 B of queues each, per lane); C5 sweep: profiles/r1e_sweep_chunk_slots_c5.log
-  int n_lanes = 4;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues
+  int n_lanes = 6;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues (4 -> 6: pipelined e2e +2.5 %, profiles/r2_sweep_lanes.log)
   uint64_t frame_id = 0;
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
   int pool = 0;               // RTB_POOL=1: binary-LBVH scenes in global memory are traversed by the regrouping kernel k_traverse_pool
@@ -867,7 +867,8 @@ int rtb_render(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, siz
     std::string why;
     if (!resolve_frame(ctx->host.d, *p, g, why)) return fail(ctx, RTB_E_ARG, why);
     const int64_t slots = (int64_t)((g.width + 7) / 8) * ((g.height + 3) / 4) * 32 * g.spp;
-    if (slots >= (1 << 22) && g.debug == 0) ctx->chunk_slots_once = (slots + ctx->n_lanes - 1) / ctx->n_lanes;
+    const int parts = std::min(ctx->n_lanes, 4);  // more than four row ranges cost more in launches than their overlap returns
+    if (slots >= (1 << 22) && g.debug == 0) ctx->chunk_slots_once = (slots + parts - 1) / parts;
   }
   const int rc = render_frame(ctx, p, nullptr, 0, /*to_internal_frame=*/true, /*sync=*/false, f);
   const bool was_split = ctx->chunk_slots_once > 0;

@@ -31,14 +31,16 @@ namespace {
 
 constexpr int kBlock = 256;
 // Persistent traversal kernels (global-memory variant): block size and resident blocks per SM the register allocation is
-// bounded for.  Measured on the B200 (profiles/r1e_sweep_occupancy.log): 128 x 10 = 40 warps per SM at 48
-// registers (152 B of spills outside the node loop) beats 256 x 4 = 32 warps at 64 registers by 3-4 % on C3 / C4; 48 warps
-// (40 registers) loses again.  Build-time knobs so the sweep can be repeated (tools/build_variants.sh).
+// bounded for.  Measured on the B200: round 1 (profiles/r1e_sweep_occupancy.log) found 128 x 10 = 40 warps per SM
+// at 48 registers ahead of 256 x 4 = 32 warps at 64 registers by 3-4 % on C3 / C4, and 48 warps (40 registers) behind again;
+// with round 2's per-ray slab constants (three more live registers) 128 x 9 = 36 warps at 56 registers, which keeps the leaf
+// loop free of spills, is ahead of 10 by 0.7 % (C4) / 1.3 % (C3) and of 8 by 3.5 % (profiles/r2_sweep_occupancy.log).
+// Build-time knobs so the sweep can be repeated (tools/build_variants.sh).
 #ifndef RTB_TRAVERSE_BLOCK
 #define RTB_TRAVERSE_BLOCK 128
 #endif
 #ifndef RTB_TRAVERSE_MIN_BLOCKS
-#define RTB_TRAVERSE_MIN_BLOCKS 10
+#define RTB_TRAVERSE_MIN_BLOCKS 9
 #endif
 constexpr int kTravBlock = RTB_TRAVERSE_BLOCK;
 // Streaming kernels that compact into queues (k_raygen, k_shade): threads per block = length of a contiguous queue run.
