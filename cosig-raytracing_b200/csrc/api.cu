@@ -73,8 +73,6 @@ struct LaneState {
   Queues q;
   void* pool_scratch = nullptr;   // k_traverse_pool's stack scratch (RTB_POOL=1)
   size_t pool_scratch_bytes = 0;
-  void* coop_scratch = nullptr;   // k_traverse_lbvh's cooperative-finish frontiers
-  size_t coop_scratch_bytes = 0;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_done = nullptr;
   uint64_t frame_id = 0;   // last frame that used this lane (its totals belong to that frame)
   bool used = false;       // work was enqueued since the last join
@@ -135,7 +133,6 @@ struct rtb_context {
   int n_lanes = 6;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues (4 -> 6: pipelined e2e +2.5 %, profiles/r2_sweep_lanes.log)
   uint64_t frame_id = 0;
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
-  int coop = 1;               // RTB_COOP=0: no cooperative finish (every ray is walked by one lane to its end)
   int pool = 0;               // RTB_POOL=1: binary-LBVH scenes in global memory are traversed by the regrouping kernel k_traverse_pool
   int wide = 0;               // RTB_WIDE=1: RTB_BVH_LBVH scenes are stored as 8-wide quantised records instead of binary two-box records (measured slower: profiles/r2_sweep_wide.log)
   int packet_closest = -1;     // RTB_PACKET_CLOSEST: closest-hit rays of depth <= this go through the packet kernels (-1: none, k_raygen + per-lane)
@@ -237,7 +234,6 @@ void free_targets(DeviceState& d) {
     dfree(l.q.base); dfree(l.q.counters); dfree(l.q.totals);
     l.q = Queues();
     dfree(l.pool_scratch); l.pool_scratch_bytes = 0;
-    dfree(l.coop_scratch); l.coop_scratch_bytes = 0;
   }
   dfree(d.frame); d.frame_bytes = 0; d.frame_exported = false;
   for (int k = 0; k < DeviceState::kMaxLanes; k++) { dfree(d.frame_async[k]); d.frame_async_bytes[k] = 0; }
@@ -452,19 +448,6 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
         L.pool_scratch_bytes = need;
       }
     }
-    void* coop = nullptr;
-    if (ctx->coop != 0 && bvh == RTB_BVH_LBVH && smem_bytes == 0 && !use_pool) {
-      if (!d.grid_traverse[bvh]) d.grid_traverse[bvh] = d.sm_count * traverse_blocks_per_sm(bvh);
-      const size_t need = coop_scratch_bytes(d.grid_traverse[bvh]);
-      if (L.coop_scratch_bytes < need) {
-        CK(ctx, cudaStreamSynchronize(stream));
-        dfree(L.coop_scratch);
-        L.coop_scratch_bytes = 0;
-        CK(ctx, cudaMalloc(&L.coop_scratch, need));
-        L.coop_scratch_bytes = need;
-      }
-      coop = L.coop_scratch;
-    }
     if (L.frame_id != ctx->frame_id) {  // first chunk of this frame on this lane
       L.frame_id = ctx->frame_id;
       CK(ctx, cudaEventRecord(L.ev_begin, stream));
@@ -530,7 +513,7 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
           }
           if (mode != 0) {
             if (use_pool) timed(0, [&] { launch_traverse_pool(sv, qv, depth, mode, pool_grid, L.pool_scratch, stream); });
-            else timed(0, [&] { launch_traverse(bvh, sv, qv, depth, mode, smem_bytes ? d.sm_count : d.grid_traverse[bvh], smem_bytes, coop, stream); });
+            else timed(0, [&] { launch_traverse(bvh, sv, qv, depth, mode, smem_bytes ? d.sm_count : d.grid_traverse[bvh], smem_bytes, stream); });
           }
           if (depth < f.max_depth) {
             timed(1, [&] { launch_shade(f, sv, qv, c, depth, ctx->tail_max, shade_grid, stream); });
@@ -719,7 +702,6 @@ int rtb_create(rtb_context** out, const int32_t* device_ids, int32_t n_devices) 
   if (const char* env = std::getenv("RTB_SPLIT_BLOCKING")) ctx->split_blocking = std::atoi(env);
   if (const char* env = std::getenv("RTB_WIDE")) ctx->wide = std::atoi(env);
   if (const char* env = std::getenv("RTB_POOL")) ctx->pool = std::atoi(env);
-  if (const char* env = std::getenv("RTB_COOP")) ctx->coop = std::atoi(env);
   if (const char* env = std::getenv("RTB_PACKET_CLOSEST")) ctx->packet_closest = std::atoi(env);
   if (const char* env = std::getenv("RTB_PACKET_SHADOW")) ctx->packet_shadow = std::atoi(env);
   if (const char* env = std::getenv("RTB_TAIL_MAX")) ctx->tail_max = (int32_t)std::max(0LL, std::atoll(env));

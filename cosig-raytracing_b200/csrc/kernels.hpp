@@ -39,10 +39,7 @@ void launch_raygen(int bvh, const FrameParams& f, const SceneView& s, const Queu
 // smem_bytes > 0 selects the shared-memory staged variant (grid = sm_count blocks of 1024 threads); it must have been
 // enabled for that size with traverse_enable_smem and equal traverse_smem_bytes(bvh, s).
 // mode: bit 0 = the closest-hit rays of `depth`, bit 1 = the shadow rays emitted at depth - 1.
-// coop: coop_scratch_bytes(grid) bytes of device memory private to the launching stream (the per-warp frontiers of the cooperative
-// finish, binary LBVH records in global memory), or nullptr to walk every ray serially to its end.
-void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int mode, int grid, size_t smem_bytes, void* coop, cudaStream_t st);
-size_t coop_scratch_bytes(int grid);
+void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int mode, int grid, size_t smem_bytes, cudaStream_t st);
 // Packet kernels (one warp walks the BVH once for 32 neighbouring rays).  launch_primary: ray generation + depth-0 traversal
 // fused, fills the depth-0 ray queue with the hits only (grid blocks of stream_block_threads() threads, one slot per thread and
 // iteration).  launch_packet: kind 0 = closest-hit rays of `depth`, kind 1 = shadow rays emitted at `depth`.

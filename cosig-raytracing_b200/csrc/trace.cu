@@ -266,116 +266,11 @@ __device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, 
   return false;
 }
 
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Cooperative finish (the end of every persistent launch).  Once the work list is exhausted no lane can be refilled, and a launch
-// lasts as long as its longest ray: ~350 dependent node visits at one L2 round trip each, walked by ONE lane while 31 idle
-// (profiles/r1e_timeline_k_traverse_c4.log: the queue of depth 0 runs dry long before the last warp finishes).  When a warp is down
-// to RTB_COOP_MAX live rays it therefore stops walking them lane by lane: for each, the owner spills its traversal stack into a
-// per-warp frontier in global scratch and ALL 32 lanes expand it — every round each lane pops one entry, tests a two-box record
-// (or a leaf's triangles), the warp merges the closest hit (min t, then min leaf index: closer_hit's rule, which is what makes the
-// result independent of this change of order) and pushes the surviving children back, far ones below near ones.  The ray's
-// remaining visits collapse into visits/32 rounds.  LBVH flavour, scene in global memory only: the reference flavour's tie
-// winners depend on its fixed order, so it keeps the serial walk.
-// ---------------------------------------------------------------------------------------------------------------------
-#define RTB_COOP_CAP 2048
-#ifndef RTB_COOP_MAX
-#define RTB_COOP_MAX 8
-#endif
-template <bool ANALYTIC>
-__device__ __noinline__ void coop_finish(const SceneView& s, const float4* nodes, const float4* tri_isect, Lane& L, const SlabRay& sr_own, int32_t& cur, int& sp,
-                                            const float2* stack, const int src, float2* fr, unsigned& overflow, unsigned& n_nodes, unsigned& n_tris) {
-  const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  // the ray and its state, from the owner lane
-  Lane R;
-  R.o = mk3(__shfl_sync(kFull, L.o.x, src), __shfl_sync(kFull, L.o.y, src), __shfl_sync(kFull, L.o.z, src));
-  R.d = mk3(__shfl_sync(kFull, L.d.x, src), __shfl_sync(kFull, L.d.y, src), __shfl_sync(kFull, L.d.z, src));
-  R.inv = mk3(0.0f, 0.0f, 0.0f);
-  R.item = 0; R.done = false;
-  R.shadow = __shfl_sync(kFull, L.shadow ? 1 : 0, src) != 0;
-  SlabRay sr;
-  sr.inv = mk3(__shfl_sync(kFull, sr_own.inv.x, src), __shfl_sync(kFull, sr_own.inv.y, src), __shfl_sync(kFull, sr_own.inv.z, src));
-  sr.ood_mn = mk3(__shfl_sync(kFull, sr_own.ood_mn.x, src), __shfl_sync(kFull, sr_own.ood_mn.y, src), __shfl_sync(kFull, sr_own.ood_mn.z, src));
-  sr.ood_mx = mk3(__shfl_sync(kFull, sr_own.ood_mx.x, src), __shfl_sync(kFull, sr_own.ood_mx.y, src), __shfl_sync(kFull, sr_own.ood_mx.z, src));
-  float bt = __shfl_sync(kFull, L.t, src), bu = __shfl_sync(kFull, L.u, src), bv = __shfl_sync(kFull, L.v, src);
-  int32_t btri = __shfl_sync(kFull, L.tri, src);
-  // the owner's deferred children and its current node / leaf become the frontier
-  int n_fr = 0;
-  if (lane == src) {
-    for (int i = 0; i < sp; i++) fr[i] = stack[i];
-    n_fr = sp;
-    if (cur != RTB_REF_DONE) fr[n_fr++] = make_float2(0.0f, __int_as_float(cur));
-  }
-  n_fr = __shfl_sync(kFull, n_fr, src);
-  __syncwarp();
-  bool occluded = false;
-  while (n_fr > 0) {
-    int take = n_fr < 32 ? n_fr : 32;
-    if (take > RTB_COOP_CAP - n_fr) take = RTB_COOP_CAP - n_fr;  // a round pushes at most two entries per popped one
-    if (take <= 0) { if (lane == 0) overflow++; break; }
-    const float2 e = lane < take ? fr[n_fr - 1 - lane] : make_float2(0.0f, 0.0f);
-    n_fr -= take;
-    __syncwarp();
-    const int32_t ref = __float_as_int(e.y);
-    const bool live = lane < take && !(e.x > bt);
-    bool hl = false, hr = false;
-    float dl = 0.0f, dr = 0.0f;
-    int32_t lref = 0, rref = 0;
-    R.t = bt; R.u = bu; R.v = bv; R.tri = btri;
-    bool occ = false;
-    if (live && ref >= 0) {
-      float4 n0, n1, n2, n3;
-      ld8<false>(&nodes[4 * (size_t)ref], n0, n1);
-      ld8<false>(&nodes[4 * (size_t)ref + 2], n2, n3);
-      hl = slab_hit(sr, mk3(n0), mk3(n1), bt, dl);
-      hr = slab_hit(sr, mk3(n2), mk3(n3), bt, dr);
-      lref = __float_as_int(n0.w); rref = __float_as_int(n1.w);
-      n_nodes++;
-    } else if (live) {
-      const int32_t code = ~ref;
-      const int32_t first = code >> 3, count = (code & 7) + 1;
-      n_tris += count;
-      for (int32_t i = 0; i < count && !occ; i++) occ = lane_test_triangle<false, ANALYTIC, true>(R, s, tri_isect, first + i);
-    }
-    if (R.shadow) {
-      if (__any_sync(kFull, occ)) { occluded = true; break; }
-    } else {
-      // closest hit of the round: min t, then min leaf index (closer_hit<true>); every lane carries the old best, so it takes part
-      const unsigned tmin = __reduce_min_sync(kFull, __float_as_uint(R.t));
-      const unsigned cand = __float_as_uint(R.t) == tmin ? (unsigned)R.tri : 0xffffffffu;
-      const unsigned trimin = __reduce_min_sync(kFull, cand);
-      const int winner = __ffs((int)__ballot_sync(kFull, __float_as_uint(R.t) == tmin && (unsigned)R.tri == trimin)) - 1;
-      bt = __uint_as_float(tmin);
-      btri = (int32_t)trimin;
-      bu = __shfl_sync(kFull, R.u, winner);
-      bv = __shfl_sync(kFull, R.v, winner);
-    }
-    // surviving children: the far ones first, the near ones on top (popped first next round)
-    const bool both = hl && hr, any = hl || hr;
-    const bool left_near = !(dr < dl);
-    const float d_near = both ? (left_near ? dl : dr) : (hl ? dl : dr);
-    const int32_t r_near = both ? (left_near ? lref : rref) : (hl ? lref : rref);
-    const unsigned bf = __ballot_sync(kFull, both), bn = __ballot_sync(kFull, any);
-    if (both) fr[n_fr + __popc(bf & lt)] = make_float2(left_near ? dr : dl, __int_as_float(left_near ? rref : lref));
-    if (any) fr[n_fr + __popc(bf) + __popc(bn & lt)] = make_float2(d_near, __int_as_float(r_near));
-    n_fr += __popc(bf) + __popc(bn);
-    __syncwarp();
-  }
-  if (lane == src) {
-    if (L.shadow) { if (occluded) L.tri = 0; }
-    else { L.t = bt; L.u = bu; L.v = bv; L.tri = btri; }
-    cur = RTB_REF_DONE;
-    sp = 0;
-    L.done = true;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // k_traverse, LBVH flavour: ordered traversal over 64-byte two-box nodes (see lbvh.cu for the layout).
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool SMEM, bool ANALYTIC>
-__global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB_TRAVERSE_MIN_BLOCKS) k_traverse_lbvh(const SceneView s, const QueueView q, const int depth, const int mode, float2* __restrict__ coop) {
+__global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB_TRAVERSE_MIN_BLOCKS) k_traverse_lbvh(const SceneView s, const QueueView q, const int depth, const int mode) {
   extern __shared__ float4 sm_scene[];
   const float4* nodes = s.nodes;
   const float4* tri_isect = s.tri_isect;
@@ -416,16 +311,7 @@ __global__ void __launch_bounds__(SMEM ? kBlockSmem : kTravBlock, SMEM ? 1 : RTB
   WorkPool pool;
   unsigned overflow = 0, n_nodes = 0, n_tris = 0;
 
-  float2* const frontier = (SMEM || coop == nullptr) ? nullptr : coop + ((size_t)blockIdx.x * (blockDim.x >> 5) + (size_t)(threadIdx.x >> 5)) * RTB_COOP_CAP;
   for (;;) {
-    // ---- the work list is dry and this warp is down to a few rays: finish them with all 32 lanes ----
-    if (!SMEM && frontier != nullptr && pool.exhausted) {
-      const unsigned live = __ballot_sync(kFull, L.item >= 0 && !L.done);
-      if (live != 0u && __popc(live) <= RTB_COOP_MAX) {
-        for (unsigned m = live; m != 0u; m &= m - 1u)
-          coop_finish<ANALYTIC>(s, nodes, tri_isect, L, sr, cur, sp, stack, __ffs((int)m) - 1, frontier, overflow, n_nodes, n_tris);
-      }
-    }
     // ---- publish finished lanes and refill, in batches ----
     const int n_out = __popc(__ballot_sync(kFull, L.item < 0 || L.done));
     if (n_out >= RefillMin<SMEM>::value) {
@@ -1531,9 +1417,7 @@ cudaError_t traverse_enable_smem(int bvh, size_t bytes) {
 
 // Scenes with analytic primitives (s.n_prims > 0) run the ANALYTIC instantiations; everything else keeps the leaner
 // triangle-only code.  The shared-memory variant exists for triangle-only scenes.
-size_t coop_scratch_bytes(int grid) { return (size_t)grid * (kTravBlock / 32) * RTB_COOP_CAP * sizeof(float2); }
-
-void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int mode, int grid, size_t smem_bytes, void* coop, cudaStream_t st) {
+void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth, int mode, int grid, size_t smem_bytes, cudaStream_t st) {
   const bool ref = bvh == RTB_BVH_REFERENCE;
   if (bvh == RTB_BVH_WIDE) {
     if (s.n_prims > 0) k_traverse_wide<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode);
@@ -1543,13 +1427,13 @@ void launch_traverse(int bvh, const SceneView& s, const QueueView& q, int depth,
   }
   if (s.n_prims > 0) {
     if (ref) k_traverse_ref<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode);
-    else k_traverse_lbvh<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode, (float2*)coop);
+    else k_traverse_lbvh<false, true><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode);
   } else if (smem_bytes > 0) {  // small scene: one 1024-thread block per SM works out of its shared-memory copy
     if (ref) k_traverse_ref<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth, mode);
-    else k_traverse_lbvh<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth, mode, nullptr);
+    else k_traverse_lbvh<true, false><<<grid, kBlockSmem, smem_bytes, st>>>(s, q, depth, mode);
   } else {
     if (ref) k_traverse_ref<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode);
-    else k_traverse_lbvh<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode, (float2*)coop);
+    else k_traverse_lbvh<false, false><<<grid, kTravBlock, 0, st>>>(s, q, depth, mode);
   }
 }
 
