@@ -67,7 +67,7 @@ struct Queues {
 };
 
 // A lane = a stream with its own wavefront queues.  Chunks (and, for asynchronous renders, whole frames) alternate between
-// the two lanes of a device, so the latency-bound tail of one chunk — a few very long rays — overlaps the bulk of the next.
+// the lanes of a device, so the latency-bound tail of one chunk — a few very long rays — overlaps the bulk of the next.
 struct LaneState {
   cudaStream_t stream = nullptr;
   Queues q;
@@ -211,7 +211,7 @@ void device_sync(DeviceState& d) {
   d.copy_pending = false;
 }
 
-// lane 0's stream (the one the host sees) waits for everything enqueued on lane 1
+// lane 0's stream (the one the host sees) waits for everything enqueued on the other lanes
 cudaError_t join_lanes(DeviceState& d) {
   for (int k = 1; k < DeviceState::kMaxLanes; k++)
     if (d.lane[k].used) {
@@ -461,7 +461,7 @@ int render_on_device(rtb_context* ctx, DeviceState& d, const FrameParams& f, voi
       if (ctx->profiling) cudaEventRecord(b, stream);
       launches++;
     };
-    // successive resolves may write the same pixels (frames in flight on both lanes): keep them in issue order
+    // successive resolves may write the same pixels (frames in flight on several lanes): keep them in issue order
     auto ordered_resolve = [&](auto&& launch) -> cudaError_t {
       cudaError_t e = cudaSuccess;
       if (d.resolve_pending) e = cudaStreamWaitEvent(stream, d.ev_resolve, 0);

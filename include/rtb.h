@@ -179,7 +179,7 @@ int rtb_get_stats(rtb_context* ctx, rtb_stats* out);
 int rtb_set_profiling(rtb_context* ctx, int32_t enable); /* per-kernel-family CUDA-event timing in rtb_stats */
 int rtb_set_cancel_flag(rtb_context* ctx, const volatile int32_t* flag); /* polled between wavefront depths */
 int rtb_synchronize(rtb_context* ctx);
-/* Asynchronous renders (rtb_render_device with sync == 0) rotate over a few internal streams per device (RTB_LANES, default 4)
+/* Asynchronous renders (rtb_render_device with sync == 0) rotate over a few internal streams per device (RTB_LANES, default 6)
  * so that successive chunks / frames overlap.  rtb_get_stream returns the primary stream (cudaStream_t) of device `index`;
  * rtb_flush makes that stream wait for everything enqueued so far on the others, so that an event the host records on it
  * afterwards (or work it orders behind it) covers all frames in flight. */
