@@ -60,7 +60,7 @@ cudaError_t pool_reserve(Pool& pl, T*& out, size_t bytes) {
 }
 
 struct Queues {
-  float4* base = nullptr;      // one allocation: 12 arrays of capacity slots
+  float4* base = nullptr;      // one allocation: RTB_QUEUE_BYTES_PER_SLOT bytes per slot (queue_view carves it)
   int32_t* counters = nullptr;
   unsigned long long* totals = nullptr;
   int32_t capacity = 0, depth_cap = 0;
@@ -129,7 +129,7 @@ struct rtb_context {
   bool profiling = false;
   int64_t chunk_slots_once = 0;  // rtb_render: chunk size of the frame being enqueued (a blocking frame is split over the lanes), 0 = chunk_slots
   int split_blocking = 1;        // RTB_SPLIT_BLOCKING: 0 = one chunk per blocking frame as long as it fits chunk_slots
-  int64_t chunk_slots = 1 << 24;  // RTB_CHUNK_SLOTS: pixel-samples per chunk (192 B of queues each, per lane); C5 sweep: profiles/r1e_sweep_chunk_slots_c5.log
+  int64_t chunk_slots = 1 << 24;  // RTB_CHUNK_SLOTS: pixel-samples per chunk (RTB_QUEUE_BYTES_PER_SLOT = 168 B of queues each, per lane); C5 sweep: profiles/r1e_sweep_chunk_slots_c5.log
   int n_lanes = 6;            // RTB_LANES (1..8): chunks / async frames rotate over this many streams, each with its own queues (4 -> 6: pipelined e2e +2.5 %, profiles/r2_sweep_lanes.log)
   uint64_t frame_id = 0;
   int smem_mode = 1;          // RTB_SMEM: 1 = stage nodes + triangles in shared memory when they fit (small scenes), 0 = never
@@ -247,7 +247,7 @@ int ensure_queues(rtb_context* ctx, LaneState& l, int32_t capacity, int32_t dept
   CK(ctx, cudaStreamSynchronize(l.stream));
   dfree(l.q.base); dfree(l.q.counters); dfree(l.q.totals);
   l.q = Queues();
-  CK(ctx, cudaMalloc(&l.q.base, (size_t)capacity * 12 * sizeof(float4)));
+  CK(ctx, cudaMalloc(&l.q.base, (size_t)capacity * RTB_QUEUE_BYTES_PER_SLOT));
   CK(ctx, cudaMalloc(&l.q.counters, (size_t)depth_cap * RTB_CNT_BLOCKS * sizeof(int32_t)));
   CK(ctx, cudaMalloc(&l.q.totals, RTB_TOTALS * sizeof(unsigned long long)));
   l.q.capacity = capacity;
@@ -260,10 +260,13 @@ QueueView queue_view(const Queues& q) {
   QueueView v;
   float4* p = q.base;
   const size_t c = (size_t)q.capacity;
-  v.ray_o[0] = p; v.ray_o[1] = p + c; v.ray_d[0] = p + 2 * c; v.ray_d[1] = p + 3 * c; v.ray_att[0] = p + 4 * c; v.ray_att[1] = p + 5 * c;
-  v.sh_o = p + 6 * c; v.sh_d = p + 7 * c; v.sh_lit = p + 8 * c; v.sh_unlit = p + 9 * c;
-  v.hits = p + 10 * c;
-  v.accum = p + 11 * c;
+  // nine float4 arrays, then three float2 arrays (capacity is a multiple of 32, so everything stays 16-byte aligned)
+  v.ray_o[0] = p; v.ray_o[1] = p + c; v.ray_d[0] = p + 2 * c; v.ray_d[1] = p + 3 * c;
+  v.sh_o = p + 4 * c; v.sh_d = p + 5 * c; v.sh_lit = p + 6 * c;
+  v.hits = p + 7 * c;
+  v.accum = p + 8 * c;
+  float2* h = (float2*)(p + 9 * c);
+  v.ray_a[0] = h; v.ray_a[1] = h + c; v.sh_un = h + 2 * c;
   v.counters = q.counters;
   v.totals = q.totals;
   v.depth_cap = q.depth_cap;
@@ -633,7 +636,7 @@ int collect_stats(rtb_context* ctx) {
   st.rays_traversed = entered + st.rays_continuation + st.rays_shadow;
   st.packet_node_fetches = pk_nodes;
   st.packet_tri_fetches = pk_tris;
-  st.bytes_per_slot = 12 * (int64_t)sizeof(float4);
+  st.bytes_per_slot = RTB_QUEUE_BYTES_PER_SLOT;
   cudaSetDevice(ctx->devs[0].device);
   return RTB_OK;
 }

@@ -129,12 +129,14 @@ struct SceneView {
 __host__ __device__ __forceinline__ int32_t lbvh_leaf_ref(int32_t first, int32_t count) { return ~((first << 3) | (count - 1)); }
 
 // Wavefront queues.
-// Ray queue entry: o = (origin, slot bits), d = (dir, 0), att = (attenuation, 0).
-// Shadow queue entry: o = (origin, distToLight), d = (dir, slot bits), lit / unlit = the two candidate increments of the
-// slot's sampleColor (BVHRayTracing.compute:418 evaluated for both outcomes of the shadow test).
+// Ray queue entry (40 B): o = (origin, slot bits), d = (dir, attenuation.x), a = (attenuation.y, attenuation.z).
+// Shadow queue entry (56 B): o = (origin, distToLight), d = (dir, slot bits), lit = (lit increment, unlit.x), un = (unlit.y, unlit.z):
+// the two candidate increments of the slot's sampleColor (BVHRayTracing.compute:418 evaluated for both outcomes of the shadow test).
+// No padding lanes are left: RTB_QUEUE_BYTES_PER_SLOT = 2 * 40 + 56 + 16 (hit record) + 16 (accumulator) = 168 (round 1: 192).
+#define RTB_QUEUE_BYTES_PER_SLOT 168
 struct QueueView {
-  float4* ray_o[2]; float4* ray_d[2]; float4* ray_att[2];
-  float4* sh_o; float4* sh_d; float4* sh_lit; float4* sh_unlit;
+  float4* ray_o[2]; float4* ray_d[2]; float2* ray_a[2];
+  float4* sh_o; float4* sh_d; float4* sh_lit; float2* sh_un;
   float4* hits;           // per ray-queue entry of the current depth: (t, u, v, leaf-order triangle index bits; -1 = miss)
   float4* accum;          // per slot: running sampleColor
   int32_t* counters;      // RTB_CNT_BLOCKS blocks of depth_cap ints: ray queue sizes | shadow queue sizes | traverse fetch | (spare)

@@ -223,7 +223,9 @@ __device__ __forceinline__ void lane_finish(Lane& L, const QueueView& q, int32_t
     __stcs(&q.hits[L.item], make_float4(L.t, L.u, L.v, __int_as_float(L.tri)));
   } else {  // lit <=> no occluder with Epsilon < t <= distToLight (compute:406)
     const int32_t j = L.item - n_closest;
-    const float4 inc = (L.tri == 0) ? __ldcs(&q.sh_unlit[j]) : __ldcs(&q.sh_lit[j]);
+    const float4 lit = __ldcs(&q.sh_lit[j]);  // (lit increment, unlit.x)
+    float3 inc = make_float3(lit.x, lit.y, lit.z);
+    if (L.tri == 0) { const float2 un = __ldcs(&q.sh_un[j]); inc = make_float3(lit.w, un.x, un.y); }
     const int32_t slot = __float_as_int(__ldcs(&q.sh_d[j]).w);
     const float4 prev = q.accum[slot];
     q.accum[slot] = make_float4(prev.x + inc.x, prev.y + inc.y, prev.z + inc.z, 0.0f);
@@ -954,8 +956,8 @@ __global__ void __launch_bounds__(kStreamBlock) k_primary(const FrameParams f, c
     if (found) {
       const int32_t at = first_at[0] + __popc(m[0] & below);
       __stcs(&q.ray_o[0][at], make_float4(ray.o.x, ray.o.y, ray.o.z, __int_as_float(slot)));
-      __stcs(&q.ray_d[0][at], make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f));
-      __stcs(&q.ray_att[0][at], make_float4(1.0f, 1.0f, 1.0f, 0.0f));
+      __stcs(&q.ray_d[0][at], make_float4(ray.d.x, ray.d.y, ray.d.z, 1.0f));
+      __stcs(&q.ray_a[0][at], make_float2(1.0f, 1.0f));
       __stcs(&q.hits[at], make_float4(L.t, L.u, L.v, __int_as_float(L.tri)));
     }
   }
@@ -1005,7 +1007,9 @@ __global__ void __launch_bounds__(kStreamBlock) k_packet(const SceneView s, cons
     if (valid) {
       if (kind == 0) __stcs(&q.hits[idx], make_float4(L.t, L.u, L.v, __int_as_float(L.tri)));
       else {
-        const float4 inc = (L.tri == 0) ? __ldcs(&q.sh_unlit[idx]) : __ldcs(&q.sh_lit[idx]);
+        const float4 lit = __ldcs(&q.sh_lit[idx]);
+        float3 inc = make_float3(lit.x, lit.y, lit.z);
+        if (L.tri == 0) { const float2 un = __ldcs(&q.sh_un[idx]); inc = make_float3(lit.w, un.x, un.y); }
         const float4 prev = q.accum[slot];
         q.accum[slot] = make_float4(prev.x + inc.x, prev.y + inc.y, prev.z + inc.z, 0.0f);
       }
@@ -1086,8 +1090,8 @@ __global__ void __launch_bounds__(kStreamBlock) k_raygen(const FrameParams f, co
     if (survives) {
       const int32_t at = first[0] + __popc(m[0] & below);
       __stcs(&q.ray_o[0][at], make_float4(ray.o.x, ray.o.y, ray.o.z, __int_as_float(slot)));
-      __stcs(&q.ray_d[0][at], make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f));
-      __stcs(&q.ray_att[0][at], make_float4(1.0f, 1.0f, 1.0f, 0.0f));
+      __stcs(&q.ray_d[0][at], make_float4(ray.d.x, ray.d.y, ray.d.z, 1.0f));
+      __stcs(&q.ray_a[0][at], make_float2(1.0f, 1.0f));
     }
   }
   for (int o = 16; o > 0; o >>= 1) n_valid += __shfl_xor_sync(kFull, n_valid, o);
@@ -1204,7 +1208,9 @@ __global__ void __launch_bounds__(kStreamBlock, RTB_SHADE_MIN_BLOCKS) k_shade(co
     f3 att = mk3(1.0f, 1.0f, 1.0f), prev = mk3(0.0f, 0.0f, 0.0f);
     Hit hit; hit.t = 0.0f; hit.u = 0.0f; hit.v = 0.0f; hit.tri = -1;
     if (active) {
-      const float4 o = __ldcs(&q.ray_o[in_q][idx]), d = __ldcs(&q.ray_d[in_q][idx]), a = __ldcs(&q.ray_att[in_q][idx]);
+      const float4 o = __ldcs(&q.ray_o[in_q][idx]), d = __ldcs(&q.ray_d[in_q][idx]);
+      const float2 a2 = __ldcs(&q.ray_a[in_q][idx]);
+      const float4 a = make_float4(d.w, a2.x, a2.y, 0.0f);
       const float4 hrec = __ldcs(&q.hits[idx]);
       slot = __float_as_int(o.w);
       ray.o = mk3(o); ray.d = mk3(d);
@@ -1244,14 +1250,14 @@ __global__ void __launch_bounds__(kStreamBlock, RTB_SHADE_MIN_BLOCKS) k_shade(co
       const int32_t at = b_sh + __popc(m_sh & below);
       __stcs(&q.sh_o[at], make_float4(o.sh_origin.x, o.sh_origin.y, o.sh_origin.z, o.sh_dist));
       __stcs(&q.sh_d[at], make_float4(o.sh_dir.x, o.sh_dir.y, o.sh_dir.z, __int_as_float(slot)));
-      __stcs(&q.sh_lit[at], make_float4(o.lit.x, o.lit.y, o.lit.z, 0.0f));
-      __stcs(&q.sh_unlit[at], make_float4(o.unlit.x, o.unlit.y, o.unlit.z, 0.0f));
+      __stcs(&q.sh_lit[at], make_float4(o.lit.x, o.lit.y, o.lit.z, o.unlit.x));
+      __stcs(&q.sh_un[at], make_float2(o.unlit.y, o.unlit.z));
     }
     if (o.emit_ray) {
       const int32_t at = b_nx + __popc(m_nx & below);
       __stcs(&q.ray_o[out_q][at], make_float4(o.start.x, o.start.y, o.start.z, __int_as_float(slot)));
-      __stcs(&q.ray_d[out_q][at], make_float4(o.dir.x, o.dir.y, o.dir.z, 0.0f));
-      __stcs(&q.ray_att[out_q][at], make_float4(o.att.x, o.att.y, o.att.z, 0.0f));
+      __stcs(&q.ray_d[out_q][at], make_float4(o.dir.x, o.dir.y, o.dir.z, o.att.x));
+      __stcs(&q.ray_a[out_q][at], make_float2(o.att.y, o.att.z));
     }
   }
 
@@ -1273,7 +1279,9 @@ __global__ void __launch_bounds__(kBlock) k_tail(const FrameParams f, const Scen
   const int in_q = depth0 & 1;
   unsigned n_hits = 0, n_cont = 0, n_shadow = 0, overflow = 0;
   for (int32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-    const float4 o4 = __ldcs(&q.ray_o[in_q][idx]), d4 = __ldcs(&q.ray_d[in_q][idx]), a4 = __ldcs(&q.ray_att[in_q][idx]);
+    const float4 o4 = __ldcs(&q.ray_o[in_q][idx]), d4 = __ldcs(&q.ray_d[in_q][idx]);
+    const float2 a2 = __ldcs(&q.ray_a[in_q][idx]);
+    const float4 a4 = make_float4(d4.w, a2.x, a2.y, 0.0f);
     const float4 hrec = __ldcs(&q.hits[idx]);
     const int32_t slot = __float_as_int(o4.w);
     Ray ray = make_ray(mk3(o4), mk3(d4));
