@@ -5,7 +5,8 @@
 // Pipeline (all on one stream, no host round trip):
 //   k_centroid_bounds   min/max of the triangle centroids (warp shuffles + one atomic per block and component)
 //   k_morton            63-bit Morton key (21 bits per axis, one scale: the centroids' bounding cube), value = emission index
-//   cub radix sort      keys + values
+//   k_sort_*            keys + values: stable LSD radix sort, 8 bits per pass (hand-written: histogram per tile, one scan of the
+//                       256 x tiles counts, stable scatter ranked with __match_any_sync); k_sort_check refuses an unsorted result
 //   k_hierarchy         Karras 2012 binary radix tree over the sorted keys (ties broken by index), parent links, ranges
 //   k_refit             bottom-up AABBs: each leaf thread climbs, the second arrival at a node merges its children
 //   k_emit / k_emit4    traversal records: every tree node whose range holds <= RTB_LEAF_MAX triangles collapses into a leaf
@@ -13,9 +14,6 @@
 //                       64-byte record carrying BOTH children's boxes (default); RTB_LBVH_WIDTH 4: every larger node of
 //                       even depth becomes a 128-byte record carrying its (up to) four grandchildren's boxes, compacted
 // The sorted value array is the leaf order (perm) used by launch_pack.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-
 #include "kernels.hpp"
 
 namespace rtb {
@@ -40,19 +38,20 @@ struct Workspace {
   int32_t* idx4;             // n-1: compact index of each emitted 4-wide node (exclusive scan of the emit flags)
   void* wide_queue[2];       // n-1 WideItem each: work lists of the wide collapse (one tree level per launch, ping-pong)
   int32_t* wide_counters;    // 4
-  void* cub_temp;
-  size_t cub_bytes;
+  unsigned long long* keys_tmp;  // n: ping-pong partner of keys_sorted
+  int32_t* vals_tmp;             // n: ping-pong partner of the caller's perm
+  int32_t* sort_hist;            // 256 * sort_tiles(n): digit counts per tile, digit-major; scanned in place
+  int32_t* scan_sums[3];         // block totals of the scan, one array per level
+  int32_t* sort_error;           // 1 int: set when the sorted keys are not ascending
 };
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-size_t cub_temp_bytes(int32_t n) {
-  size_t bytes = 0, scan = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const int32_t*)nullptr,
-                                  (int32_t*)nullptr, n, 0, 63);
-  cub::DeviceScan::ExclusiveSum(nullptr, scan, (const int32_t*)nullptr, (int32_t*)nullptr, n);
-  return bytes > scan ? bytes : scan;
-}
+// ---- sizes of the sort / scan scratch ----
+constexpr int kSortThreads = 256, kSortRounds = 16, kSortTile = kSortThreads * kSortRounds;  // keys per block and pass
+constexpr int kScanBlock = 1024;                                                              // elements per block of the scan
+inline int32_t sort_tiles(int32_t n) { return (n + kSortTile - 1) / kSortTile; }
+inline size_t scan_level_count(size_t n) { return (n + kScanBlock - 1) / kScanBlock; }
 
 Workspace carve(void* base, int32_t n) {
   char* p = (char*)base;
@@ -72,9 +71,108 @@ Workspace carve(void* base, int32_t n) {
   w.wide_queue[0] = take(ni * 8);
   w.wide_queue[1] = take(ni * 8);
   w.wide_counters = (int32_t*)take(16);
-  w.cub_bytes = cub_temp_bytes(n);
-  w.cub_temp = take(w.cub_bytes);
+  w.keys_tmp = (unsigned long long*)take(nt * 8);
+  w.vals_tmp = (int32_t*)take(nt * 4);
+  const size_t hist = 256 * (size_t)sort_tiles(n);
+  w.sort_hist = (int32_t*)take(hist * 4);
+  size_t level = scan_level_count(hist > ni ? hist : ni);
+  for (int k = 0; k < 3; k++) { w.scan_sums[k] = (int32_t*)take(level * 4); level = scan_level_count(level); }
+  w.sort_error = (int32_t*)take(4);
   return w;
+}
+
+
+// ---- exclusive prefix sum of int32 (hand-written; replaces a library scan) ------------------------------------------------------
+// Three phases per level: every block scans kScanBlock elements in shared memory and writes its total; the totals are scanned the
+// same way (recursively: three levels cover 2^30 elements); every block adds its offset.  In place is allowed (out == in).
+__global__ void __launch_bounds__(kScanBlock) k_scan_block(const int32_t* __restrict__ in, int32_t* __restrict__ out, int32_t n, int32_t* __restrict__ sums) {
+  __shared__ int32_t warp_total[kScanBlock / 32];
+  const int32_t i = blockIdx.x * kScanBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int32_t v = i < n ? in[i] : 0;
+  int32_t x = v;  // inclusive scan inside the warp
+  for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) warp_total[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int32_t t = warp_total[lane];
+    for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+    warp_total[lane] = t;  // inclusive over the warps
+  }
+  __syncthreads();
+  const int32_t before = warp == 0 ? 0 : warp_total[warp - 1];
+  if (i < n) out[i] = before + x - v;
+  if (threadIdx.x == kScanBlock - 1 && sums) sums[blockIdx.x] = before + x;
+}
+__global__ void __launch_bounds__(kScanBlock) k_scan_add(int32_t* __restrict__ out, int32_t n, const int32_t* __restrict__ sums) {
+  const int32_t i = blockIdx.x * kScanBlock + threadIdx.x;
+  if (i < n && blockIdx.x > 0) out[i] += sums[blockIdx.x];
+}
+void exclusive_scan(const int32_t* in, int32_t* out, int32_t n, int32_t* const (&sums)[3], int level, cudaStream_t st) {
+  if (n <= 0) return;
+  const int32_t blocks = (int32_t)scan_level_count((size_t)n);
+  k_scan_block<<<blocks, kScanBlock, 0, st>>>(in, out, n, blocks > 1 ? sums[level] : nullptr);
+  if (blocks > 1) {
+    exclusive_scan(sums[level], sums[level], blocks, sums, level + 1, st);  // level <= 2: 1024^3 elements
+    k_scan_add<<<blocks, kScanBlock, 0, st>>>(out, n, sums[level]);
+  }
+}
+
+// ---- stable LSD radix sort of (63-bit key, int32 value) pairs, 8 bits per pass (hand-written; replaces a library sort) -----------
+// A block owns a tile of kSortTile consecutive keys.  k_sort_hist counts the tile's digits; one exclusive scan over the digit-major
+// table hist[digit][tile] turns the counts into each (digit, tile)'s first output position; k_sort_scatter walks the tile again in
+// kSortRounds rounds of 256 keys and places every key at base[digit] + (keys of that digit in earlier rounds) + (in earlier warps of
+// this round) + (in earlier lanes of this warp) — earlier in every sense that the input order defines, hence stable, which is what
+// makes the value (the triangle's emission index) the tie-break of equal Morton keys.
+__global__ void __launch_bounds__(kSortThreads) k_sort_hist(const unsigned long long* __restrict__ keys, int32_t n, int shift, int32_t tiles, int32_t* __restrict__ hist) {
+  __shared__ int32_t count[256];
+  count[threadIdx.x] = 0;
+  __syncthreads();
+  const int32_t base = blockIdx.x * kSortTile;
+  for (int r = 0; r < kSortRounds; r++) {
+    const int32_t i = base + r * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&count[(unsigned)(keys[i] >> shift) & 255u], 1);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * tiles + blockIdx.x] = count[threadIdx.x];
+}
+__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, int32_t n, int shift,
+                                                               int32_t tiles, const int32_t* __restrict__ first, unsigned long long* __restrict__ keys_out,
+                                                               int32_t* __restrict__ vals_out) {
+  __shared__ int32_t running[256];                      // position of the next key of each digit
+  __shared__ int32_t warp_count[kSortThreads / 32][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  running[threadIdx.x] = first[(size_t)threadIdx.x * tiles + blockIdx.x];
+  const int32_t base = blockIdx.x * kSortTile;
+  for (int r = 0; r < kSortRounds; r++) {
+    for (int w = 0; w < kSortThreads / 32; w++) warp_count[w][threadIdx.x] = 0;
+    __syncthreads();
+    const int32_t i = base + r * kSortThreads + threadIdx.x;
+    const bool valid = i < n;
+    const unsigned long long key = valid ? keys[i] : 0ull;
+    const unsigned digit = valid ? (unsigned)(key >> shift) & 255u : 256u + (unsigned)lane;  // padding lanes match nobody
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank_in_warp == 0) warp_count[warp][digit] = __popc(peers);
+    __syncthreads();
+    if (valid) {
+      int32_t at = running[digit] + rank_in_warp;
+      for (int w = 0; w < warp; w++) at += warp_count[w][digit];
+      keys_out[at] = key;
+      vals_out[at] = vals[i];
+    }
+    __syncthreads();
+    int32_t total = 0;
+    for (int w = 0; w < kSortThreads / 32; w++) total += warp_count[w][threadIdx.x];
+    running[threadIdx.x] += total;
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(kBlock) k_sort_check(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, int32_t n, int32_t* error) {
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long a = keys[i], b = keys[i + 1];
+    if (a > b || (a == b && vals[i] >= vals[i + 1])) atomicExch(error, 1);  // ascending keys, ties in input order
+  }
 }
 
 __global__ void k_init_bounds(unsigned* bounds) {
@@ -473,11 +571,19 @@ inline int grid_for(int64_t n) {
 
 }  // namespace
 
+static size_t sort_scratch_bytes(int32_t n) {
+  const size_t nt = (size_t)n, ni = (size_t)(n > 1 ? n - 1 : 1), hist = 256 * (size_t)sort_tiles(n);
+  size_t total = align_up(nt * 8) + align_up(nt * 4) + align_up(hist * 4) + align_up(4);
+  size_t level = scan_level_count(hist > ni ? hist : ni);
+  for (int k = 0; k < 3; k++) { total += align_up(level * 4); level = scan_level_count(level); }
+  return total;
+}
+
 size_t lbvh_workspace_bytes(int32_t n) {
   if (n <= 0) return 256;
   const size_t ni = (size_t)(n > 1 ? n - 1 : 1), nt = (size_t)n, na = 2 * nt;
   return align_up(24) + 2 * align_up(nt * 8) + align_up(nt * 4) + 2 * align_up(ni * 8) + align_up(na * 4) + align_up(ni * 4) +
-         align_up(na * 2 * sizeof(float4)) + align_up(ni * 4) + 2 * align_up(ni * 8) + align_up(16) + align_up(cub_temp_bytes(n)) + 256;
+         align_up(na * 2 * sizeof(float4)) + align_up(ni * 4) + 2 * align_up(ni * 8) + align_up(16) + sort_scratch_bytes(n) + 256;
 }
 
 cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaStream_t st, bool wide) {
@@ -486,10 +592,29 @@ cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaS
   k_init_bounds<<<1, 32, 0, st>>>(w.bounds);
   k_centroid_bounds<<<grid_for(n), kBlock, 0, st>>>(raw, n, w.bounds);
   k_morton<<<grid_for(n), kBlock, 0, st>>>(raw, n, w.bounds, w.keys, w.vals);
-  size_t temp = w.cub_bytes;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_temp, temp, (const unsigned long long*)w.keys, w.keys_sorted, (const int32_t*)w.vals,
-                                                  b.perm, n, 0, 63, st);
+  // eight stable passes of eight bits; the buffers ping-pong so that the last pass lands in (keys_sorted, perm)
+  cudaError_t e = cudaMemsetAsync(w.sort_error, 0, sizeof(int32_t), st);
   if (e != cudaSuccess) return e;
+  {
+    const int32_t tiles = sort_tiles(n);
+    const unsigned long long* kin = w.keys;
+    const int32_t* vin = w.vals;
+    for (int pass = 0; pass < 8; pass++) {
+      unsigned long long* kout = (pass & 1) ? w.keys_sorted : w.keys_tmp;
+      int32_t* vout = (pass & 1) ? b.perm : w.vals_tmp;
+      k_sort_hist<<<tiles, kSortThreads, 0, st>>>(kin, n, 8 * pass, tiles, w.sort_hist);
+      exclusive_scan(w.sort_hist, w.sort_hist, 256 * tiles, w.scan_sums, 0, st);
+      k_sort_scatter<<<tiles, kSortThreads, 0, st>>>(kin, vin, n, 8 * pass, tiles, w.sort_hist, kout, vout);
+      kin = kout;
+      vin = vout;
+    }
+    k_sort_check<<<grid_for(n), kBlock, 0, st>>>(w.keys_sorted, b.perm, n, w.sort_error);
+    int32_t bad = 0;
+    e = cudaMemcpyAsync(&bad, w.sort_error, sizeof bad, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    if (bad) return cudaErrorAssert;  // never build a hierarchy over keys that are not sorted
+  }
   if (n > 1) {
     e = cudaMemsetAsync(w.flag, 0, (size_t)(n - 1) * 4, st);
     if (e != cudaSuccess) return e;
@@ -528,17 +653,13 @@ cudaError_t lbvh_build(const float4* raw, int32_t n, const LbvhBuffers& b, cudaS
 #if RTB_LBVH_WIDTH == 4
   if (n > 1) {
     k_mark4<<<grid_for(n - 1), kBlock, 0, st>>>(n, w.range, w.parent, w.flag);
-    temp = w.cub_bytes;
-    e = cub::DeviceScan::ExclusiveSum(w.cub_temp, temp, (const int32_t*)w.flag, w.idx4, n - 1, st);
-    if (e != cudaSuccess) return e;
+    exclusive_scan(w.flag, w.idx4, n - 1, w.scan_sums, 0, st);
   }
   k_emit4<<<grid_for(n > 1 ? n - 1 : 1), kBlock, 0, st>>>(n, w.child, w.range, w.box, w.bounds, w.flag, w.idx4, b.nodes, b.root_out);
 #else
   if (n > 1) {  // w.flag has done its job in k_refit: reuse it for the live flags
     k_mark_live<<<grid_for(n - 1), kBlock, 0, st>>>(n, w.range, w.flag);
-    temp = w.cub_bytes;
-    e = cub::DeviceScan::ExclusiveSum(w.cub_temp, temp, (const int32_t*)w.flag, w.idx4, n - 1, st);
-    if (e != cudaSuccess) return e;
+    exclusive_scan(w.flag, w.idx4, n - 1, w.scan_sums, 0, st);
   }
   k_emit<<<grid_for(n > 1 ? n - 1 : 1), kBlock, 0, st>>>(n, w.child, w.range, w.box, w.bounds, w.flag, w.idx4, b.nodes, b.root_out);
 #endif
