@@ -6,7 +6,7 @@ from util import abi, params, scene_mod, synth, tiny_scene
 rt_mod = importlib.import_module("cosig-raytracing_b200.raytracer")
 
 def run(tag, env, mode, prim, obj, p):
-    for k in ("RTB_TAIL_MAX", "RTB_SMEM", "RTB_CHUNK_SLOTS", "RTB_LANES"):
+    for k in ("RTB_TAIL_MAX", "RTB_SMEM", "RTB_CHUNK_SLOTS", "RTB_LANES", "RTB_WIDE", "RTB_POOL", "RTB_PACKET_CLOSEST", "RTB_PACKET_SHADOW"):
         os.environ.pop(k, None)
     os.environ.update(env)
     rt = rt_mod.RayTracer(bvh_mode=mode, primitive_mode=prim)
@@ -30,6 +30,31 @@ for mode in (abi.RTB_BVH_REFERENCE, abi.RTB_BVH_LBVH):
     run(f"analytic mode{mode}", {"RTB_TAIL_MAX": "2000"}, mode, 1, s1, params(96, 64, 4, soft_shadows=1, light_size=2.0, glossy=1, roughness=0.1))
     run(f"heightfield mode{mode}", {}, mode, 0, hf, params(128, 72, 6))
     run(f"tiny mode{mode}", {}, mode, 0, tiny_scene(1), params(33, 17, 2, debug_mode=2))
+# round 2: the optional traversal kernels (packets on both flavours, 8-wide quantised records, the regrouping pool), each against
+# the default kernel's frame, and the hand-written radix sort / scan / dense emit on a scene large enough for several tiles
+want = rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH)
+ref_frame = want.RenderAsync(hf, params(128, 72, 6)).pixels
+want.close()
+for tag, env, mode in (("packets lbvh", {"RTB_PACKET_CLOSEST": "16", "RTB_PACKET_SHADOW": "16", "RTB_SMEM": "0"}, abi.RTB_BVH_LBVH),
+                       ("packets reference", {"RTB_PACKET_CLOSEST": "1", "RTB_PACKET_SHADOW": "0"}, abi.RTB_BVH_REFERENCE),
+                       ("wide records", {"RTB_WIDE": "1", "RTB_SMEM": "0"}, abi.RTB_BVH_LBVH),
+                       ("wide records smem", {"RTB_WIDE": "1", "RTB_SMEM": "1"}, abi.RTB_BVH_LBVH),
+                       ("pool", {"RTB_POOL": "1", "RTB_SMEM": "0"}, abi.RTB_BVH_LBVH)):
+    run(tag, env, mode, 0, hf, params(128, 72, 6))
+    run(tag + " analytic", env, mode, 1, s1, params(96, 64, 4))
+for k in ("RTB_WIDE", "RTB_POOL", "RTB_PACKET_CLOSEST", "RTB_PACKET_SHADOW", "RTB_SMEM"):
+    os.environ.pop(k, None)
+big = synth.heightfield_scene(150, 60)   # 18 000 triangles: five sort tiles, two scan levels of the digit table
+run("own sort, 5 tiles", {}, abi.RTB_BVH_LBVH, 0, big, params(96, 54, 3))
+# group ring of one rank and the external-memory path are exercised by the GPU tests (they need a second process / cuda-python)
+rt = rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH)
+rt.group_create(0, 1, 96 * 64 * 4, 2)
+outs = [np.zeros((64, 96, 4), np.uint8) for _ in range(4)]
+for t in [rt.GroupRenderBegin(s1, params(96, 64, 3), o) for o in outs]:
+    rt.GroupRenderEnd(t)
+assert all((o == outs[0]).all() for o in outs)
+rt.close()
+print("group of one ok", flush=True)
 # GIF sweep: palette kernel (vector and scalar paths), indexed pipelined readback, fused rotation call
 gif = importlib.import_module("cosig-raytracing_b200.gif_generator")
 rt = rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH)
