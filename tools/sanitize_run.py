@@ -1,4 +1,6 @@
-"""Small renders through every kernel variant, for compute-sanitizer (memcheck) — keep it tiny: the tool slows kernels ~50x."""
+"""Small renders through every kernel variant.  Written for compute-sanitizer (memcheck; keep it tiny: the tool slows kernels ~50x);
+where the sanitizer is not available it still is a functional sweep: every optional traversal kernel must reproduce the default
+kernel's frame and primary hits, and pipelined frames must equal blocking ones."""
 import importlib, os, sys
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np
@@ -16,10 +18,12 @@ def run(tag, env, mode, prim, obj, p):
     for t in ts:
         rt.RenderEnd(t)
     assert all((o == a).all() for o in out), tag
-    rt.primary_hits(obj, p)
+    hits = rt.primary_hits(obj, p)
     st = rt.stats()
+    assert st.reserved[0] == 0, (tag, "traversal stack overflow")
     rt.close()
     print(tag, "ok", st.rays_primary, st.rays_continuation, st.rays_shadow, flush=True)
+    return a, hits
 
 s1 = synth.sample_scene("test_scene_1")
 hf = synth.heightfield_scene(40, 20)
@@ -32,15 +36,16 @@ for mode in (abi.RTB_BVH_REFERENCE, abi.RTB_BVH_LBVH):
     run(f"tiny mode{mode}", {}, mode, 0, tiny_scene(1), params(33, 17, 2, debug_mode=2))
 # round 2: the optional traversal kernels (packets on both flavours, 8-wide quantised records, the regrouping pool), each against
 # the default kernel's frame, and the hand-written radix sort / scan / dense emit on a scene large enough for several tiles
-want = rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH)
-ref_frame = want.RenderAsync(hf, params(128, 72, 6)).pixels
-want.close()
+ref_frame, ref_hits = run("default lbvh", {"RTB_SMEM": "0"}, abi.RTB_BVH_LBVH, 0, hf, params(128, 72, 6))
 for tag, env, mode in (("packets lbvh", {"RTB_PACKET_CLOSEST": "16", "RTB_PACKET_SHADOW": "16", "RTB_SMEM": "0"}, abi.RTB_BVH_LBVH),
                        ("packets reference", {"RTB_PACKET_CLOSEST": "1", "RTB_PACKET_SHADOW": "0"}, abi.RTB_BVH_REFERENCE),
                        ("wide records", {"RTB_WIDE": "1", "RTB_SMEM": "0"}, abi.RTB_BVH_LBVH),
                        ("wide records smem", {"RTB_WIDE": "1", "RTB_SMEM": "1"}, abi.RTB_BVH_LBVH),
                        ("pool", {"RTB_POOL": "1", "RTB_SMEM": "0"}, abi.RTB_BVH_LBVH)):
-    run(tag, env, mode, 0, hf, params(128, 72, 6))
+    frame, hits = run(tag, env, mode, 0, hf, params(128, 72, 6))
+    if mode == abi.RTB_BVH_LBVH:  # order-independent closest hit (closer_hit's tie rule): identical t bits and ids, identical frame
+        assert (hits[1].view(np.uint32) == ref_hits[1].view(np.uint32)).all() and (hits[0] == ref_hits[0]).all(), tag
+        assert (frame == ref_frame).mean() > 0.9999, tag
     run(tag + " analytic", env, mode, 1, s1, params(96, 64, 4))
 for k in ("RTB_WIDE", "RTB_POOL", "RTB_PACKET_CLOSEST", "RTB_PACKET_SHADOW", "RTB_SMEM"):
     os.environ.pop(k, None)
