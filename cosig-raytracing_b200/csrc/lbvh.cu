@@ -505,6 +505,10 @@ __global__ void __launch_bounds__(128) k_wide_level(int32_t n, const int2* __res
           if (c > bc) { bc = c; bs = sidx; bk = k; }
         }
       }
+      if (bs < 0) {  // every remaining cost compared false (NaN coordinates): any free slot and any remaining child will do
+        for (int sidx = 0; sidx < 8 && bs < 0; sidx++) if (child_of_slot[sidx] < 0) bs = sidx;
+        for (int k = 0; k < ns && bk < 0; k++) if (!(child_done & (1u << k))) bk = k;
+      }
       child_of_slot[bs] = bk;
       child_done |= 1u << bk;
     }
