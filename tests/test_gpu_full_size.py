@@ -347,3 +347,16 @@ def test_group_of_one_equals_render_begin(samples_scene2):
                 rt.GroupRenderEnd(t)
     finally:
         del _os.environ["RTB_GROUP_TIMEOUT_MS"]
+
+
+# ---- every optional traversal kernel reproduces the default one ---------------------------------------------------------------------------
+def test_optional_kernels_reproduce_the_default_kernel():
+    """tools/sanitize_run.py: small renders through every kernel variant — wavefront / tail / shared-memory schedules in both BVH modes, the
+    packet kernels on both flavours, the 8-wide quantised records (global and shared memory), the regrouping pool, analytic primitives
+    under each, the hand-written sort on several tiles, a group of one, the GIF path — asserting identical primary t bits / ids and
+    frames against the default LBVH kernel, pipelined frames equal to blocking ones, and no traversal-stack overflow."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize_run.py")], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "sanitize run complete" in r.stdout
+    for tag in ("packets lbvh ok", "packets reference ok", "wide records ok", "wide records smem ok", "pool ok", "own sort, 5 tiles ok", "group of one ok"):
+        assert tag in r.stdout, tag
