@@ -85,7 +85,7 @@ struct DeviceState {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_done = nullptr;  // scene upload timing / cross-device completion
   cudaEvent_t ev_resolve = nullptr;  // orders the resolve kernels of successive chunks / frames (they may share pixels)
   bool resolve_pending = false;
-  static constexpr int kMaxLanes = 8;
+  static constexpr int kMaxLanes = 16;
   LaneState lane[kMaxLanes];
   int next_lane = 0;
   int last_lane = 0;              // lane of the last chunk enqueued (where a frame's readback is ordered)
