@@ -1166,6 +1166,7 @@ int rtb_group_create(rtb_context* ctx, int32_t rank, int32_t world, size_t frame
   group_release(ctx);
   rtb_context::Group& g = ctx->group;
   CK(ctx, cudaSetDevice(ctx->devs[0].device));
+  g.active = true;  // from here on a failing call leaves a group that rtb_group_destroy / rtb_destroy cleans up
   g.rank = rank; g.world = world; g.n_buf = n_buffers; g.frame_bytes = frame_bytes;
   g.stride = (frame_bytes + 255) & ~(size_t)255;
   const size_t flag_bytes = 4096;
@@ -1191,7 +1192,6 @@ int rtb_group_create(rtb_context* ctx, int32_t rank, int32_t world, size_t frame
   CK(ctx, cudaEventCreateWithFlags(&g.gate_done, cudaEventDisableTiming));
   if (const char* env = std::getenv("RTB_GROUP_TIMEOUT_MS")) g.timeout_ns = (unsigned long long)std::max(1LL, std::atoll(env)) * 1000000ull;
   g.seq = 0;
-  g.active = true;
   return RTB_OK;
 }
 
@@ -1204,7 +1204,7 @@ int rtb_group_destroy(rtb_context* ctx) {
 int rtb_group_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* ticket) {
   if (!ctx || !p || !ticket) return fail(ctx, RTB_E_ARG, "null argument");
   rtb_context::Group& g = ctx->group;
-  if (!g.active) return fail(ctx, RTB_E_ARG, "no group (rtb_group_create)");
+  if (!g.active || !g.base || !g.error || !g.gate || !g.gate_done) return fail(ctx, RTB_E_ARG, "no group (rtb_group_create)");
   if (!ctx->has_scene) return fail(ctx, RTB_E_NOSCENE, "no scene uploaded (rtb_upload_scene)");
   rtb_render_params pp = *p;
   pp.band_rank = g.rank; pp.band_world = g.world; pp.out_layout = RTB_OUT_FRAME;
