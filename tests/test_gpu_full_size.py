@@ -360,3 +360,84 @@ def test_optional_kernels_reproduce_the_default_kernel():
     assert "sanitize run complete" in r.stdout
     for tag in ("packets lbvh ok", "packets reference ok", "wide records ok", "wide records smem ok", "pool ok", "own sort, 5 tiles ok", "group of one ok"):
         assert tag in r.stdout, tag
+
+
+# ---- structure of the GPU-built hierarchies ---------------------------------------------------------------------------------------------
+def _leaf_range(ref):
+    code = ~int(ref)
+    return code >> 3, (code & 7) + 1
+
+
+def _check_tree(nodes_u32, nodes_f32, perm, tri_min, tri_max, wide):
+    """Walks the records from the root: every triangle is referenced by exactly one leaf, every child box contains the triangles
+    (leaf) or the child boxes (inner node) below it, every record is reached exactly once.  Returns (records reached, max depth)."""
+    n_tris = len(perm)
+    covered = np.zeros(n_tris, np.int32)
+    reached = np.zeros(len(nodes_u32), np.int32)
+
+    def children(i):
+        """[(ref, box_min[3], box_max[3])] of record i."""
+        if not wide:
+            f, u = nodes_f32[i], nodes_u32[i]
+            return [(np.int32(u[3]), f[0:3], f[4:7]), (np.int32(u[7]), f[8:11], f[12:15])]
+        f, u = nodes_f32[i], nodes_u32[i]
+        p = f[0:3].astype(np.float64)
+        hdr = int(u[3])
+        cell = np.array([2.0 ** (((hdr >> (8 * a)) & 255) - 127 - 15) for a in range(3)])
+        valid = hdr >> 24
+        refs = np.concatenate([u[4:8], u[20:24]]).astype(np.uint32).view(np.int32)
+        q = u[8:20].astype(np.uint32).view(np.uint8).reshape(6, 8)  # lo.x lo.y lo.z hi.x hi.y hi.z, one byte per slot
+        out = []
+        for s in range(8):
+            if not (valid >> s) & 1:
+                assert refs[s] == np.int32(-2 ** 31), "an empty slot must carry the DONE reference"
+                continue
+            lo = p + q[0:3, s] * cell
+            hi = p + q[3:6, s] * cell
+            out.append((refs[s], lo, hi))
+        return out
+
+    stack = [(0, None, None, 1)]
+    max_depth = 0
+    while stack:
+        i, bmin, bmax, depth = stack.pop()
+        max_depth = max(max_depth, depth)
+        reached[i] += 1
+        for ref, lo, hi in children(i):
+            lo64, hi64 = np.asarray(lo, np.float64), np.asarray(hi, np.float64)
+            assert (lo64 <= hi64).all()
+            if bmin is not None:  # nested in the box its parent holds for this record (quantisation may only grow boxes by a cell)
+                slack = 1e-4 * (1.0 + np.abs(bmax - bmin).max())
+                assert (lo64 >= bmin - slack).all() and (hi64 <= bmax + slack).all(), f"record {i}: child box leaves its parent's box"
+            if ref < 0:
+                first, count = _leaf_range(ref)
+                assert 1 <= count <= 4 and first + count <= n_tris
+                ids = perm[first:first + count]
+                covered[first:first + count] += 1
+                assert (tri_min[ids] >= lo64 - 1e-9).all() and (tri_max[ids] <= hi64 + 1e-9).all(), f"record {i}: a leaf's triangle sticks out of its box"
+            else:
+                stack.append((int(ref), lo64, hi64, depth + 1))
+    assert (covered == 1).all(), f"{(covered != 1).sum()} triangles are not referenced exactly once"
+    assert (reached == 1).all(), f"{(reached != 1).sum()} records are not reached exactly once (the array must be dense)"
+    return int(reached.sum()), max_depth
+
+
+@pytest.mark.parametrize("wide", ["0", "1"])
+@pytest.mark.parametrize("scene_name", ["heightfield", "test_scene_2"])
+def test_gpu_built_hierarchy_is_a_valid_bvh(scene_name, wide, monkeypatch):
+    """K2: the tree the GPU builds — Morton keys, the hand-written radix sort, Karras hierarchy, refit, and either the dense binary
+    two-box records or the 8-wide quantised records — bounds every triangle, references each exactly once, and has no dead records."""
+    monkeypatch.setenv("RTB_WIDE", wide)
+    obj = synth.heightfield_scene(200, 100) if scene_name == "heightfield" else synth.sample_scene(scene_name)
+    with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as rt:
+        rt.RenderAsync(obj, params(64, 48, 2))
+        nodes, perm = rt.bvh()
+        vn, _ = rt.triangles()
+    assert nodes.shape[1] == (24 if wide == "1" else 16)
+    assert sorted(perm.tolist()) == list(range(len(perm))), "perm is not a permutation of the triangles"
+    v = vn[:, :9].reshape(-1, 3, 3).astype(np.float64)
+    reached, depth = _check_tree(nodes.view(np.uint32), nodes, perm, v.min(axis=1), v.max(axis=1), wide == "1")
+    assert reached == len(nodes)
+    # the wide tree is shallower and smaller than the binary one
+    if wide == "1":
+        assert len(nodes) < len(perm) / 8 and depth <= 16
