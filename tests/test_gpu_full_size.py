@@ -397,6 +397,10 @@ def _check_tree(nodes_u32, nodes_f32, perm, tri_min, tri_max, wide):
             out.append((refs[s], lo, hi))
         return out
 
+    def grid_cell(i):
+        hdr = int(nodes_u32[i][3])
+        return max(2.0 ** (((hdr >> (8 * a)) & 255) - 127 - 15) for a in range(3))
+
     stack = [(0, None, None, 1)]
     max_depth = 0
     while stack:
@@ -406,8 +410,8 @@ def _check_tree(nodes_u32, nodes_f32, perm, tri_min, tri_max, wide):
         for ref, lo, hi in children(i):
             lo64, hi64 = np.asarray(lo, np.float64), np.asarray(hi, np.float64)
             assert (lo64 <= hi64).all()
-            if bmin is not None:  # nested in the box its parent holds for this record (quantisation may only grow boxes by a cell)
-                slack = 1e-4 * (1.0 + np.abs(bmax - bmin).max())
+            if bmin is not None:  # nested in the box its parent holds for this record; a wide record rounds its children outward on ITS grid, so they may stick out by one of its cells
+                slack = 1e-4 * (1.0 + np.abs(bmax - bmin).max()) + (grid_cell(i) if wide else 0.0)
                 assert (lo64 >= bmin - slack).all() and (hi64 <= bmax + slack).all(), f"record {i}: child box leaves its parent's box"
             if ref < 0:
                 first, count = _leaf_range(ref)
