@@ -146,6 +146,8 @@ SYMBOLS = {
     "rtb_group_render_begin": (C.c_int, [_VP, C.POINTER(RenderParams), _VP, C.c_size_t, C.POINTER(C.c_int32)]),
     "rtb_group_render_end": (C.c_int, [_VP, C.c_int32]),
     "rtb_group_destroy": (C.c_int, [_VP]),
+    "rtb_group_create_host": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_size_t, C.c_int32, C.c_char_p]),
+    "rtb_group_frame": (C.c_int, [_VP, C.c_int32, C.POINTER(C.c_void_p)]),
     "rtb_external_import": (C.c_int, [_VP, C.c_int32, _VP, C.c_size_t, C.c_int32, C.POINTER(_VP)]),
     "rtb_external_release": (C.c_int, [_VP, _VP]),
     "rtb_frame_read": (C.c_int, [_VP, _VP, C.c_size_t]),

@@ -16,6 +16,12 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
 #include "gif.hpp"
 #include "kernels.hpp"
 
@@ -153,6 +159,14 @@ struct rtb_context {
     static constexpr int kTickets = 16;
     cudaEvent_t ticket[kTickets] = {};
     unsigned long long timeout_ns = 10000000000ull;
+    // host ring (rtb_group_create_host): the frames lie in POSIX shared memory that every rank has page-locked; each rank copies
+    // its own bands there over its own PCIe link, the flags are words of the same mapping
+    bool host = false;
+    uint8_t* hbase = nullptr;     // mmap of the shared object: one 4096-byte header, then n_buf frames of `stride` bytes
+    uint8_t* hdev = nullptr;      // the same bytes as this device addresses them
+    size_t hbytes = 0;
+    bool registered = false;
+    std::string shm_name;
   } group;
   struct External { cudaExternalMemory_t mem; void* ptr; size_t bytes; };
   std::vector<External> externals;  // rtb_external_import: graphics-API allocations mapped into device 0's address space
@@ -644,6 +658,38 @@ int collect_stats(rtb_context* ctx) {
 }  // namespace
 
 namespace {
+// Header of the host ring (first 4096 bytes of the shared object).  Every field is written by exactly one party: rank 0 writes
+// the shape once (magic last) and `begun0`; `done[rank * 8 + buffer]` is written by that rank's device (group.cu: k_group_post,
+// ordered behind the copy of its bands on its copy stream).  Sequence numbers are compared as signed differences.
+struct HostRingHeader {
+  uint32_t magic, world, n_buf, reserved;
+  uint64_t frame_bytes, stride;
+  alignas(64) uint32_t begun0;     // frames rank 0 has begun: slot k % n_buf may be overwritten with frame k once begun0 > k
+  alignas(64) uint32_t done[32 * 8];
+};
+static_assert(sizeof(HostRingHeader) <= 4096, "the header is one page");
+constexpr uint32_t kHostRingMagic = 0x52544248u;  // "RTBH"
+constexpr size_t kHostRingHeaderBytes = 4096;
+
+unsigned long long monotonic_ns() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+
+// Host-side wait on a word of the shared header: spins briefly, then yields; false after timeout_ns.
+bool host_wait_reached(const uint32_t* word, uint32_t target, unsigned long long timeout_ns) {
+  const unsigned long long t0 = monotonic_ns();
+  for (unsigned spins = 0;; spins++) {
+    if ((int32_t)(__atomic_load_n(word, __ATOMIC_ACQUIRE) - target) >= 0) return true;
+    if (spins > 2000) {
+      if (monotonic_ns() - t0 > timeout_ns) return false;
+      timespec nap = {0, 20000};
+      nanosleep(&nap, nullptr);
+    }
+  }
+}
+
 void group_release(rtb_context* ctx) {
   rtb_context::Group& g = ctx->group;
   if (!g.active) return;
@@ -654,7 +700,111 @@ void group_release(rtb_context* ctx) {
   for (auto& e : g.ticket) if (e) cudaEventDestroy(e);
   if (g.base) { if (g.owner) cudaFree(g.base); else cudaIpcCloseMemHandle(g.base); }
   if (g.error) cudaFree(g.error);
+  if (g.hbase) {
+    if (g.registered) cudaHostUnregister(g.hbase);
+    munmap(g.hbase, g.hbytes);
+    if (g.owner && !g.shm_name.empty()) shm_unlink(g.shm_name.c_str());
+  }
+  cudaGetLastError();
   g = rtb_context::Group();
+}
+
+// Host-ring form of rtb_group_render_begin: render this rank's bands into a device frame buffer of its own, copy exactly those
+// bands into the frame's slot of the shared host ring (one strided copy: the bands of a rank are band_rows * width * 4 bytes every
+// world * that many), post done[rank][slot] behind the copy.  No rank touches another rank's GPU or PCIe link.
+int group_host_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, int32_t* ticket) {
+  rtb_context::Group& g = ctx->group;
+  if (rgba8) return fail(ctx, RTB_E_ARG, "a host-ring group delivers frames in the ring (rtb_group_frame): pass rgba8 = NULL");
+  if (!g.hbase || !g.hdev) return fail(ctx, RTB_E_ARG, "no group (rtb_group_create_host)");
+  rtb_render_params pp = *p;
+  pp.band_rank = g.rank; pp.band_world = g.world; pp.out_layout = RTB_OUT_FRAME;
+  if (pp.band_rows <= 0) pp.band_rows = 8;
+  FrameParams f;
+  std::string why;
+  if (!resolve_frame(ctx->host.d, pp, f, why)) return fail(ctx, RTB_E_ARG, why);
+  const size_t row_bytes = (size_t)f.width * 4, need = row_bytes * (size_t)f.height;
+  if (need > g.frame_bytes) return fail(ctx, RTB_E_SIZE, "frame larger than the group's buffers");
+  DeviceState& d = ctx->devs[0];
+  CK(ctx, cudaSetDevice(d.device));
+  HostRingHeader* hdr = (HostRingHeader*)g.hbase;
+  const uint64_t k = g.seq;
+  const int j = (int)(k % (uint64_t)g.n_buf), slot = (int)(k % rtb_context::Group::kTickets);
+  // slot j still holds frame k - n_buf until rank 0's caller has moved on, which it says by beginning frame k
+  if (g.rank == 0) __atomic_store_n(&hdr->begun0, (uint32_t)(k + 1), __ATOMIC_RELEASE);
+  else if (!host_wait_reached(&hdr->begun0, (uint32_t)(k + 1), g.timeout_ns))
+    return fail(ctx, RTB_E_CUDA, "rank 0 of the group did not begin this frame in time (RTB_GROUP_TIMEOUT_MS)");
+  if (!g.ticket[slot]) CK(ctx, cudaEventCreateWithFlags(&g.ticket[slot], cudaEventDisableTiming));
+  else CK(ctx, cudaEventSynchronize(g.ticket[slot]));  // the ring of tickets is full: wait for the frame begun kTickets calls ago
+  const int n_dev_buf = std::max(2, ctx->n_lanes), buf = (int)(k % (uint64_t)n_dev_buf);
+  if (d.frame_async_bytes[buf] < need) {
+    device_sync(d);
+    dfree(d.frame_async[buf]);
+    d.frame_async_bytes[buf] = 0;
+    CK(ctx, cudaMalloc(&d.frame_async[buf], need));
+    d.frame_async_bytes[buf] = need;
+  }
+  if (k >= (uint64_t)n_dev_buf) {  // the device buffer's previous frame must have left it
+    cudaEvent_t prev = g.ticket[(k - (uint64_t)n_dev_buf) % rtb_context::Group::kTickets];
+    for (auto& l : d.lane) if (l.stream) CK(ctx, cudaStreamWaitEvent(l.stream, prev, 0));
+  }
+  FrameParams f2;
+  const int rc = render_frame(ctx, &pp, d.frame_async[buf], d.frame_async_bytes[buf], /*to_internal_frame=*/false, /*sync=*/false, f2);
+  if (rc != RTB_OK) return rc;
+  LaneState& last = d.lane[d.last_lane];
+  for (int l = 0; l < DeviceState::kMaxLanes; l++)  // multi-chunk frame: every lane that carried one of its chunks
+    if (l != d.last_lane && d.lane[l].stream && d.lane[l].frame_id == ctx->frame_id) CK(ctx, cudaStreamWaitEvent(last.stream, d.lane[l].ev_done, 0));
+  CK(ctx, cudaEventRecord(last.ev_done, last.stream));
+  last.used = true;
+  CK(ctx, cudaStreamWaitEvent(d.copy_stream, last.ev_done, 0));
+  // ReadPixels (RayTracer.cs:371-375) of this rank's rows only
+  const uint8_t* src = (const uint8_t*)d.frame_async[buf];
+  uint8_t* dst = g.hbase + kHostRingHeaderBytes + (size_t)j * g.stride;
+  size_t copied = 0;
+  if (g.world == 1) {
+    CK(ctx, cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, d.copy_stream));
+    copied = need;
+  } else {
+    const size_t band_bytes = row_bytes * (size_t)f.band_rows;
+    const int n_bands = (f.height + f.band_rows - 1) / f.band_rows;
+    const int owned = n_bands > g.rank ? (n_bands - g.rank + g.world - 1) / g.world : 0;
+    if (owned > 0) {
+      const int last_band = g.rank + (owned - 1) * g.world;
+      const bool last_short = (size_t)(last_band + 1) * (size_t)f.band_rows > (size_t)f.height;
+      const int full = last_short ? owned - 1 : owned;
+      const size_t first = (size_t)g.rank * band_bytes, pitch = (size_t)g.world * band_bytes;
+      if (full > 0) {
+        CK(ctx, cudaMemcpy2DAsync(dst + first, pitch, src + first, pitch, band_bytes, (size_t)full, cudaMemcpyDeviceToHost, d.copy_stream));
+        copied += band_bytes * (size_t)full;
+      }
+      if (last_short) {
+        const size_t off = (size_t)last_band * band_bytes, rest = need - off;
+        CK(ctx, cudaMemcpyAsync(dst + off, src + off, rest, cudaMemcpyDeviceToHost, d.copy_stream));
+        copied += rest;
+      }
+    }
+  }
+  launch_group_post((uint32_t*)(g.hdev + offsetof(HostRingHeader, done)) + (size_t)g.rank * 8 + j, (uint32_t)(k + 1), d.copy_stream);
+  CK(ctx, cudaGetLastError());
+  CK(ctx, cudaEventRecord(g.ticket[slot], d.copy_stream));
+  d.copy_pending = true;
+  ctx->stats.d2h_bytes = (int64_t)copied;
+  ctx->stats.kernel_launches += 1;
+  *ticket = (int32_t)(k & 0x7fffffff);
+  g.seq++;
+  return RTB_OK;
+}
+
+int group_host_end(rtb_context* ctx, int32_t ticket) {
+  rtb_context::Group& g = ctx->group;
+  if (g.seq - (uint64_t)ticket <= (uint64_t)rtb_context::Group::kTickets) CK(ctx, cudaEventSynchronize(g.ticket[(uint64_t)ticket % rtb_context::Group::kTickets]));
+  CK(ctx, cudaGetLastError());
+  if (g.rank != 0) return RTB_OK;
+  const HostRingHeader* hdr = (const HostRingHeader*)g.hbase;
+  const int j = (int)((uint64_t)ticket % (uint64_t)g.n_buf);
+  for (int r = 1; r < g.world; r++)
+    if (!host_wait_reached(&hdr->done[(size_t)r * 8 + j], (uint32_t)ticket + 1u, g.timeout_ns))
+      return fail(ctx, RTB_E_CUDA, "a rank of the group did not arrive in time (RTB_GROUP_TIMEOUT_MS)");
+  return RTB_OK;
 }
 }  // namespace
 
@@ -906,6 +1056,7 @@ namespace {
 int begin_frame(rtb_context* ctx, const rtb_render_params* p, uint8_t* host_dst, size_t bytes, int32_t* ticket, bool indexed) {
   if (!ctx || !p || !host_dst || !ticket) return fail(ctx, RTB_E_ARG, "null argument");
   if (p->band_world > 1) return fail(ctx, RTB_E_ARG, "rtb_render_begin renders whole frames");
+  if (ctx->group.active && ctx->group.host) return fail(ctx, RTB_E_ARG, "a host-ring group owns the pipelined frame buffers: use rtb_group_render_begin, or destroy the group");
   if (!ctx->has_scene) return fail(ctx, RTB_E_NOSCENE, "no scene uploaded (rtb_upload_scene)");
   FrameParams f;
   std::string why;
@@ -1195,6 +1346,76 @@ int rtb_group_create(rtb_context* ctx, int32_t rank, int32_t world, size_t frame
   return RTB_OK;
 }
 
+// Host ring: the frames of the job land in POSIX shared memory `shm_name` ("/name"; rank 0 creates it, the others attach once
+// rank 0's call has returned), page-locked by every rank.  The readback then uses every GPU's own PCIe link instead of rank 0's
+// alone, and no device memory is shared between the processes at all.
+int rtb_group_create_host(rtb_context* ctx, int32_t rank, int32_t world, size_t frame_bytes, int32_t n_buffers, const char* shm_name) {
+  if (!ctx || !shm_name) return fail(ctx, RTB_E_ARG, "null argument");
+  if (world < 1 || world > 32 || rank < 0 || rank >= world || n_buffers < 1 || n_buffers > 8 || frame_bytes == 0) return fail(ctx, RTB_E_ARG, "bad group shape");
+  if (shm_name[0] != '/' || std::strlen(shm_name) < 2 || std::strlen(shm_name) > 200) return fail(ctx, RTB_E_ARG, "shm_name must look like \"/name\"");
+  if (ctx->devs.size() != 1) return fail(ctx, RTB_E_ARG, "a group member is a single-device context");
+  group_release(ctx);
+  rtb_context::Group& g = ctx->group;
+  CK(ctx, cudaSetDevice(ctx->devs[0].device));
+  g.active = true;
+  g.host = true;
+  g.rank = rank; g.world = world; g.n_buf = n_buffers; g.frame_bytes = frame_bytes;
+  g.stride = (frame_bytes + 4095) & ~(size_t)4095;
+  g.hbytes = kHostRingHeaderBytes + g.stride * (size_t)n_buffers;
+  int fd = -1;
+  if (rank == 0) {
+    shm_unlink(shm_name);  // a stale object of a crashed job
+    fd = shm_open(shm_name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) return fail(ctx, RTB_E_IO, std::string("shm_open(create) failed for ") + shm_name);
+    g.owner = true;
+    g.shm_name = shm_name;
+    // posix_fallocate, not just ftruncate: a /dev/shm that is too small must fail HERE, not as SIGBUS when a page is first touched
+    if (ftruncate(fd, (off_t)g.hbytes) != 0 || posix_fallocate(fd, 0, (off_t)g.hbytes) != 0) {
+      close(fd);
+      return fail(ctx, RTB_E_IO, "the host ring does not fit into /dev/shm");
+    }
+  } else {
+    fd = shm_open(shm_name, O_RDWR, 0600);
+    if (fd < 0) return fail(ctx, RTB_E_IO, std::string("shm_open failed for ") + shm_name + " (rank 0 creates it first)");
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || (size_t)sb.st_size != g.hbytes) { close(fd); return fail(ctx, RTB_E_ARG, "the host ring has another shape than this call describes"); }
+  }
+  void* m = mmap(nullptr, g.hbytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) return fail(ctx, RTB_E_IO, "mmap of the host ring failed");
+  g.hbase = (uint8_t*)m;
+  HostRingHeader* hdr = (HostRingHeader*)g.hbase;
+  if (rank == 0) {
+    std::memset(g.hbase, 0, kHostRingHeaderBytes);
+    hdr->world = (uint32_t)world; hdr->n_buf = (uint32_t)n_buffers; hdr->frame_bytes = frame_bytes; hdr->stride = g.stride;
+    __atomic_store_n(&hdr->magic, kHostRingMagic, __ATOMIC_RELEASE);
+  } else if (__atomic_load_n(&hdr->magic, __ATOMIC_ACQUIRE) != kHostRingMagic || hdr->world != (uint32_t)world || hdr->n_buf != (uint32_t)n_buffers ||
+             hdr->frame_bytes != frame_bytes) {
+    return fail(ctx, RTB_E_ARG, "the host ring was created for another group shape");
+  }
+  CK(ctx, cudaHostRegister(g.hbase, g.hbytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+  g.registered = true;
+  void* dp = nullptr;
+  CK(ctx, cudaHostGetDevicePointer(&dp, g.hbase, 0));
+  g.hdev = (uint8_t*)dp;
+  if (const char* env = std::getenv("RTB_GROUP_TIMEOUT_MS")) g.timeout_ns = (unsigned long long)std::max(1LL, std::atoll(env)) * 1000000ull;
+  g.seq = 0;
+  return RTB_OK;
+}
+
+// Rank 0 of a host-ring group: where the frame of `ticket` lies (after rtb_group_render_end(ticket)); it stays there until rank 0
+// begins frame ticket + n_buffers.
+int rtb_group_frame(rtb_context* ctx, int32_t ticket, const uint8_t** rgba8) {
+  if (!ctx || !rgba8) return fail(ctx, RTB_E_ARG, "null argument");
+  *rgba8 = nullptr;
+  rtb_context::Group& g = ctx->group;
+  if (!g.active || !g.host || !g.hbase) return fail(ctx, RTB_E_ARG, "no host-ring group (rtb_group_create_host)");
+  if (g.rank != 0) return fail(ctx, RTB_E_ARG, "frames are complete on rank 0 only");
+  if (ticket < 0 || (uint64_t)ticket >= g.seq || g.seq - (uint64_t)ticket > (uint64_t)g.n_buf) return fail(ctx, RTB_E_ARG, "that frame has left the ring");
+  *rgba8 = g.hbase + kHostRingHeaderBytes + ((uint64_t)ticket % (uint64_t)g.n_buf) * g.stride;
+  return RTB_OK;
+}
+
 int rtb_group_destroy(rtb_context* ctx) {
   if (!ctx) return RTB_E_ARG;
   group_release(ctx);
@@ -1204,6 +1425,10 @@ int rtb_group_destroy(rtb_context* ctx) {
 int rtb_group_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* ticket) {
   if (!ctx || !p || !ticket) return fail(ctx, RTB_E_ARG, "null argument");
   rtb_context::Group& g = ctx->group;
+  if (g.active && g.host) {
+    if (!ctx->has_scene) return fail(ctx, RTB_E_NOSCENE, "no scene uploaded (rtb_upload_scene)");
+    return group_host_begin(ctx, p, rgba8, ticket);
+  }
   if (!g.active || !g.base || !g.error || !g.gate || !g.gate_done) return fail(ctx, RTB_E_ARG, "no group (rtb_group_create)");
   if (!ctx->has_scene) return fail(ctx, RTB_E_NOSCENE, "no scene uploaded (rtb_upload_scene)");
   rtb_render_params pp = *p;
@@ -1265,6 +1490,7 @@ int rtb_group_render_end(rtb_context* ctx, int32_t ticket) {
   if (!g.active) return fail(ctx, RTB_E_ARG, "no group (rtb_group_create)");
   if (ticket < 0 || (uint64_t)ticket >= g.seq) return fail(ctx, RTB_E_ARG, "unknown ticket");
   CK(ctx, cudaSetDevice(ctx->devs[0].device));
+  if (g.host) return group_host_end(ctx, ticket);
   if (g.seq - (uint64_t)ticket <= (uint64_t)rtb_context::Group::kTickets) CK(ctx, cudaEventSynchronize(g.ticket[(uint64_t)ticket % rtb_context::Group::kTickets]));
   uint32_t err = 0;
   CK(ctx, cudaMemcpy(&err, g.error, sizeof err, cudaMemcpyDeviceToHost));

@@ -252,9 +252,14 @@ __device__ __forceinline__ bool lane_test_triangle(Lane& L, const SceneView& s, 
 #if RTB_TRI_F4 == 4
   ld8<SMEM>(&tri_isect[RTB_TRI_F4 * tri], a, b);
 #else
-  a = ld4<SMEM>(&tri_isect[RTB_TRI_F4 * tri]); b = ld4<SMEM>(&tri_isect[RTB_TRI_F4 * tri + 1]);
+  const float4* rec = tri_isect + RTB_TRI_F4 * (size_t)(uint32_t)tri;  // one widening multiply-add for the record's address
+  a = ld4<SMEM>(rec); b = ld4<SMEM>(rec + 1);
 #endif
+#if RTB_TRI_F4 == 4
   const float4 c = ld4<SMEM>(&tri_isect[RTB_TRI_F4 * tri + 2]);
+#else
+  const float4 c = ld4<SMEM>(rec + 2);
+#endif
   Ray r; r.o = L.o; r.d = L.d;
   float t, u, v;
   if (ANALYTIC && __float_as_int(c.w) != 0) {  // analytic primitive: hit record = (t_world, t_object, face code)

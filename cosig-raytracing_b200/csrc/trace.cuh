@@ -406,8 +406,9 @@ template <bool SMEM, int STRIDE = 1>
 __device__ __forceinline__ int32_t lbvh_visit(const float4* nodes, int32_t cur, const SlabRay& sr, float bound, float2* stack,
                                               int& sp, unsigned& overflow) {
   float4 n0, n1, n2, n3;
-  ld8<SMEM>(&nodes[4 * cur], n0, n1);
-  ld8<SMEM>(&nodes[4 * cur + 2], n2, n3);
+  const float4* rec = nodes + 4 * (size_t)(uint32_t)cur;  // one widening multiply-add (4 * cur in 32 bits costs a shift first)
+  ld8<SMEM>(rec, n0, n1);
+  ld8<SMEM>(rec + 2, n2, n3);
   float dl, dr;
   const bool hl = slab_hit(sr, mk3(n0), mk3(n1), bound, dl);
   const bool hr = slab_hit(sr, mk3(n2), mk3(n3), bound, dr);

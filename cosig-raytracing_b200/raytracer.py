@@ -307,6 +307,26 @@ class RayTracer:
     def GroupRenderEnd(self, ticket: int) -> None:
         self._check(self._lib.rtb_group_render_end(self._ctx, ticket))
 
+    def group_create_host(self, rank: int, world: int, frame_bytes: int, n_buffers: int = 4, name: Optional[str] = None) -> str:
+        """Host-ring form: frames land in POSIX shared memory every rank has page-locked, each rank's bands over its own PCIe link.
+        Rank 0 returns the name of the shared object (send it to the other ranks, which pass it in); use GroupRenderBegin(..., out=None)
+        and group_frame(ticket, height, width) afterwards."""
+        if name is None:
+            if rank != 0:
+                raise ValueError("ranks other than 0 need the name rank 0 returned")
+            import os
+            name = f"/rtb200-{os.getpid()}-{id(self) & 0xffffff:x}"
+        self._check(self._lib.rtb_group_create_host(self._ctx, rank, world, frame_bytes, n_buffers, name.encode()))
+        return name
+
+    def group_frame(self, ticket: int, height: int, width: int) -> np.ndarray:
+        """Rank 0 of a host-ring group: the frame of `ticket` as a [height, width, 4] uint8 VIEW of the ring (valid until n_buffers more
+        frames have been begun; copy it to keep it)."""
+        ptr = C.c_void_p()
+        self._check(self._lib.rtb_group_frame(self._ctx, ticket, C.byref(ptr)))
+        buf = (C.c_uint8 * (height * width * 4)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(height, width, 4)
+
     def group_destroy(self):
         self._check(self._lib.rtb_group_destroy(self._ctx))
 

@@ -215,6 +215,16 @@ int rtb_group_create(rtb_context* ctx, int32_t rank, int32_t world, size_t frame
 int rtb_group_render_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba8, size_t bytes, int32_t* ticket);
 int rtb_group_render_end(rtb_context* ctx, int32_t ticket);
 int rtb_group_destroy(rtb_context* ctx);
+/* Host-ring form of the same group, for consumers of the frames in HOST memory: the ring of `n_buffers` frames lies in POSIX shared
+ * memory `shm_name` ("/name": rank 0 creates it, the other ranks attach after rank 0's call has returned; the name travels over
+ * the host's own channel), page-locked by every rank.  Every rank renders its bands into a device buffer of its own and copies
+ * exactly those bands into the frame's slot over ITS OWN PCIe link (one strided copy), so the readback bandwidth grows with the
+ * number of GPUs instead of being rank 0's link alone; no device memory is shared between the processes.  Same begin / end calls,
+ * with rgba8 = NULL on every rank; after rtb_group_render_end(ticket) rank 0 finds the whole frame at rtb_group_frame(ticket),
+ * where it stays until rank 0 begins frame ticket + n_buffers (the other ranks do not overwrite a slot before that: they wait,
+ * on the host, for rank 0's begin of the same frame, bounded by RTB_GROUP_TIMEOUT_MS). */
+int rtb_group_create_host(rtb_context* ctx, int32_t rank, int32_t world, size_t frame_bytes, int32_t n_buffers, const char* shm_name);
+int rtb_group_frame(rtb_context* ctx, int32_t ticket, const uint8_t** rgba8);
 
 /* ReadPixels (RayTracer.cs:371-375) of the context's own frame buffer — the one rtb_frame_export shares — after the
  * peers have stored their bands into it. */

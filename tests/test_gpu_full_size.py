@@ -349,6 +349,125 @@ def test_group_of_one_equals_render_begin(samples_scene2):
         del _os.environ["RTB_GROUP_TIMEOUT_MS"]
 
 
+# ---- the host ring: every rank copies its own bands into shared page-locked memory (rtb_group_create_host) ------------------------------
+_HOST_RING_CHILD = r"""
+import importlib, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+from util import abi, params, synth
+rt_mod = importlib.import_module("cosig-raytracing_b200.raytracer")
+name = sys.stdin.readline().strip()
+obj = synth.sample_scene("test_scene_2")
+rt = rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH)
+rt.group_create_host({rank}, {world}, {w} * {h} * 4, {nbuf}, name)
+print("joined", flush=True)
+tickets = []
+for k in range({frames}):
+    if k >= {nbuf}:
+        rt.GroupRenderEnd(tickets[k - {nbuf}])
+    tickets.append(rt.GroupRenderBegin(obj, params({w}, {h}, 4, 1, has_fov=1, fov_deg=20.0 + 2.0 * k, band_rows={band_rows})))
+for t in tickets[-{nbuf}:]:
+    rt.GroupRenderEnd(t)
+print("stored", flush=True)
+sys.stdin.readline()
+rt.close()
+"""
+
+
+@pytest.mark.parametrize("world,h,band_rows", [(2, 240, 8), (3, 236, 16)])
+def test_host_ring_processes_on_one_gpu(samples_scene2, world, h, band_rows):
+    """rtb_group_create_host: `world` ranks (processes; here all on one GPU) render the bands of a stream of frames and each copies ITS
+    rows into the frame's slot of a ring in shared page-locked host memory; rank 0 reads whole frames at rtb_group_frame.  More frames
+    than buffers, so slots are reused under the begun-by-rank-0 rule.  236 rows in bands of 16 over 3 ranks: the last band is short (12
+    rows) and the ranks own 5 / 5 / 5 bands.  Every frame must equal the one-context render bit for bit, in order."""
+    obj = samples_scene2
+    w, frames, nbuf = 400, 7, 2
+    settings = [params(w, h, 4, 1, has_fov=1, fov_deg=20.0 + 2.0 * k, band_rows=band_rows) for k in range(frames)]
+    with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as one:
+        want = [one.RenderAsync(obj, params(w, h, 4, 1, has_fov=1, fov_deg=20.0 + 2.0 * k)).pixels for k in range(frames)]
+    rt = rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH)
+    children = []
+    try:
+        name = rt.group_create_host(0, world, w * h * 4, nbuf)
+        for r in range(1, world):
+            c = subprocess.Popen([sys.executable, "-c", _HOST_RING_CHILD.format(root=ROOT, tests=os.path.join(ROOT, "tests"), rank=r, world=world, w=w, h=h,
+                                                                                nbuf=nbuf, frames=frames, band_rows=band_rows)],
+                                 stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
+            c.stdin.write(name + "\n"); c.stdin.flush()
+            children.append(c)
+
+        def expect(c, word):
+            line = ""
+            for _ in range(50):
+                line = c.stdout.readline()
+                if not line or line.strip() == word:
+                    break
+            assert line.strip() == word, f"child ended with {line!r} instead of {word!r} (exit code {c.poll()})"
+
+        for c in children:
+            expect(c, "joined")
+        got, tickets = [], []
+        for k, p in enumerate(settings):
+            if k >= nbuf:  # the frame leaves the ring when frame k is begun: take it out first
+                rt.GroupRenderEnd(tickets[k - nbuf])
+                got.append(rt.group_frame(tickets[k - nbuf], h, w).copy())
+            tickets.append(rt.GroupRenderBegin(obj, p))
+        for t in tickets[-nbuf:]:
+            rt.GroupRenderEnd(t)
+            got.append(rt.group_frame(t, h, w).copy())
+        with pytest.raises(rt_mod.RtbError):
+            rt.group_frame(tickets[0], h, w)  # long gone
+        for c in children:
+            expect(c, "stored")
+        for k, (o, wnt) in enumerate(zip(got, want)):
+            assert (o == wnt).all(), f"frame {k}: {(o != wnt).any(axis=-1).sum()} pixels differ"
+        for c in children:
+            c.stdin.write("done\n"); c.stdin.flush()
+        for c in children:
+            assert c.wait(timeout=120) == 0
+    finally:
+        for c in children:
+            if c.poll() is None:
+                c.kill()
+        rt.close()
+
+
+def test_host_ring_of_one_and_its_errors(samples_scene2):
+    """world = 1: the host ring is rtb_render_begin / _end into library-owned memory.  A caller buffer is refused (the frame lives in the
+    ring), rtb_render_begin is refused while the group owns the pipelined buffers, a missing peer is an error after the timeout."""
+    obj = samples_scene2
+    p = params(320, 200, 3)
+    with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as rt:
+        want = rt.RenderAsync(obj, p).pixels
+        name = rt.group_create_host(0, 1, 320 * 200 * 4, 3)
+        assert os.path.exists("/dev/shm" + name)
+        for rounds in range(3):
+            tickets = [rt.GroupRenderBegin(obj, p) for _ in range(3)]
+            for t in tickets:
+                rt.GroupRenderEnd(t)
+                assert (rt.group_frame(t, 200, 320) == want).all()
+        out = np.zeros((200, 320, 4), np.uint8)
+        with pytest.raises(rt_mod.RtbError):
+            rt.GroupRenderBegin(obj, p, out)
+        with pytest.raises(rt_mod.RtbError):
+            rt.RenderBegin(obj, p, out)
+        with pytest.raises(rt_mod.RtbError):
+            rt.group_create_host(0, 1, 320 * 200 * 4, 3, "no-leading-slash")
+        rt.group_destroy()
+        assert not os.path.exists("/dev/shm" + name)
+        assert (rt.RenderAsync(obj, p).pixels == want).all()
+        with pytest.raises(rt_mod.RtbError):
+            rt.group_create_host(1, 2, 320 * 200 * 4, 3, "/rtb200-test-nobody-made-this")
+    os.environ["RTB_GROUP_TIMEOUT_MS"] = "300"
+    try:
+        with rt_mod.RayTracer(bvh_mode=abi.RTB_BVH_LBVH) as rt:
+            rt.group_create_host(0, 2, 320 * 200 * 4, 2)  # rank 1 never joins
+            t = rt.GroupRenderBegin(obj, p)
+            with pytest.raises(rt_mod.RtbError):
+                rt.GroupRenderEnd(t)
+    finally:
+        del os.environ["RTB_GROUP_TIMEOUT_MS"]
+
+
 # ---- every optional traversal kernel reproduces the default one ---------------------------------------------------------------------------
 def test_optional_kernels_reproduce_the_default_kernel():
     """tools/sanitize_run.py: small renders through every kernel variant — wavefront / tail / shared-memory schedules in both BVH modes, the

@@ -58,6 +58,10 @@ outs = [np.zeros((64, 96, 4), np.uint8) for _ in range(4)]
 for t in [rt.GroupRenderBegin(s1, params(96, 64, 3), o) for o in outs]:
     rt.GroupRenderEnd(t)
 assert all((o == outs[0]).all() for o in outs)
+rt.group_create_host(0, 1, 96 * 64 * 4, 2)   # the host ring of one rank: same frames, out of the shared mapping
+for t in [rt.GroupRenderBegin(s1, params(96, 64, 3)) for _ in range(2)]:
+    rt.GroupRenderEnd(t)
+    assert (rt.group_frame(t, 64, 96) == outs[0]).all()
 rt.close()
 print("group of one ok", flush=True)
 # GIF sweep: palette kernel (vector and scalar paths), indexed pipelined readback, fused rotation call
