@@ -167,6 +167,7 @@ struct rtb_context {
     size_t hbytes = 0;
     bool registered = false;
     std::string shm_name;
+    bool slot_open[8] = {};       // rank 0: the slot's frame has been begun and not yet ended (its reader has not even seen it)
   } group;
   struct External { cudaExternalMemory_t mem; void* ptr; size_t bytes; };
   std::vector<External> externals;  // rtb_external_import: graphics-API allocations mapped into device 0's address space
@@ -730,6 +731,7 @@ int group_host_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba
   const uint64_t k = g.seq;
   const int j = (int)(k % (uint64_t)g.n_buf), slot = (int)(k % rtb_context::Group::kTickets);
   // slot j still holds frame k - n_buf until rank 0's caller has moved on, which it says by beginning frame k
+  if (g.rank == 0 && g.slot_open[j]) return fail(ctx, RTB_E_ARG, "the ring is full: end the frame begun n_buffers calls ago (and read it) before beginning another");
   if (g.rank == 0) __atomic_store_n(&hdr->begun0, (uint32_t)(k + 1), __ATOMIC_RELEASE);
   else if (!host_wait_reached(&hdr->begun0, (uint32_t)(k + 1), g.timeout_ns))
     return fail(ctx, RTB_E_CUDA, "rank 0 of the group did not begin this frame in time (RTB_GROUP_TIMEOUT_MS)");
@@ -790,6 +792,7 @@ int group_host_begin(rtb_context* ctx, const rtb_render_params* p, uint8_t* rgba
   ctx->stats.d2h_bytes = (int64_t)copied;
   ctx->stats.kernel_launches += 1;
   *ticket = (int32_t)(k & 0x7fffffff);
+  g.slot_open[j] = true;
   g.seq++;
   return RTB_OK;
 }
@@ -804,6 +807,7 @@ int group_host_end(rtb_context* ctx, int32_t ticket) {
   for (int r = 1; r < g.world; r++)
     if (!host_wait_reached(&hdr->done[(size_t)r * 8 + j], (uint32_t)ticket + 1u, g.timeout_ns))
       return fail(ctx, RTB_E_CUDA, "a rank of the group did not arrive in time (RTB_GROUP_TIMEOUT_MS)");
+  if (g.seq - (uint64_t)ticket <= (uint64_t)g.n_buf) g.slot_open[j] = false;
   return RTB_OK;
 }
 }  // namespace

@@ -222,7 +222,8 @@ int rtb_group_destroy(rtb_context* ctx);
  * number of GPUs instead of being rank 0's link alone; no device memory is shared between the processes.  Same begin / end calls,
  * with rgba8 = NULL on every rank; after rtb_group_render_end(ticket) rank 0 finds the whole frame at rtb_group_frame(ticket),
  * where it stays until rank 0 begins frame ticket + n_buffers (the other ranks do not overwrite a slot before that: they wait,
- * on the host, for rank 0's begin of the same frame, bounded by RTB_GROUP_TIMEOUT_MS). */
+ * on the host, for rank 0's begin of the same frame, bounded by RTB_GROUP_TIMEOUT_MS).  Rank 0 therefore keeps at most n_buffers
+ * frames begun and not ended: beginning one more is RTB_E_ARG (it would overwrite a frame nobody has seen). */
 int rtb_group_create_host(rtb_context* ctx, int32_t rank, int32_t world, size_t frame_bytes, int32_t n_buffers, const char* shm_name);
 int rtb_group_frame(rtb_context* ctx, int32_t ticket, const uint8_t** rgba8);
 

@@ -445,6 +445,14 @@ def test_host_ring_of_one_and_its_errors(samples_scene2):
             for t in tickets:
                 rt.GroupRenderEnd(t)
                 assert (rt.group_frame(t, 200, 320) == want).all()
+        tickets = [rt.GroupRenderBegin(obj, p) for _ in range(3)]
+        with pytest.raises(rt_mod.RtbError):   # a fourth frame would overwrite the first, which nobody has read yet
+            rt.GroupRenderBegin(obj, p)
+        rt.GroupRenderEnd(tickets[0])
+        tickets.append(rt.GroupRenderBegin(obj, p))
+        for t in tickets[1:]:
+            rt.GroupRenderEnd(t)
+            assert (rt.group_frame(t, 200, 320) == want).all()
         out = np.zeros((200, 320, 4), np.uint8)
         with pytest.raises(rt_mod.RtbError):
             rt.GroupRenderBegin(obj, p, out)
