@@ -50,3 +50,39 @@ def gather_bands(mine, height: int, width: int, rank: int, world: int, band_rows
         return frame
     dist.gather(padded, None, dst=dst)
     return None
+
+
+def host_ring_copy_plan(height: int, width: int, rank: int, world: int, band_rows: int = 8) -> dict:
+    """What a rank of a host-ring group (rtb_group_create_host) copies into the frame's slot, in bytes of the row-major RGBA8 frame:
+    one strided copy — `full` pieces of `piece` bytes, the first at `first`, one every `pitch` — plus, when the rank's last band is
+    cut short by the frame's end, one linear copy of `tail_bytes` at `tail_offset`.  Mirrors api.cu: group_host_begin (the C code is
+    what runs; this restatement lets the CPU tests check that the ranks' plans tile a frame exactly once)."""
+    row_bytes = width * 4
+    need = row_bytes * height
+    if world <= 1:
+        return dict(first=0, pitch=need, piece=need, full=1, tail_offset=0, tail_bytes=0)
+    band_bytes = row_bytes * band_rows
+    n_bands = (height + band_rows - 1) // band_rows
+    owned = (n_bands - rank + world - 1) // world if n_bands > rank else 0
+    if owned == 0:
+        return dict(first=0, pitch=0, piece=0, full=0, tail_offset=0, tail_bytes=0)
+    last_band = rank + (owned - 1) * world
+    last_short = (last_band + 1) * band_rows > height
+    full = owned - 1 if last_short else owned
+    off = last_band * band_bytes
+    return dict(first=rank * band_bytes, pitch=world * band_bytes, piece=band_bytes, full=full,
+                tail_offset=off if last_short else 0, tail_bytes=need - off if last_short else 0)
+
+
+def apply_copy_plan(plan: dict, src: np.ndarray, dst: np.ndarray) -> int:
+    """Executes a host_ring_copy_plan between two flat uint8 views of a frame; returns the bytes moved."""
+    moved = 0
+    for i in range(plan["full"]):
+        a = plan["first"] + i * plan["pitch"]
+        dst[a:a + plan["piece"]] = src[a:a + plan["piece"]]
+        moved += plan["piece"]
+    if plan["tail_bytes"]:
+        a = plan["tail_offset"]
+        dst[a:a + plan["tail_bytes"]] = src[a:a + plan["tail_bytes"]]
+        moved += plan["tail_bytes"]
+    return moved

@@ -334,6 +334,110 @@ def test_gather_bands_world_size_2_gloo(h, band_rows):
     assert q.get(timeout=10) is True
 
 
+def test_host_ring_copy_plans_tile_the_frame_once():
+    """rtb_group_create_host: every rank copies `full` strided pieces plus at most one short tail.  Over all ranks the plans must write
+    every byte of the frame exactly once and move exactly the rank's rows (ragged heights, more ranks than bands, world = 1)."""
+    bands = __import__("importlib").import_module("cosig-raytracing_b200.bands")
+    for h in (1, 7, 8, 9, 31, 33, 150, 236, 2160):
+        for world in (1, 2, 3, 4, 8):
+            for band_rows in (4, 8, 16, 32):
+                w = 5
+                src = (np.arange(h * w * 4, dtype=np.int64) % 251 + 1).astype(np.uint8)
+                dst = np.zeros_like(src)
+                hits = np.zeros(src.size, np.int32)
+                for rank in range(world):
+                    plan = bands.host_ring_copy_plan(h, w, rank, world, band_rows)
+                    moved = bands.apply_copy_plan(plan, src, dst)
+                    assert moved == bands.local_row_count(h, rank, world, band_rows) * w * 4, (h, world, band_rows, rank)
+                    mark = np.zeros_like(src)
+                    bands.apply_copy_plan(plan, np.ones_like(src), mark)
+                    hits += mark
+                    rows = bands.owned_rows(h, rank, world, band_rows)
+                    assert (mark.reshape(h, w * 4)[rows] == 1).all() and mark.sum() == len(rows) * w * 4
+                assert (hits == 1).all() and (dst == src).all(), (h, world, band_rows)
+
+
+def _shm_ring_worker(rank, world, name, h, w, band_rows, frames, n_buf):
+    """One rank of the host-ring protocol without a GPU: waits for rank 0's begin, writes its rows of frame k into slot k % n_buf,
+    posts done[rank][slot] = k + 1 (the words and their meaning are api.cu's HostRingHeader)."""
+    import importlib
+    import time
+    from multiprocessing import shared_memory
+    bands = importlib.import_module("cosig-raytracing_b200.bands")
+    shm = shared_memory.SharedMemory(name=name)
+    try:
+        words = np.ndarray((1024,), dtype=np.uint32, buffer=shm.buf)   # [0] = begun0, [16 + rank * 8 + slot] = done
+        frame_bytes = h * w * 4
+        plan = bands.host_ring_copy_plan(h, w, rank, world, band_rows)
+        for k in range(frames):
+            t0 = time.time()
+            while int(words[0]) < k + 1:
+                assert time.time() - t0 < 60
+                time.sleep(0.0005)
+            j = k % n_buf
+            src = ((np.arange(frame_bytes, dtype=np.int64) + 7 * k) % 251).astype(np.uint8)   # frame k as every rank would render it
+            dst = np.ndarray((frame_bytes,), dtype=np.uint8, buffer=shm.buf, offset=4096 + j * frame_bytes)
+            bands.apply_copy_plan(plan, src, dst)
+            words[16 + rank * 8 + j] = k + 1
+        del words, dst
+    finally:
+        shm.close()
+
+
+@pytest.mark.parametrize("world,h,band_rows", [(2, 150, 8), (3, 236, 16)])
+def test_host_ring_protocol_over_shared_memory(world, h, band_rows):
+    """The hand-shake of the host ring run by `world` CPU processes over POSIX shared memory (no CUDA): more frames than slots, rank 0
+    begins frame k only after it has read frame k - n_buf, the others may write a slot only once rank 0 has begun that frame.  Every
+    frame rank 0 reads must be complete and be the right one."""
+    import multiprocessing as mp
+    import time
+    from multiprocessing import shared_memory
+    bands = __import__("importlib").import_module("cosig-raytracing_b200.bands")
+    w, frames, n_buf = 48, 9, 2
+    frame_bytes = h * w * 4
+    shm = shared_memory.SharedMemory(create=True, size=4096 + n_buf * frame_bytes)
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_shm_ring_worker, args=(r, world, shm.name, h, w, band_rows, frames, n_buf)) for r in range(1, world)]
+    try:
+        words = np.ndarray((1024,), dtype=np.uint32, buffer=shm.buf)
+        words[:] = 0
+        for p in procs:
+            p.start()
+        plan = bands.host_ring_copy_plan(h, w, 0, world, band_rows)
+
+        def read(k):
+            j = k % n_buf
+            t0 = time.time()
+            while any(int(words[16 + r * 8 + j]) < k + 1 for r in range(world)):
+                assert time.time() - t0 < 60, "a rank did not arrive"
+                time.sleep(0.0005)
+            got = np.ndarray((frame_bytes,), dtype=np.uint8, buffer=shm.buf, offset=4096 + j * frame_bytes)
+            want = ((np.arange(frame_bytes, dtype=np.int64) + 7 * k) % 251).astype(np.uint8)
+            assert (got == want).all(), f"frame {k}"
+
+        for k in range(frames):
+            if k >= n_buf:
+                read(k - n_buf)
+            words[0] = k + 1                                    # rank 0 begins frame k: slot k % n_buf may be overwritten now
+            j = k % n_buf
+            src = ((np.arange(frame_bytes, dtype=np.int64) + 7 * k) % 251).astype(np.uint8)
+            dst = np.ndarray((frame_bytes,), dtype=np.uint8, buffer=shm.buf, offset=4096 + j * frame_bytes)
+            bands.apply_copy_plan(plan, src, dst)
+            words[16 + 0 * 8 + j] = k + 1
+        for k in range(max(0, frames - n_buf), frames):
+            read(k)
+        for p in procs:
+            p.join(60)
+            assert p.exitcode == 0
+        del words, dst
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+        shm.close()
+        shm.unlink()
+
+
 # ---- the C++ host mirror (include/rtb_raytracer.hpp) --------------------------------------------------------------------------
 def build_cpp_test():
     import subprocess
