@@ -539,6 +539,9 @@ struct Scene {
   // Checker-only (see LeafAccel below): big leaves get a private sub-tree; node index -> entry of leaf_accel, or -1
   std::vector<int> accel_of_node;
   std::vector<struct LeafAccel> leaf_accel;
+  // Checker-only (orc_set_exact_closest): TraverseBVH culls a node only when its slab entry lies clearly BEYOND the best t so far,
+  // which makes it return the exact closest hit (what a scan of all triangles returns) instead of the reference's answer.
+  bool exact_closest = false;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -725,7 +728,10 @@ static Hit TraverseBVH(const Scene& sc, const Ray& r, Counters& c) {
     const GpuNode& n = sc.nodes[ni];
     c.nodes_visited++;
     float dst = IntersectAABB(r, n.mn, n.mx);
-    if (dst >= hit.t) continue;
+    // The reference culls with `dst >= hit.t` (:245-246) on FP32 slab distances of exact boxes.  Between two nearly coincident
+    // surfaces that discards, now and then, the box of the NEARER triangle (its entry distance rounds to >= a best t that is only an
+    // ulp or two farther), and the reference keeps the farther hit.  exact_closest keeps such nodes: the cull needs a clear margin.
+    if (sc.exact_closest ? (dst == kInfinity || dst > hit.t + (1e-4f * fabsf(hit.t) + 1e-5f)) : (dst >= hit.t)) continue;
     if (n.count > 0) {
       const int accel = sc.accel_of_node[(size_t)ni];
       if (accel >= 0) { c.tris_tested += n.count; IntersectLeafAccelerated(sc, sc.leaf_accel[(size_t)accel], r, hit); }
@@ -1210,6 +1216,14 @@ int32_t orc_brute_closest(const orc_scene* s, const float* o3, const float* d3, 
 // Applies to scenes built afterwards.  Returns the previous value.
 int orc_set_leaf_accel(int32_t min_count) { const int prev = g_leaf_accel_min; g_leaf_accel_min = min_count < 0 ? 0 : min_count; return prev; }
 int32_t orc_n_accelerated_leaves(const orc_scene* s) { return (int32_t)s->s.leaf_accel.size(); }
+
+// Checker-only: 1 = TraverseBVH returns the exact closest hit (see Scene::exact_closest), 0 = the reference's traversal.  The
+// GPU-LBVH flavour of the product, which tests padded boxes, is held against this mode; the reference-shape flavour against mode 0.
+int orc_set_exact_closest(orc_scene* s, int32_t on) {
+  if (!s) return RTB_E_ARG;
+  s->s.exact_closest = on != 0;
+  return RTB_OK;
+}
 
 int orc_version(void) { return 2; }
 

@@ -69,6 +69,7 @@ def lib():
         L.orc_random_unit_vector.argtypes = [VP, VP]
         L.orc_sample_ray.argtypes = [VP, C.POINTER(_abi.RenderParams), C.c_int32, C.c_int32, C.c_int32, VP, VP]
         L.orc_set_leaf_accel.argtypes = [C.c_int32]
+        L.orc_set_exact_closest.argtypes = [VP, C.c_int32]
         L.orc_n_accelerated_leaves.argtypes = [VP]
         L.orc_gif_color_table.argtypes = [VP]
         L.orc_gif_convert_to_indexed.argtypes = [VP, C.c_int32, C.c_int32, VP]
@@ -109,6 +110,12 @@ class OracleScene:
         if getattr(self, "h", None):
             lib().orc_free(self.h)
             self.h = None
+
+    def set_exact_closest(self, on: bool):
+        """Checker-only: the traversal returns the exact closest hit (what a scan of all triangles finds) instead of the reference's
+        answer, which now and then loses the nearer of two nearly coincident surfaces to its FP32 cull (oracle.cpp: exact_closest)."""
+        if lib().orc_set_exact_closest(self.h, 1 if on else 0) != 0:
+            raise RuntimeError("orc_set_exact_closest failed")
 
     def set_primitive_mode(self, mode: int):
         """0 = tessellated (reference behaviour), 1 = analytic spheres / boxes (HittableObjects.cs semantics)."""

@@ -489,6 +489,18 @@ def test_optional_kernels_reproduce_the_default_kernel():
         assert tag in r.stdout, tag
 
 
+# ---- randomised parity sweep ----------------------------------------------------------------------------------------------------------------
+def test_randomised_parity_sweep():
+    """tools/parity_fuzz.py on 160 seeds (profiles/r2_parity_fuzz.log holds a 3000-seed run): random meshes / spheres / boxes under random
+    composite transformations, random materials incl. out-of-range indices, random cameras and every render setting.  Reference-shape
+    flavour: frame, primary ids / t bits / materials and ray counters identical to the oracle.  LBVH flavour: every primary hit that differs
+    from the oracle's traversal is the brute-force closest hit, frames equal the oracle's exact-closest mode; 8-wide records equal the binary
+    ones; analytic frames identical up to equal-t ties between coincident primitives."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "parity_fuzz.py"), "--seeds", "160"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert "160 seeds" in r.stdout and " 0 failures" in r.stdout
+
+
 # ---- structure of the GPU-built hierarchies ---------------------------------------------------------------------------------------------
 def _leaf_range(ref):
     code = ~int(ref)

@@ -5,6 +5,7 @@ import ctypes as C
 import hashlib
 import json
 import os
+import sys
 import re
 import subprocess
 
@@ -288,6 +289,39 @@ def test_parser_tolerances_and_errors(pkg):
     empty = rt_mod.SceneService.LoadScene("/nonexistent/scene.txt")  # missing file -> empty ObjectData (SceneService.cs:28-33)
     assert empty.Image is None and not empty.TriangleMeshes
     assert not rt_mod.SceneService.ParseScene(b"").Transformations
+
+
+def test_exact_closest_mode_is_the_brute_force_closest_hit(oracle):
+    """Checker-only mode of the oracle (orc_set_exact_closest) that the LBVH flavour is held against: on random scenes its primary hits
+    must carry the t bits of a scan over ALL triangles, also on the pixels where the reference's own traversal (FP32 cull on exact boxes)
+    keeps the farther of two nearly coincident surfaces — seed 1199 of tools/parity_fuzz.py has 15 of those."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import parity_fuzz as F
+    checked = differing = 0
+    for seed in (3, 7, 19, 1199, 1598):
+        obj = F.random_scene(seed)
+        p, _ = F.random_settings(seed)
+        packed = scene_mod.pack_scene(obj)
+        osc = oracle.OracleScene.from_desc(packed.desc)
+        ref = osc.render(p, want_aux=True)
+        osc.set_exact_closest(True)
+        rx = osc.render(p, want_aux=True)
+        osc.set_exact_closest(False)
+        again = osc.render(p, want_aux=True)
+        assert (again["rgba8"] == ref["rgba8"]).all()  # the switch leaves the reference's traversal as it was
+        h, w = rx["prim"].shape
+        ys, xs = np.nonzero((rx["t"].view(np.uint32) != ref["t"].view(np.uint32)) | (rx["prim"] != ref["prim"]))
+        differing += len(ys)
+        rng = np.random.RandomState(seed)
+        for y, x in list(zip(ys, xs)) + [(rng.randint(h), rng.randint(w)) for _ in range(120)]:
+            o, d = osc.primary_ray(p, int(x), int(y))
+            tb, ids, n = osc.brute_closest(o, d, cap=64)
+            checked += 1
+            if n == 0:
+                assert rx["prim"][y, x] < 0
+            else:
+                assert rx["prim"][y, x] >= 0 and np.float32(tb).view(np.uint32) == rx["t"].view(np.uint32)[y, x], (seed, x, y)
+    assert differing >= 15 and checked > 600
 
 
 # ---- band arithmetic and the world-size-2 gather (gloo) ------------------------------------------------------------------------
