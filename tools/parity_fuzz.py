@@ -12,6 +12,9 @@ blur, debug views) and renders it
     (same t bits, id among the tied ids); frame within 1/255 on >= 99.9 % of the pixels on seeds without manufactured ties (every 4th
     seed has coincident primitives and duplicate triangles, where the two flavours may legitimately pick different winners) — and
     the 8-wide records (RTB_WIDE) must give the LBVH flavour's frame;
+  * through one of eight schedules / optional kernels per seed (pure wavefront, global-memory scene, tiny chunks, packet kernels, the
+    regrouping pool, 8-wide records in shared memory): the reference-shape ones must give the oracle's frame, the LBVH ones the default
+    LBVH context's frame, exactly; every 5th seed also pipelines three frames through rtb_render_begin / _end;
   * with analytic spheres / boxes (every 3rd seed): frame identical to the oracle's analytic mode in reference shape.
 
 This is test infrastructure (it imports oracle/): a way to spend GPU minutes on cases nobody wrote down.  Prints one line per failure
@@ -51,7 +54,7 @@ def random_transform(rng, spread=20.0, allow_scale=True):
     return scene_mod.CompositeTransformation(els)
 
 
-def random_scene(seed):
+def random_scene(seed, big=False):
     """Seeds with seed % 4 == 3 are TIE seeds: primitives may share a transformation (exactly coincident spheres / boxes with different
     materials), meshes may hold duplicate triangles and coplanar grids.  All other seeds give every primitive its own transformation and
     keep exact duplicates out, so that equal-t ties are as rare as in a modelled scene."""
@@ -108,8 +111,10 @@ def random_scene(seed):
         return first_xf + next_xf[0] - 1   # one transformation per object (at most 3 + 4 + 3 objects)
 
     for _ in range(rng.randint(0, 4)):
-        n = int(rng.choice([1, 2, 5, 40, 300, 2000]))
+        n = int(rng.choice([2000, 20000, 100000])) if big else int(rng.choice([1, 2, 5, 40, 300, 2000]))
         shape = rng.randint(0, 4) if ties else rng.randint(0, 2)
+        if big and n > 2000:
+            shape = 1  # a soup of 100 000 cube-sized triangles is no scene (every ray meets thousands of boxes); small ones on a sheet are
         if shape == 0:       # soup
             v = (rng.rand(n, 3, 3).astype(np.float32) - 0.5) * 30.0
         elif shape == 1:     # small triangles scattered on a sheet
@@ -132,14 +137,14 @@ def random_scene(seed):
             v[2::11, 1] = v[2::11, 0]
         m = np.array([mat_index() for _ in range(len(v))], np.int32)
         s.TriangleMeshes.append(scene_mod.TrianglesMesh(xf_index(), materials=m, vertices=v))
-    for _ in range(rng.randint(0, 5)):
+    for _ in range(rng.randint(0, 5)):  # (regular seeds have 13 transformations left for spheres and boxes: counts stay small also when big)
         s.Spheres.append(scene_mod.SphereDescription(xf_index(), mat_index()))
     for _ in range(rng.randint(0, 4)):
         s.Boxes.append(scene_mod.BoxDescription(xf_index(), mat_index()))
     return s
 
 
-def random_settings(seed):
+def random_settings(seed, big=False):
     rng = np.random.RandomState(seed + 77777)
     kw = {}
     if rng.rand() < 0.2:
@@ -168,25 +173,49 @@ def random_settings(seed):
     aa = int(rng.choice([1, 1, 1, 2, 3, 4, 5, 8, 16]))
     depth = int(rng.choice([0, 1, 2, 3, 4, 6, 9]))
     w, h = int(rng.choice([33, 64, 96, 130])), int(rng.choice([17, 48, 64, 75]))
+    if big:
+        w, h = [(320, 200), (256, 144), (400, 300)][rng.randint(0, 3)]
+        aa = int(rng.choice([1, 1, 2, 4]))
     return params(w, h, depth, aa, **kw), dict(w=w, h=h, depth=depth, aa=aa, **kw)
 
 
+ENV_KNOBS = ("RTB_TAIL_MAX", "RTB_SMEM", "RTB_CHUNK_SLOTS", "RTB_LANES", "RTB_WIDE", "RTB_POOL", "RTB_PACKET_CLOSEST", "RTB_PACKET_SHADOW")
+# Schedules and optional kernels (read from the environment at rtb_create), each held to: reference shape -> the oracle's frame,
+# LBVH -> the default LBVH context's frame (the closest hit and the occlusion test do not depend on the order of the tests).
+VARIANTS = [
+    ("reference shape, pure wavefront (no tail kernel)", abi.RTB_BVH_REFERENCE, {"RTB_TAIL_MAX": "0"}),
+    ("reference shape, scene in global memory", abi.RTB_BVH_REFERENCE, {"RTB_SMEM": "0"}),
+    ("reference shape, 2048-slot chunks", abi.RTB_BVH_REFERENCE, {"RTB_CHUNK_SLOTS": "2048", "RTB_TAIL_MAX": "300"}),
+    ("reference shape, packet kernels for the primary rays", abi.RTB_BVH_REFERENCE, {"RTB_PACKET_CLOSEST": "1", "RTB_PACKET_SHADOW": "0"}),
+    ("LBVH, pure wavefront, global memory", abi.RTB_BVH_LBVH, {"RTB_TAIL_MAX": "0", "RTB_SMEM": "0"}),
+    ("LBVH, packet kernels at every depth", abi.RTB_BVH_LBVH, {"RTB_PACKET_CLOSEST": "16", "RTB_PACKET_SHADOW": "16", "RTB_SMEM": "0"}),
+    ("LBVH, regrouping pool kernel", abi.RTB_BVH_LBVH, {"RTB_POOL": "1", "RTB_SMEM": "0"}),
+    ("LBVH, 8-wide records in shared memory, one lane", abi.RTB_BVH_LBVH, {"RTB_WIDE": "1", "RTB_SMEM": "1", "RTB_LANES": "1"}),
+]
+
+
 class Tracers:
-    """One context per (bvh flavour, primitive mode, wide) — created once, reused over the seeds (every seed is a new scene: the upload
-    path and its pooled memory get exercised too)."""
+    """One context per (bvh flavour, primitive mode, environment) — created once, reused over the seeds (every seed is a new scene: the
+    upload path and its pooled memory get exercised too)."""
 
     def __init__(self):
         self.cache = {}
 
-    def get(self, mode, prim=0, wide=False):
-        key = (mode, prim, wide)
+    def get(self, mode, prim=0, wide=False, env=None):
+        env = dict(env or {})
+        if wide:
+            env["RTB_WIDE"] = "1"
+        key = (mode, prim, tuple(sorted(env.items())))
         if key not in self.cache:
-            if wide:
-                os.environ["RTB_WIDE"] = "1"
+            saved = {k: os.environ.pop(k, None) for k in ENV_KNOBS}
+            os.environ.update(env)
             try:
                 self.cache[key] = rt_mod.RayTracer(bvh_mode=mode, primitive_mode=prim)
             finally:
-                os.environ.pop("RTB_WIDE", None)
+                for k in ENV_KNOBS:
+                    os.environ.pop(k, None)
+                    if saved[k] is not None:
+                        os.environ[k] = saved[k]
         return self.cache[key]
 
     def close(self):
@@ -194,9 +223,9 @@ class Tracers:
             rt.close()
 
 
-def check_seed(seed, tracers, fails, stats_out):
-    obj = random_scene(seed)
-    p, desc = random_settings(seed)
+def check_seed(seed, tracers, fails, stats_out, big=False):
+    obj = random_scene(seed, big)
+    p, desc = random_settings(seed, big)
     packed = scene_mod.pack_scene(obj)
     osc = O.OracleScene.from_desc(packed.desc)
     ref = osc.render(p, want_aux=True)
@@ -275,6 +304,22 @@ def check_seed(seed, tracers, fails, stats_out):
     pw, tw, mw = rw.primary_hits(obj, p)
     if not ((pw == pl).all() and (tw.view(np.uint32) == tl.view(np.uint32)).all()):
         fail(f"8-wide records: primary hits differ from the binary LBVH's (ids {(pw != pl).sum()}, t bits {(tw.view(np.uint32) != tl.view(np.uint32)).sum()})")
+    # ---- one schedule / optional kernel per seed, round robin ------------------------------------------------------------------------------
+    vname, vmode, venv = VARIANTS[seed % len(VARIANTS)]
+    rv = tracers.get(vmode, 0, env=venv)
+    texv = rv.RenderAsync(obj, p)
+    want_v = ref["rgba8"] if vmode == abi.RTB_BVH_REFERENCE else texl.pixels
+    if not (texv.pixels == want_v).all():
+        fail(f"{vname}: {(texv.pixels != want_v).any(axis=-1).sum()} of {n_px} pixels differ from the {'oracle' if vmode == abi.RTB_BVH_REFERENCE else 'default LBVH'} frame")
+    if rv.stats().reserved[0] != 0:
+        fail(f"{vname}: traversal-stack overflow")
+    # pipelined frames (rtb_render_begin / _end) must be the blocking frame
+    if seed % 5 == 0:
+        outs = [np.zeros_like(tex.pixels) for _ in range(3)]
+        for tk in [rt.RenderBegin(obj, p, o) for o in outs]:
+            rt.RenderEnd(tk)
+        if not all((o == tex.pixels).all() for o in outs):
+            fail("rtb_render_begin / _end frames differ from the blocking frame")
     # ---- analytic spheres / boxes -------------------------------------------------------------------------------------------------
     if seed % 3 == 0 and (obj.Spheres or obj.Boxes):
         osc.set_primitive_mode(1)
@@ -309,6 +354,8 @@ def main():
     ap.add_argument("--seeds", type=int, default=200)
     ap.add_argument("--first", type=int, default=0)
     ap.add_argument("--seconds", type=float, default=0.0, help="stop after this much wall time (0 = run all seeds)")
+    ap.add_argument("--big", action="store_true", help="meshes of 2 000 .. 300 000 triangles, frames of 256x144 .. 400x300 (several sort tiles, deep trees, "
+                                                       "scenes that do not fit shared memory)")
     ap.add_argument("--oracle-only", action="store_true", help="draw the scenes and run the oracle only (works without a GPU)")
     a = ap.parse_args()
     O.build()
@@ -317,7 +364,7 @@ def main():
     t0 = time.time()
     for seed in range(a.first, a.first + a.seeds):
         try:
-            rays += check_seed(seed, tracers, fails, stats_out)
+            rays += check_seed(seed, tracers, fails, stats_out, a.big)
         except Exception as exc:  # an API error on a random scene is a finding too
             fails.append((seed, repr(exc)))
             print(f"FAIL seed {seed}: exception {exc!r}", flush=True)
