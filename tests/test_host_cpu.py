@@ -261,6 +261,28 @@ def test_native_parser_round_trips_sample_scenes(pkg, oracle, name):
         assert x.tobytes() == y.tobytes()
 
 
+def test_native_parser_round_trips_random_scenes(pkg, oracle):
+    """The generator of tools/parity_fuzz.py (random transformations, materials, meshes, spheres, boxes; out-of-range indices; scenes
+    without lights or materials) through text -> library parser -> same scene, and through the oracle's restatement of SceneService ->
+    the same flattened triangles and the same rendered frame as the scene that never was text."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import parity_fuzz as F
+    rt_mod = __import__("importlib").import_module("cosig-raytracing_b200.raytracer")
+    for seed in range(40):
+        obj = F.random_scene(seed)
+        text = synth.scene_to_text(obj).encode()
+        parsed = rt_mod.SceneService.ParseScene(text)
+        _same_scene(obj, parsed)
+        a = oracle.OracleScene.from_text(text)
+        b, holder = oracle_scene(oracle, obj)
+        assert a.triangles()[0].shape == b.triangles()[0].shape
+        for x, y in zip(a.triangles(), b.triangles()):
+            assert x.tobytes() == y.tobytes(), seed
+        if seed % 8 == 0:
+            p, _ = F.random_settings(seed)
+            assert (a.render(p)["rgba8"] == b.render(p)["rgba8"]).all(), seed
+
+
 @pytest.mark.skipif(not os.path.isdir(REFERENCE_SCENES), reason="reference tree only exists in the build container")
 @pytest.mark.parametrize("name", synth.SAMPLE_SCENES)
 def test_native_parser_reads_reference_files(pkg, name):
