@@ -704,8 +704,8 @@ void group_release(rtb_context* ctx) {
   if (g.hbase) {
     if (g.registered) cudaHostUnregister(g.hbase);
     munmap(g.hbase, g.hbytes);
-    if (g.owner && !g.shm_name.empty()) shm_unlink(g.shm_name.c_str());
   }
+  if (g.owner && !g.shm_name.empty()) shm_unlink(g.shm_name.c_str());  // also when creation failed half-way (nothing mapped yet)
   cudaGetLastError();
   g = rtb_context::Group();
 }
