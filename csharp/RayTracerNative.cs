@@ -17,7 +17,7 @@ using Unity.Collections;
 using Unity.Collections.LowLevel.Unsafe;
 using UnityEngine;
 
-internal static class RtbNative
+public static class RtbNative
 {
     const string Lib = "rtb200"; // librtb200.so / rtb200.dll in Assets/Plugins/x86_64
 
