@@ -250,7 +250,12 @@ public sealed class RayTracerNative : IDisposable
 
     public RtbNative.Stats GetStats() { Check(RtbNative.rtb_get_stats(ctx, out RtbNative.Stats s)); return s; }
 
-    public static void SaveTexture(Texture2D tex, string path) => System.IO.File.WriteAllBytes(path, tex.EncodeToPNG()); // :504
+    public static void SaveTexture(Texture2D tex, string path)                                                          // :504-509
+    {
+        byte[] png = tex.EncodeToPNG();
+        System.IO.Directory.CreateDirectory(System.IO.Path.GetDirectoryName(path));
+        System.IO.File.WriteAllBytes(path, png);
+    }
 
     // RebuildBVH (RayTracer.cs:386-404) + SetupMaterialBuffer (:455-499): flatten ObjectData into rtb_scene_desc — CSR of the
     // transformations, one triangle array with a range per mesh — and hand it over.  The library copies what it needs during the
