@@ -460,6 +460,51 @@ def test_random_unit_vector_hash_bits_and_sincos_accuracy(oracle):
     assert worst <= 5e-7, worst
 
 
+# ---- the kernel's debug views (compute:484-508), one of which the Unity dump uses to expose the primary t ----------------------------------
+@pytest.mark.parametrize("name", synth.SAMPLE_SCENES)
+def test_debug_views_against_float64(pkg, oracle, name):
+    """_DebugMode 1 (depth: t / 100, red on a miss), 2 (normal * 0.5 + 0.5, blue on a miss), 3 (green hit mask on grey): the pixel-centre
+    perspective ray re-traced after the sample loop, restated in float64 from the shader text.  csharp/Editor/DumpGoldens.cs dumps view 1
+    of the real reference, so this is the view a future pin of the primary hit distance goes through.  Also with the orthographic switch
+    on: the shader's debug block ignores it (the re-trace is always perspective)."""
+    obj = synth.sample_scene(name)
+    osc, holder = oracle_scene(oracle, obj)
+    w, h = 80, 60
+    tri18, mat_idx, _ = osc.triangles()
+    t64 = tri18.astype(np.float64)
+    v0, e1, e2 = t64[:, 0:3], t64[:, 3:6] - t64[:, 0:3], t64[:, 6:9] - t64[:, 0:3]
+    n0, n1, n2 = t64[:, 9:12], t64[:, 12:15], t64[:, 15:18]
+    for ortho in (0, 1):
+        p0 = params(w, h, 2, is_orthographic=ortho)
+        u25 = np.zeros(25, np.float32)
+        wh = (C.c_int32 * 2)()
+        assert abi.load().rtb_resolve_frame(holder.ptr(), C.byref(p0), u25.ctypes.data_as(C.POINTER(C.c_float)), wh) == abi.RTB_OK
+        M = u25[:16].reshape(4, 4).astype(np.float64)
+        cam_d, tan_half = float(u25[16]), float(u25[17])
+        ys, xs = np.mgrid[0:h, 0:w]
+        plane_h = 2.0 * cam_d * tan_half
+        plane_w = plane_h * (w / h)
+        uu = ((xs.ravel() + 0.5) / w - 0.5) * plane_w
+        vv = ((ys.ravel() + 0.5) / h - 0.5) * plane_h
+        oc = np.array([0.0, 0.0, cam_d])
+        dc = _normalize64(np.stack([uu, vv, np.zeros_like(uu)], -1) - oc)
+        o = np.broadcast_to(M[:3, :3] @ oc + M[:3, 3], dc.shape).copy()
+        d = _normalize64(dc @ M[:3, :3].T)
+        t, pos, nrm, mi = _scene64(o, d, v0, e1, e2, n0, n1, n2, mat_idx, ())
+        hit = np.isfinite(t)
+        want = {
+            1: np.where(hit[:, None], np.repeat((np.where(hit, t, 0.0) / 100.0)[:, None], 3, 1), np.array([1.0, 0.0, 0.0])),
+            2: np.where(hit[:, None], np.nan_to_num(nrm) * 0.5 + 0.5, np.array([0.0, 0.0, 1.0])),
+            3: np.where(hit[:, None], np.array([0.0, 1.0, 0.0]), np.array([0.2, 0.2, 0.2])),
+        }
+        for mode in (1, 2, 3):
+            ref = osc.render(params(w, h, 2, is_orthographic=ortho, debug_mode=mode))["rgba8"][..., :3]
+            got = np.floor(np.clip(want[mode], 0.0, 1.0) * 255.0 + 0.5).astype(np.uint8).reshape(h, w, 3)
+            diff = np.abs(got.astype(np.int32) - ref.astype(np.int32)).max(-1)
+            assert (diff <= 1).mean() >= 0.995, f"{name} debug view {mode} ortho {ortho}: {(diff <= 1).mean() * 100:.2f}% within 1/255, worst {int(diff.max())}"
+        assert 0.05 < hit.mean() < 1.0
+
+
 # ---- distribution effects: soft shadows, glossy reflections, motion blur — seeds and placement restated from the shader text -----------
 def _ruv64(sx, sy, sz):
     """RandomUnitVector (compute:116-131): Hash33 in FP32 exactly as the test above restates it, then z, a, r and cos / sin in float64."""
