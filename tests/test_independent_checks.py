@@ -392,8 +392,8 @@ def _normalize_f32(v):
     return np.array([_f(v[0] * r), _f(v[1] * r), _f(v[2] * r)], np.float32)
 
 
-def _sample_ray_f32(u25, w, h, n_samples, px, py, i):
-    """compute:283-340 for AA sample i of pixel (px, py), perspective camera."""
+def _sample_ray_f32(u25, w, h, n_samples, px, py, i, ortho=False):
+    """compute:283-340 for AA sample i of pixel (px, py); perspective camera, or the orthographic branch (:318-327)."""
     M = u25[:16].reshape(4, 4)
     cam_d, tan_half = _f(u25[16]), _f(u25[17])
     grid_w = int(np.ceil(np.sqrt(np.float32(n_samples))))
@@ -409,8 +409,16 @@ def _sample_ray_f32(u25, w, h, n_samples, px, py, i):
         oy = _f(_f(_f(gy) + jy) / _f(grid_h))
     u = _f(_f(_f(_f(_f(px) + ox) / _f(w)) - _f(0.5)) * plane_w)
     v = _f(_f(_f(_f(_f(py) + oy) / _f(h)) - _f(0.5)) * plane_h)
-    dc = _normalize_f32(np.array([_f(u - _f(0.0)), _f(v - _f(0.0)), _f(_f(0.0) - cam_d)], np.float32))
-    oc = np.array([0.0, 0.0, cam_d], np.float32)
+    if ortho:
+        half_h = _f(u25[18])
+        half_w = _f(half_h * aspect)
+        ou = _f(_f(_f(_f(_f(_f(px) + ox) / _f(w)) - _f(0.5)) * _f(2.0)) * half_w)
+        ov = _f(_f(_f(_f(_f(_f(py) + oy) / _f(h)) - _f(0.5)) * _f(2.0)) * half_h)
+        oc = np.array([ou, ov, cam_d], np.float32)
+        dc = np.array([0.0, 0.0, -1.0], np.float32)
+    else:
+        dc = _normalize_f32(np.array([_f(u - _f(0.0)), _f(v - _f(0.0)), _f(_f(0.0) - cam_d)], np.float32))
+        oc = np.array([0.0, 0.0, cam_d], np.float32)
     o = np.array([_f(_f(_f(_f(M[r, 0] * oc[0]) + _f(M[r, 1] * oc[1])) + _f(M[r, 2] * oc[2])) + _f(M[r, 3] * _f(1.0))) for r in range(3)], np.float32)
     d = _normalize_f32(np.array([_f(_f(_f(M[r, 0] * dc[0]) + _f(M[r, 1] * dc[1])) + _f(M[r, 2] * dc[2])) for r in range(3)], np.float32))
     return o, d
@@ -520,7 +528,8 @@ def _ruv64(sx, sy, sz):
     return np.array([r * np.cos(a), r * np.sin(a), z])
 
 
-def _render64_fx(tri18, mat_idx, materials, u25, w, h, max_depth, n_samples, light_size=0.0, roughness=0.0, shutter=0.0, intensity=1.0):
+def _render64_fx(tri18, mat_idx, materials, u25, w, h, max_depth, n_samples, light_size=0.0, roughness=0.0, shutter=0.0, intensity=1.0,
+                 ortho=False, ambient=True, diffuse=True, specular=True, refraction=True):
     """CSMain with its distribution effects (compute:283-478) in float64, one path at a time, written from the shader text: stratified
     AA samples (the FP32 restatement above, bit-exact), motion blur `origin += (RUV(x + i, y, i) - 0.5) * 0.2 * shutter` (:342-349), soft
     shadows `lightPos += RUV(x + 9 i, y + 4 i + depth, i) * lightSize` (:383-388), glossy `dir = normalize(dir + RUV(x + 55 i + depth,
@@ -541,7 +550,7 @@ def _render64_fx(tri18, mat_idx, materials, u25, w, h, max_depth, n_samples, lig
             for px in range(w):
                 acc = np.zeros(3)
                 for i in range(n_samples):
-                    o32, d32 = _sample_ray_f32(u25, w, h, n_samples, px, py, i)
+                    o32, d32 = _sample_ray_f32(u25, w, h, n_samples, px, py, i, ortho)
                     o, d = o32.astype(np.float64), d32.astype(np.float64)
                     if shutter > 0.0:
                         o = o + (_ruv64(px + i, py, i) - 0.5) * 0.2 * shutter
@@ -552,20 +561,20 @@ def _render64_fx(tri18, mat_idx, materials, u25, w, h, max_depth, n_samples, lig
                             col += att * bg
                             break
                         c, ka, kd, ks, kr, ior = (mats[mi][:3], *mats[mi][3:]) if mi >= 0 else (np.ones(3), 0.1, 0.7, 0.0, 0.0, 1.0)
-                        local = c * ka
+                        local = c * ka if ambient else np.zeros(3)
                         light = light0 + (_ruv64(px + i * 9.0, py + i * 4.0 + depth, i) * light_size if light_size > 0.0 else 0.0)
                         ldir = (light - pos) / np.linalg.norm(light - pos)
                         ndl = max(0.0, float(nrm @ ldir))
-                        if ndl > 0.0:
+                        if diffuse and ndl > 0.0:
                             st, _, _, _ = query(pos + nrm * 1e-2, ldir)
                             if not np.isfinite(st) or st > np.linalg.norm(light - pos):
                                 local = local + c * kd * ndl
-                                if ks > 0.0:
+                                if specular and ks > 0.0:
                                     hv = ldir + (-d) / np.linalg.norm(d)
                                     hv /= np.linalg.norm(hv)
                                     local = local + ks * max(float(nrm @ hv), 0.0) ** 32
                         col += att * local * intensity
-                        reflect, refract = ks > 0.0, kr > 0.0
+                        reflect, refract = ks > 0.0, refraction and kr > 0.0
                         if not reflect and not refract:
                             break
                         I = d / np.linalg.norm(d)
@@ -627,6 +636,39 @@ def test_distribution_effects_against_float64(pkg, oracle, kw, fx):
     # and the effect is really on: the frame differs from the one without it
     plain = osc.render(params(w, h, depth, aa))["rgba8"][..., :3]
     assert (plain != ref).any(axis=-1).mean() > 0.02
+
+
+@pytest.mark.parametrize("kw,fx", [
+    (dict(is_orthographic=1), dict(ortho=True)),
+    (dict(is_orthographic=1, aa_samples=4), dict(ortho=True)),
+    (dict(enable_ambient=0), dict(ambient=False)),
+    (dict(enable_diffuse=0), dict(diffuse=False)),
+    (dict(enable_specular=0), dict(specular=False)),
+    (dict(enable_refraction=0), dict(refraction=False)),
+    (dict(light_intensity=1.7), dict(intensity=1.7)),
+    (dict(has_bg=1, bg=(0.9, 0.1, 0.4), has_fov=1, fov_deg=55.0), dict()),
+    (dict(has_cam_pos=1, cam_pos=(5.0, -60.0, 30.0), has_cam_rot=1, cam_rot_euler_deg=(-60.0, 10.0, 5.0)), dict()),
+])
+def test_render_settings_against_float64(pkg, oracle, kw, fx):
+    """Every switch of RenderSettings that changes the picture — orthographic camera (compute:318-327), the four lighting toggles
+    (:381, :392, :407, :423), light intensity (:418), background / fov / camera overrides (uniforms resolved by the library's host code) —
+    through the float64 per-path restatement.  The specular toggle only gates the highlight (:407): a mirror still reflects with it off
+    (:421).  Tolerance as for the whole-frame check: 99 % of the pixels within 1/255."""
+    obj = synth.sample_scene("test_scene_1")
+    osc, holder = oracle_scene(oracle, obj)
+    w, h, depth = 56, 40, 4
+    aa = kw.get("aa_samples", 1)
+    p = params(w, h, depth, aa, **{k: v for k, v in kw.items() if k != "aa_samples"})
+    ref = osc.render(p)["rgba8"][..., :3]
+    u25 = np.zeros(25, np.float32)
+    wh = (C.c_int32 * 2)()
+    assert abi.load().rtb_resolve_frame(holder.ptr(), C.byref(p), u25.ctypes.data_as(C.POINTER(C.c_float)), wh) == abi.RTB_OK
+    tri18, mat_idx, _ = osc.triangles()
+    got = _render64_fx(tri18, mat_idx, obj.Materials, u25, w, h, depth, aa, **fx)
+    diff = np.abs(got.astype(np.int32) - ref.astype(np.int32)).max(-1)
+    assert (diff <= 1).mean() >= 0.99, f"{kw}: {(diff <= 1).mean() * 100:.2f}% within 1/255, worst {int(diff.max())}"
+    plain = osc.render(params(w, h, depth, aa))["rgba8"][..., :3]
+    assert (plain != ref).any(axis=-1).mean() > 0.02, "the setting changes nothing: not a test"
 
 
 @pytest.mark.parametrize("w,h,depth", [(64, 48, 3), (96, 72, 6)])
