@@ -622,7 +622,7 @@ def test_distribution_effects_against_float64(pkg, oracle, kw, fx):
     all four frames identical, byte for byte.)"""
     obj = synth.sample_scene("test_scene_1")
     osc, holder = oracle_scene(oracle, obj)
-    w, h, depth, aa = 44, 32, 4, 4
+    w, h, depth, aa = 36, 26, 4, 4
     p = params(w, h, depth, aa, **kw)
     ref = osc.render(p)["rgba8"][..., :3]
     u25 = np.zeros(25, np.float32)
@@ -656,7 +656,7 @@ def test_render_settings_against_float64(pkg, oracle, kw, fx):
     (:421).  Tolerance as for the whole-frame check: 99 % of the pixels within 1/255."""
     obj = synth.sample_scene("test_scene_1")
     osc, holder = oracle_scene(oracle, obj)
-    w, h, depth = 56, 40, 4
+    w, h, depth = 44, 32, 4
     aa = kw.get("aa_samples", 1)
     p = params(w, h, depth, aa, **{k: v for k, v in kw.items() if k != "aa_samples"})
     ref = osc.render(p)["rgba8"][..., :3]
