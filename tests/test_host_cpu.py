@@ -101,11 +101,12 @@ def test_oracle_reaches_c3_at_full_size(oracle):
         plain_scene = oracle.OracleScene.from_desc(packed.desc)
     finally:
         oracle.set_leaf_accel(prev)
-    pl = params(3840, 2160, 2)  # depth 2 keeps the plain scan within the CPU suite's budget
-    a = plain_scene.render(pl, rows=(1000, 1001, 1), want_aux=True)
-    b = osc.render(pl, rows=(1000, 1001, 1), want_aux=True)
-    assert (a["rgba8"][1000] == b["rgba8"][1000]).all() and (a["prim"][1000] == b["prim"][1000]).all()
-    assert (a["t"][1000].view(np.uint32) == b["t"][1000].view(np.uint32)).all()
+    pl = params(1280, 720, 2)  # a 720p row at depth 2 keeps the plain scan (98 310 triangle tests per node visit) within the CPU suite's budget
+    a = plain_scene.render(pl, rows=(333, 334, 1), want_aux=True)
+    b = osc.render(pl, rows=(333, 334, 1), want_aux=True)
+    assert (a["rgba8"][333] == b["rgba8"][333]).all() and (a["prim"][333] == b["prim"][333]).all()
+    assert (a["t"][333].view(np.uint32) == b["t"][333].view(np.uint32)).all()
+    assert (a["prim"][333] >= 0).mean() > 0.3  # the row crosses the sphere grid
 
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE_SCENES), reason="reference tree only exists in the build container")
